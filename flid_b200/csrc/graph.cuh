@@ -1,0 +1,39 @@
+// Device-resident temporal adjacency: CSR over nodes, time-sorted inside each node.
+#pragma once
+#include "common.cuh"
+
+struct flid_graph {
+    int64_t num_nodes = 0;    // largest valid node id
+    int64_t num_entries = 0;  // 2 * events
+    int64_t max_degree = 0;
+    int64_t* indptr = nullptr;  // [num_nodes + 2]
+    int2* adj = nullptr;        // [M] (.x = neighbour id, .y = edge id)
+    double* ts = nullptr;       // [M]
+};
+
+namespace flid {
+
+#ifdef __CUDACC__
+// Warp-cooperative searchsorted(ts[lo:hi), t, side='left'): first position whose
+// timestamp is >= t.  32 probes per round, so ceil(log32(deg)) + 1 dependent loads.
+__device__ __forceinline__ int64_t warp_lower_bound(const double* __restrict__ ts, int64_t lo, int64_t hi, double t,
+                                                    int lane) {
+    while (lo < hi) {
+        const int64_t len = hi - lo;
+        const int64_t stride = (len + 31) >> 5;
+        const int64_t p = lo + (int64_t)lane * stride;
+        const bool before = (p < hi) && (__ldg(ts + p) < t);
+        const int c = __popc(__ballot_sync(FULL, before));
+        if (c == 0) {
+            hi = lo;
+        } else {
+            const int64_t first_false = lo + (int64_t)c * stride;
+            lo = lo + (int64_t)(c - 1) * stride + 1;
+            hi = first_false < hi ? first_false : hi;
+        }
+    }
+    return lo;
+}
+#endif
+
+}  // namespace flid

@@ -1,0 +1,661 @@
+// TGAT temporal-embedding path (models/TGAT.py:50-144, models/modules.py:7-69,126-245),
+// eval mode, re-associated so that the per-neighbour work is a pure streaming pass:
+//
+//   scores_h[j] = scale * (Wq_h q)^T (Wk_h x_j)  =  x_j . u_h ,  u_h = (scale Wk_h^T Wq_h) q
+//   out         = Wr [ Wv_h sum_j a_hj x_j ]_h + br = sum_h (Wr_h Wv_h) z_h + br , z_h = sum_j a_hj x_j
+//
+// with q = [h_self | te(0)], x_j = [h_nbr_j | e_j | te(dt_j)].  Per attention evaluation
+// the kernels are: level_sample (index work) -> [u GEMM] -> attn (gather + cos time
+// encoding + masked online softmax + weighted sum; HBM-bound) -> out GEMM -> LayerNorm
+// -> MergeLayer GEMMs.  This file holds the fp32 reference-parity mode.
+#include "tgat.cuh"
+
+#include <math.h>
+
+#include <algorithm>
+
+#include "gemm.cuh"
+
+namespace flid {
+
+// ------------------------------------------------------------------ weight folding
+__global__ void fold_qk_kernel(const float* __restrict__ wq, const float* __restrict__ wk, int qd, int kd, int H,
+                               float scale, float* __restrict__ mfoldT) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)H * kd * qd) return;
+    const int row = (int)(idx / qd), b = (int)(idx % qd), h = row / kd, a = row % kd, hd = qd / H;
+    double s = 0.0;
+    for (int r = 0; r < hd; ++r) s += (double)wk[(int64_t)(h * hd + r) * kd + a] * (double)wq[(int64_t)(h * hd + r) * qd + b];
+    mfoldT[idx] = (float)(s * (double)scale);
+}
+
+__global__ void fold_vo_kernel(const float* __restrict__ wr, const float* __restrict__ wv, int qd, int kd, int H,
+                               float* __restrict__ wvoT) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int zw = H * kd;
+    if (idx >= (int64_t)qd * zw) return;
+    const int o = (int)(idx / zw), c = (int)(idx % zw), h = c / kd, a = c % kd, hd = qd / H;
+    double s = 0.0;
+    for (int r = 0; r < hd; ++r) s += (double)wr[(int64_t)o * qd + h * hd + r] * (double)wv[(int64_t)(h * hd + r) * kd + a];
+    wvoT[idx] = (float)s;
+}
+
+__global__ void te0_kernel(const float* __restrict__ w, const float* __restrict__ b, int T, float* __restrict__ te0) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < T) te0[c] = time_channel(0.f, w[c], b[c]);
+}
+
+__global__ void u0_kernel(const float* __restrict__ mfoldT, const float* __restrict__ te0, int zw, int qd, int dn,
+                          int T, float* __restrict__ u0) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= zw) return;
+    float s = 0.f;
+    for (int c = 0; c < T; ++c) s = fmaf(te0[c], mfoldT[(int64_t)row * qd + dn + c], s);
+    u0[row] = s;
+}
+
+// ------------------------------------------------------------------ root conversion
+__global__ void roots_kernel(const int64_t* __restrict__ nodes, const double* __restrict__ times, int64_t n,
+                             int64_t num_nodes, int32_t* __restrict__ ids, double* __restrict__ t_out,
+                             int* __restrict__ bad) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int64_t v = nodes[i];
+    if (v < 0 || v > num_nodes) {
+        atomicExch(bad, 1);
+        v = 0;
+    }
+    ids[i] = (int32_t)v;
+    t_out[i] = times[i];
+}
+
+// ------------------------------------------------------------------ level sampler
+// get_historical_neighbors('recent') for one recursion level, in the layout the layer
+// kernels consume: int32 ids, float32 dt (with the reference's dtype rule: float64
+// subtraction for the first n_f64 targets, float32 below; models/TGAT.py:120-125), and
+// the next (lower) level's target list [self targets ; neighbour targets].
+__global__ void __launch_bounds__(256) level_sample_kernel(
+    const int64_t* __restrict__ indptr, const int2* __restrict__ adj, const double* __restrict__ ts,
+    const int32_t* __restrict__ ids, const double* __restrict__ times, int64_t n, int64_t n_f64, int k,
+    int32_t* __restrict__ nbr, int32_t* __restrict__ eid, float* __restrict__ dt, int32_t* __restrict__ next_ids,
+    double* __restrict__ next_times, unsigned long long* __restrict__ valid_slots) {
+    __shared__ int s_cnt;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t q = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (q < n) {
+        const int32_t v = __ldg(ids + q);
+        const double t = __ldg(times + q);
+        const int64_t start = __ldg(indptr + v);
+        const int64_t cut = warp_lower_bound(ts, start, __ldg(indptr + v + 1), t, lane);
+        const int64_t have = cut - start;
+        const int cnt = have < (int64_t)k ? (int)have : k;
+        if (next_ids && lane == 0) next_ids[q] = v, next_times[q] = t;
+        const bool f64_rule = q < n_f64;
+        const float tf = (float)t;
+        for (int j = lane; j < k; j += 32) {
+            int a = 0, e = 0;
+            float tsf = 0.f;
+            if (j >= k - cnt) {
+                const int64_t p = cut - k + j;
+                const int2 ne = __ldg(adj + p);
+                a = ne.x, e = ne.y, tsf = (float)__ldg(ts + p);
+            }
+            const float d = f64_rule ? (float)(t - (double)tsf) : (tf - tsf);
+            const int64_t o = q * k + j;
+            nbr[o] = a, eid[o] = e, dt[o] = d;
+            if (next_ids) next_ids[n + o] = a, next_times[n + o] = (double)tsf;
+        }
+        if (lane == 0) atomicAdd(&s_cnt, cnt);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_cnt) atomicAdd(valid_slots, (unsigned long long)s_cnt);
+}
+
+// ------------------------------------------------------------------ attention stream
+struct AttnArgs {
+    const float* u_base;      // query folds, row stride zw
+    const int32_t* u_index;   // nullable: u row of target i is u_base[u_index[i]] (per-node table) else row i
+    const float* hrow_base;   // neighbour layer-(l-1) rows, row stride dn
+    int hrow_by_id;           // 1: row = neighbour id (feature table); 0: row = hrow_offset + i*k + j
+    int64_t hrow_offset;
+    const float* edge_feat;   // [E+1, de]
+    const int32_t* nbr;       // [n, k]
+    const int32_t* eid;
+    const float* dt;
+    const float* time_w;
+    const float* time_b;
+    float* z;                 // [n, zw]
+    int64_t n;
+    int k, dn, de, T;
+};
+
+// One warp per target.  Lane l owns float4 chunks l, l+32, ... of the concatenated
+// [node row | edge row] and time channels l, l+32, ...; u and the z accumulators live in
+// registers; neighbour rows stream through registers once (online softmax), the next
+// slot's row is in flight while the current one is reduced.
+template <int H, int NV, int TC>
+__global__ void __launch_bounds__(256) attn_kernel(AttnArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (i >= a.n) return;
+    const int k = a.k, dn = a.dn, de = a.de, T = a.T;
+    const int nv4 = dn >> 2, tot4 = (dn + de) >> 2, kd = dn + de + T;
+
+    int nb_l = 0, e_l = 0;
+    float dt_l = 0.f;
+    if (lane < k) {
+        nb_l = __ldg(a.nbr + i * k + lane);
+        e_l = __ldg(a.eid + i * k + lane);
+        dt_l = __ldg(a.dt + i * k + lane);
+    }
+    const unsigned valid = __ballot_sync(FULL, lane < k && nb_l != 0);
+    const bool all_masked = (valid == 0u);  // softmax over k equal -1e10 scores == uniform 1/k
+    unsigned todo = all_masked ? (k >= 32 ? FULL : ((1u << k) - 1u)) : valid;
+
+    const float* u = a.u_base + (a.u_index ? (int64_t)__ldg(a.u_index + i) : i) * (int64_t)(H * kd);
+    float4 uh[H][NV];
+    float ut[H][TC], tw[TC], tb[TC];
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+#pragma unroll
+        for (int r = 0; r < NV; ++r) {
+            const int f = lane + 32 * r;
+            uh[h][r] = f < tot4 ? __ldg(reinterpret_cast<const float4*>(u + h * kd) + f) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int r = 0; r < TC; ++r) {
+            const int c = lane + 32 * r;
+            ut[h][r] = c < T ? __ldg(u + h * kd + dn + de + c) : 0.f;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < TC; ++r) {
+        const int c = lane + 32 * r;
+        tw[r] = c < T ? __ldg(a.time_w + c) : 0.f;
+        tb[r] = c < T ? __ldg(a.time_b + c) : 0.f;
+    }
+
+    float4 acc[H][NV];
+    float acct[H][TC], mx[H], den[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+        mx[h] = -INFINITY, den[h] = 0.f;
+#pragma unroll
+        for (int r = 0; r < NV; ++r) acc[h][r] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < TC; ++r) acct[h][r] = 0.f;
+    }
+
+    auto load_slot = [&](int j, float4 (&x)[NV]) {
+        const int nb = __shfl_sync(FULL, nb_l, j);
+        const int e = __shfl_sync(FULL, e_l, j);
+        const float* hrow = a.hrow_base + (a.hrow_by_id ? (int64_t)nb : a.hrow_offset + i * k + j) * (int64_t)dn;
+        const float* erow = a.edge_feat + (int64_t)e * de;
+#pragma unroll
+        for (int r = 0; r < NV; ++r) {
+            const int f = lane + 32 * r;
+            if (f < nv4)
+                x[r] = __ldg(reinterpret_cast<const float4*>(hrow) + f);
+            else if (f < tot4)
+                x[r] = __ldg(reinterpret_cast<const float4*>(erow) + (f - nv4));
+            else
+                x[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+
+    float4 xc[NV], xn[NV];
+    int j = __ffs(todo) - 1;
+    todo &= todo - 1;
+    load_slot(j, xc);
+    while (true) {
+        int jn = -1;
+        if (todo) {
+            jn = __ffs(todo) - 1;
+            todo &= todo - 1;
+            load_slot(jn, xn);
+        }
+        const float d = __shfl_sync(FULL, dt_l, j);
+        float xt[TC];
+#pragma unroll
+        for (int r = 0; r < TC; ++r) xt[r] = (lane + 32 * r < T) ? time_channel(d, tw[r], tb[r]) : 0.f;
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            float s = -1e10f;  // masked_fill value (models/modules.py:220)
+            if (!all_masked) {
+                float p = 0.f;
+#pragma unroll
+                for (int r = 0; r < NV; ++r) {
+                    p = fmaf(xc[r].x, uh[h][r].x, p);
+                    p = fmaf(xc[r].y, uh[h][r].y, p);
+                    p = fmaf(xc[r].z, uh[h][r].z, p);
+                    p = fmaf(xc[r].w, uh[h][r].w, p);
+                }
+#pragma unroll
+                for (int r = 0; r < TC; ++r) p = fmaf(xt[r], ut[h][r], p);
+                s = warp_sum(p);
+            }
+            const float mnew = fmaxf(mx[h], s);
+            const float corr = expf(mx[h] - mnew);
+            const float w = expf(s - mnew);
+            mx[h] = mnew;
+            den[h] = fmaf(den[h], corr, w);
+#pragma unroll
+            for (int r = 0; r < NV; ++r) {
+                acc[h][r].x = fmaf(acc[h][r].x, corr, w * xc[r].x);
+                acc[h][r].y = fmaf(acc[h][r].y, corr, w * xc[r].y);
+                acc[h][r].z = fmaf(acc[h][r].z, corr, w * xc[r].z);
+                acc[h][r].w = fmaf(acc[h][r].w, corr, w * xc[r].w);
+            }
+#pragma unroll
+            for (int r = 0; r < TC; ++r) acct[h][r] = fmaf(acct[h][r], corr, w * xt[r]);
+        }
+        if (jn < 0) break;
+#pragma unroll
+        for (int r = 0; r < NV; ++r) xc[r] = xn[r];
+        j = jn;
+    }
+
+    float* z = a.z + i * (int64_t)(H * kd);
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+        const float inv = 1.0f / den[h];
+#pragma unroll
+        for (int r = 0; r < NV; ++r) {
+            const int f = lane + 32 * r;
+            if (f < tot4)
+                reinterpret_cast<float4*>(z + h * kd)[f] =
+                    make_float4(acc[h][r].x * inv, acc[h][r].y * inv, acc[h][r].z * inv, acc[h][r].w * inv);
+        }
+#pragma unroll
+        for (int r = 0; r < TC; ++r) {
+            const int c = lane + 32 * r;
+            if (c < T) z[h * kd + dn + de + c] = acct[h][r] * inv;
+        }
+    }
+}
+
+template <int H>
+static int launch_attn_h(const AttnArgs& a, int nv, int tc, cudaStream_t st) {
+    const unsigned blocks = (unsigned)ceil_div(a.n * 32, 256);
+#define FLID_ATTN_CASE(NV_, TC_)                              \
+    if (nv <= NV_ && tc <= TC_) {                             \
+        attn_kernel<H, NV_, TC_><<<blocks, 256, 0, st>>>(a);  \
+        FLID_LAUNCH_CHECK();                                  \
+        return FLID_OK;                                       \
+    }
+    FLID_ATTN_CASE(3, 4)
+    FLID_ATTN_CASE(6, 4)
+#undef FLID_ATTN_CASE
+    set_error("attention kernel: unsupported feature widths (node+edge floats <= 768, time dim <= 128)");
+    return FLID_ERR_INVALID;
+}
+
+static int launch_attn(const AttnArgs& a, int H, cudaStream_t st) {
+    if (a.n <= 0) return FLID_OK;
+    const int nv = (int)ceil_div((a.dn + a.de) / 4, 32), tc = (int)ceil_div(a.T, 32);
+    switch (H) {
+        case 1: return launch_attn_h<1>(a, nv, tc, st);
+        case 2: return launch_attn_h<2>(a, nv, tc, st);
+        case 4: return launch_attn_h<4>(a, nv, tc, st);
+        default: set_error("attention kernel: num_heads must be 1, 2 or 4 (got %d)", H); return FLID_ERR_INVALID;
+    }
+}
+
+// ------------------------------------------------------------------ residual + LayerNorm
+// out = LayerNorm(O + [h_self | te0])   (models/modules.py:235-238; O already holds
+// residual_fc's output incl. bias).  One warp per row.
+__global__ void __launch_bounds__(256) ln_kernel(const float* __restrict__ O, const float* __restrict__ self_base,
+                                                 const int32_t* __restrict__ self_idx, const float* __restrict__ te0,
+                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                 float* __restrict__ A, int64_t n, int dn, int T) {
+    constexpr int MAXR = 16;
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (i >= n) return;
+    const int qd = dn + T;
+    const float* self = self_base + (self_idx ? (int64_t)__ldg(self_idx + i) : i) * (int64_t)dn;
+    float x[MAXR];
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < MAXR; ++r) {
+        const int c = lane + 32 * r;
+        x[r] = 0.f;
+        if (c < qd) {
+            x[r] = O[i * qd + c] + (c < dn ? __ldg(self + c) : __ldg(te0 + (c - dn)));
+            s += x[r];
+        }
+    }
+    const float mean = warp_sum(s) / (float)qd;
+    float v = 0.f;
+#pragma unroll
+    for (int r = 0; r < MAXR; ++r) {
+        const int c = lane + 32 * r;
+        if (c < qd) {
+            const float d = x[r] - mean;
+            v = fmaf(d, d, v);
+        }
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(v) / (float)qd + 1e-5f);
+#pragma unroll
+    for (int r = 0; r < MAXR; ++r) {
+        const int c = lane + 32 * r;
+        if (c < qd) A[i * qd + c] = fmaf((x[r] - mean) * rstd, __ldg(gamma + c), __ldg(beta + c));
+    }
+}
+
+// ------------------------------------------------------------------ host pipeline
+static int dev_copy(float** dst, const float* src, size_t count, cudaStream_t st) {
+    if (!*dst) FLID_CUDA(cudaMalloc((void**)dst, count * sizeof(float)));
+    FLID_CUDA(cudaMemcpyAsync(*dst, src, count * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return FLID_OK;
+}
+
+// u rows for `n` rows of a feature table: U = feat[idx] . mfoldT[:, :dn]^T + u0
+static int query_fold(flid_tgat* m, int layer, const float* feat, const int32_t* idx, int64_t n, float* U,
+                      cudaStream_t st) {
+    const LayerDev& ld = m->layers[layer];
+    GemmArgs g{feat, m->dn, idx, ld.mfoldT, m->qd, U, m->zw, ld.u0, n, m->zw, m->dn, 0, 0};
+    return launch_gemm(g, st);
+}
+
+// everything after the attention stream for one level: out-projection(+residual_fc) ->
+// +residual -> LayerNorm -> MergeLayer.  self rows: layer-(l-1) features of the targets.
+static int output_chain(flid_tgat* m, int layer, int64_t n, const float* Z, const float* self_base,
+                        const int32_t* self_idx, const float* merge_feat, const int32_t* ids, float* O, float* A,
+                        float* Hd, float* out, cudaStream_t st) {
+    const LayerDev& ld = m->layers[layer];
+    GemmArgs g1{Z, m->zw, nullptr, ld.wvoT, m->zw, O, m->qd, ld.res_b, n, m->qd, m->zw, 0, 0};
+    FLID_TRY(launch_gemm(g1, st));
+    ln_kernel<<<(unsigned)ceil_div(n * 32, 256), 256, 0, st>>>(O, self_base, self_idx, m->te0, ld.ln_w, ld.ln_b, A, n,
+                                                               m->dn, m->T);
+    FLID_LAUNCH_CHECK();
+    const int64_t ld1 = m->qd + m->dn;
+    GemmArgs g2{A, m->qd, nullptr, ld.fc1_w, ld1, Hd, m->dn, nullptr, n, m->dn, m->qd, 0, 0};
+    FLID_TRY(launch_gemm(g2, st));
+    GemmArgs g3{merge_feat, m->dn, ids, ld.fc1_w + m->qd, ld1, Hd, m->dn, ld.fc1_b, n, m->dn, m->dn, 1, 1};
+    FLID_TRY(launch_gemm(g3, st));
+    GemmArgs g4{Hd, m->dn, nullptr, ld.fc2_w, m->dn, out, m->dn, ld.fc2_b, n, m->dn, m->dn, 0, 0};
+    return launch_gemm(g4, st);
+}
+
+int tgat_embed_ids(flid_tgat* m, const flid_graph* g, const float* node_feat, const float* edge_feat,
+                   const int32_t* ids, const double* times, int64_t n_f64, int64_t n, int k, float* out,
+                   cudaStream_t st) {
+    const int L = m->L;
+    // roots per chunk so that the widest level (level 1) stays below max_l1_targets
+    int64_t fan = 1;
+    for (int l = 1; l < L; ++l) fan *= (1 + k);
+    const int64_t chunk = std::max<int64_t>(1, m->max_l1_targets / fan);
+    const int64_t nc_max = std::min(chunk, n);
+    // level sizes / offsets for a full chunk (level L first)
+    std::vector<int64_t> cnt(L + 1), off(L + 1);
+    int64_t total = 0;
+    cnt[L] = nc_max;
+    for (int l = L; l >= 1; --l) {
+        off[l] = total;
+        total += cnt[l];
+        if (l > 1) cnt[l - 1] = cnt[l] * (1 + k);
+    }
+    const int64_t n1 = cnt[1];
+    FLID_TRY(m->ws_ids.reserve(sizeof(int32_t) * total));
+    FLID_TRY(m->ws_times.reserve(sizeof(double) * total));
+    FLID_TRY(m->ws_nbr.reserve(sizeof(int32_t) * total * k));
+    FLID_TRY(m->ws_eid.reserve(sizeof(int32_t) * total * k));
+    FLID_TRY(m->ws_dt.reserve(sizeof(float) * total * k));
+    FLID_TRY(m->ws_h.reserve(sizeof(float) * (total - cnt[L] + 1) * m->dn));
+    const bool use_table = (m->table_src == node_feat && m->table_rows > 0);
+    FLID_TRY(m->ws_u.reserve(sizeof(float) * (use_table ? (L > 1 ? cnt[2] : 1) : n1) * m->zw));
+    FLID_TRY(m->ws_z.reserve(sizeof(float) * n1 * m->zw));
+    FLID_TRY(m->ws_o.reserve(sizeof(float) * n1 * m->qd));
+    FLID_TRY(m->ws_a.reserve(sizeof(float) * n1 * m->qd));
+    FLID_TRY(m->ws_hd.reserve(sizeof(float) * n1 * m->dn));
+    FLID_TRY(m->ws_misc.reserve(64));
+    unsigned long long* d_valid = m->ws_misc.as<unsigned long long>();
+    FLID_CUDA(cudaMemsetAsync(d_valid, 0, sizeof(unsigned long long), st));
+
+    int32_t* w_ids = m->ws_ids.as<int32_t>();
+    double* w_times = m->ws_times.as<double>();
+    int32_t* w_nbr = m->ws_nbr.as<int32_t>();
+    int32_t* w_eid = m->ws_eid.as<int32_t>();
+    float* w_dt = m->ws_dt.as<float>();
+    float* w_h = m->ws_h.as<float>();
+    float *U = m->ws_u.as<float>(), *Z = m->ws_z.as<float>(), *O = m->ws_o.as<float>(), *A = m->ws_a.as<float>(),
+          *Hd = m->ws_hd.as<float>();
+
+    int64_t evals = 0, queries = 0;
+    for (int64_t r0 = 0; r0 < n; r0 += chunk) {
+        const int64_t nc = std::min(chunk, n - r0);
+        std::vector<int64_t> c(L + 1), o(L + 1), ho(L + 1);
+        int64_t tot = 0, htot = 0;
+        c[L] = nc;
+        for (int l = L; l >= 1; --l) {
+            o[l] = tot;
+            tot += c[l];
+            if (l > 1) c[l - 1] = c[l] * (1 + k);
+        }
+        for (int l = L - 1; l >= 1; --l) ho[l] = htot, htot += c[l];  // H_l buffers, l < L
+        const int64_t nf = std::max<int64_t>(0, std::min(nc, n_f64 - r0));
+        // level L targets = this chunk of roots
+        FLID_CUDA(cudaMemcpyAsync(w_ids + o[L], ids + r0, sizeof(int32_t) * nc, cudaMemcpyDeviceToDevice, st));
+        FLID_CUDA(cudaMemcpyAsync(w_times + o[L], times + r0, sizeof(double) * nc, cudaMemcpyDeviceToDevice, st));
+        // top-down sampling
+        for (int l = L; l >= 1; --l) {
+            level_sample_kernel<<<(unsigned)ceil_div(c[l] * 32, 256), 256, 0, st>>>(
+                g->indptr, g->adj, g->ts, w_ids + o[l], w_times + o[l], c[l], nf, k, w_nbr + o[l] * k,
+                w_eid + o[l] * k, w_dt + o[l] * k, l > 1 ? w_ids + o[l - 1] : nullptr,
+                l > 1 ? w_times + o[l - 1] : nullptr, d_valid);
+            FLID_LAUNCH_CHECK();
+            queries += c[l];
+        }
+        // bottom-up layers
+        for (int l = 1; l <= L; ++l) {
+            const int64_t nl = c[l];
+            const int32_t* lids = w_ids + o[l];
+            AttnArgs a;
+            a.edge_feat = edge_feat;
+            a.nbr = w_nbr + o[l] * k, a.eid = w_eid + o[l] * k, a.dt = w_dt + o[l] * k;
+            a.time_w = m->time_w, a.time_b = m->time_b;
+            a.z = Z, a.n = nl, a.k = k, a.dn = m->dn, a.de = m->de, a.T = m->T;
+            const float* self_base;
+            const int32_t* self_idx;
+            if (l == 1) {
+                if (use_table) {
+                    a.u_base = m->table.as<float>(), a.u_index = lids;
+                } else {
+                    FLID_TRY(query_fold(m, 0, node_feat, lids, nl, U, st));
+                    a.u_base = U, a.u_index = nullptr;
+                }
+                a.hrow_base = node_feat, a.hrow_by_id = 1, a.hrow_offset = 0;
+                self_base = node_feat, self_idx = lids;
+            } else {
+                const float* hprev = w_h + ho[l - 1] * m->dn;  // [c[l-1], dn]: first nl rows = self, then nl*k nbr rows
+                FLID_TRY(query_fold(m, l - 1, hprev, nullptr, nl, U, st));
+                a.u_base = U, a.u_index = nullptr;
+                a.hrow_base = hprev, a.hrow_by_id = 0, a.hrow_offset = nl;
+                self_base = hprev, self_idx = nullptr;
+            }
+            FLID_TRY(launch_attn(a, m->H, st));
+            float* dst = (l == L) ? out + r0 * m->dn : w_h + ho[l] * m->dn;
+            FLID_TRY(output_chain(m, l - 1, nl, Z, self_base, self_idx, node_feat, lids, O, A, Hd, dst, st));
+            evals += nl;
+        }
+    }
+    m->stats[0] = evals;
+    m->stats[2] = queries;
+    m->stats[1] = -1;  // fetched lazily by flid_tgat_last_stats
+    return FLID_OK;
+}
+
+}  // namespace flid
+
+// ====================================================================== C ABI
+extern "C" {
+
+int flid_tgat_create(int node_dim, int edge_dim, int time_dim, int num_layers, int num_heads, flid_tgat** out) {
+    using namespace flid;
+    FLID_REQUIRE(out != nullptr, "flid_tgat_create: out is null");
+    FLID_REQUIRE(node_dim > 0 && edge_dim > 0 && time_dim > 0 && num_layers > 0 && num_heads > 0,
+                 "flid_tgat_create: dims must be positive");
+    FLID_REQUIRE(node_dim % 4 == 0 && edge_dim % 4 == 0 && time_dim % 4 == 0,
+                 "flid_tgat_create: node/edge/time dims must be multiples of 4 (16-byte rows)");
+    // the reference's own assertion (models/modules.py:149)
+    FLID_REQUIRE((node_dim + time_dim) % num_heads == 0,
+                 "The sum of node_feat_dim and time_feat_dim should be divided by num_heads!");
+    FLID_REQUIRE(num_heads == 1 || num_heads == 2 || num_heads == 4, "flid_tgat_create: num_heads must be 1, 2 or 4");
+    FLID_REQUIRE(node_dim + edge_dim <= 768 && time_dim <= 128 && node_dim + time_dim <= 512,
+                 "flid_tgat_create: feature widths above kernel limits");
+    flid_tgat* m = new flid_tgat();
+    m->dn = node_dim, m->de = edge_dim, m->T = time_dim, m->L = num_layers, m->H = num_heads;
+    m->qd = node_dim + time_dim, m->kd = node_dim + edge_dim + time_dim, m->hd = m->qd / num_heads;
+    m->zw = num_heads * m->kd;
+    m->layers.resize(num_layers);
+    *out = m;
+    return FLID_OK;
+}
+
+void flid_tgat_free(flid_tgat* m) {
+    if (!m) return;
+    cudaFree(m->time_w), cudaFree(m->time_b), cudaFree(m->te0);
+    for (auto& l : m->layers) {
+        cudaFree(l.mfoldT), cudaFree(l.u0), cudaFree(l.wvoT), cudaFree(l.res_b), cudaFree(l.ln_w), cudaFree(l.ln_b);
+        cudaFree(l.fc1_w), cudaFree(l.fc1_b), cudaFree(l.fc2_w), cudaFree(l.fc2_b);
+    }
+    flid::DevBuf* bufs[] = {&m->raw_q, &m->raw_k, &m->raw_v, &m->raw_r, &m->table, &m->ws_ids, &m->ws_times,
+                            &m->ws_nbr, &m->ws_eid, &m->ws_dt, &m->ws_h, &m->ws_u, &m->ws_z, &m->ws_o,
+                            &m->ws_a, &m->ws_hd, &m->ws_misc, &m->ws_rid, &m->ws_rt, &m->ws_bad};
+    for (auto* b : bufs) b->release();
+    delete m;
+}
+
+int flid_tgat_set_weights(flid_tgat* m, const float* time_w, const float* time_b,
+                          const flid_tgat_layer_weights* layers_host, flid_stream stream) {
+    using namespace flid;
+    FLID_REQUIRE(m && time_w && time_b && layers_host, "flid_tgat_set_weights: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int qd = m->qd, kd = m->kd, dn = m->dn, T = m->T, H = m->H, zw = m->zw;
+    FLID_TRY(dev_copy(&m->time_w, time_w, T, st));
+    FLID_TRY(dev_copy(&m->time_b, time_b, T, st));
+    if (!m->te0) FLID_CUDA(cudaMalloc((void**)&m->te0, sizeof(float) * T));
+    te0_kernel<<<(unsigned)ceil_div(T, 128), 128, 0, st>>>(m->time_w, m->time_b, T, m->te0);
+    FLID_LAUNCH_CHECK();
+    // python: head_dim ** -0.5 is a float64; multiplying a float32 tensor by it uses its float32 value
+    const float scale = (float)pow((double)m->hd, -0.5);
+    for (int l = 0; l < m->L; ++l) {
+        const flid_tgat_layer_weights& w = layers_host[l];
+        LayerDev& d = m->layers[l];
+        FLID_REQUIRE(w.query_w && w.key_w && w.value_w && w.ln_w && w.ln_b && w.res_w && w.res_b && w.fc1_w &&
+                         w.fc1_b && w.fc2_w && w.fc2_b,
+                     "flid_tgat_set_weights: layer %d has a null weight pointer", l);
+        if (!d.mfoldT) FLID_CUDA(cudaMalloc((void**)&d.mfoldT, sizeof(float) * (size_t)zw * qd));
+        if (!d.wvoT) FLID_CUDA(cudaMalloc((void**)&d.wvoT, sizeof(float) * (size_t)zw * qd));
+        if (!d.u0) FLID_CUDA(cudaMalloc((void**)&d.u0, sizeof(float) * zw));
+        const int64_t tot = (int64_t)zw * qd;
+        fold_qk_kernel<<<(unsigned)ceil_div(tot, 256), 256, 0, st>>>(w.query_w, w.key_w, qd, kd, H, scale, d.mfoldT);
+        FLID_LAUNCH_CHECK();
+        fold_vo_kernel<<<(unsigned)ceil_div(tot, 256), 256, 0, st>>>(w.res_w, w.value_w, qd, kd, H, d.wvoT);
+        FLID_LAUNCH_CHECK();
+        u0_kernel<<<(unsigned)ceil_div(zw, 128), 128, 0, st>>>(d.mfoldT, m->te0, zw, qd, dn, T, d.u0);
+        FLID_LAUNCH_CHECK();
+        FLID_TRY(dev_copy(&d.res_b, w.res_b, qd, st));
+        FLID_TRY(dev_copy(&d.ln_w, w.ln_w, qd, st));
+        FLID_TRY(dev_copy(&d.ln_b, w.ln_b, qd, st));
+        FLID_TRY(dev_copy(&d.fc1_w, w.fc1_w, (size_t)dn * (qd + dn), st));
+        FLID_TRY(dev_copy(&d.fc1_b, w.fc1_b, dn, st));
+        FLID_TRY(dev_copy(&d.fc2_w, w.fc2_w, (size_t)dn * dn, st));
+        FLID_TRY(dev_copy(&d.fc2_b, w.fc2_b, dn, st));
+    }
+    m->have_weights = true;
+    m->table_src = nullptr;  // cached query folds are stale now
+    m->table_rows = 0;
+    return FLID_OK;
+}
+
+int flid_tgat_cache_node_table(flid_tgat* m, const float* node_feat, int64_t rows, flid_stream stream) {
+    using namespace flid;
+    FLID_REQUIRE(m && node_feat && rows > 0, "flid_tgat_cache_node_table: bad argument");
+    FLID_REQUIRE(m->have_weights, "flid_tgat_cache_node_table: weights not set");
+    FLID_TRY(m->table.reserve(sizeof(float) * (size_t)rows * m->zw));
+    FLID_TRY(query_fold(m, 0, node_feat, nullptr, rows, m->table.as<float>(), (cudaStream_t)stream));
+    m->table_src = node_feat;
+    m->table_rows = rows;
+    return FLID_OK;
+}
+
+__global__ void scatter_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ ids, int64_t n, int w,
+                                    float* __restrict__ table) {
+    const int64_t i = blockIdx.x;
+    for (int c = threadIdx.x; c < w; c += blockDim.x) table[(int64_t)ids[i] * w + c] = src[i * w + c];
+}
+
+int flid_tgat_refresh_node_rows(flid_tgat* m, const float* node_feat, const int32_t* row_ids, int64_t n,
+                                flid_stream stream) {
+    using namespace flid;
+    FLID_REQUIRE(m && node_feat && row_ids, "flid_tgat_refresh_node_rows: null argument");
+    FLID_REQUIRE(m->table_src == node_feat && m->table_rows > 0, "flid_tgat_refresh_node_rows: table not cached");
+    if (n <= 0) return FLID_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    FLID_TRY(m->ws_u.reserve(sizeof(float) * (size_t)n * m->zw));
+    FLID_TRY(query_fold(m, 0, node_feat, row_ids, n, m->ws_u.as<float>(), st));
+    scatter_rows_kernel<<<(unsigned)n, 256, 0, st>>>(m->ws_u.as<float>(), row_ids, n, m->zw, m->table.as<float>());
+    FLID_LAUNCH_CHECK();
+    return FLID_OK;
+}
+
+int flid_tgat_embed(flid_tgat* m, const flid_graph* g, const float* node_feat, const float* edge_feat,
+                    const int64_t* nodes, const double* times, int times_are_f32, int64_t n, int k, float* out,
+                    flid_stream stream) {
+    using namespace flid;
+    FLID_REQUIRE(m && g && node_feat && edge_feat, "flid_tgat_embed: null argument");
+    FLID_REQUIRE(m->have_weights, "flid_tgat_embed: weights not set");
+    FLID_REQUIRE(k > 0, "Number of sampled neighbors for each node should be greater than 0!");
+    FLID_REQUIRE(k <= 32, "flid_tgat_embed: num_neighbors above 32 is not supported by the attention kernel");
+    if (n <= 0) return FLID_OK;
+    FLID_REQUIRE(nodes && times && out, "flid_tgat_embed: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    FLID_TRY(m->ws_rid.reserve(sizeof(int32_t) * n));
+    FLID_TRY(m->ws_rt.reserve(sizeof(double) * n));
+    FLID_TRY(m->ws_bad.reserve(sizeof(int)));
+    FLID_CUDA(cudaMemsetAsync(m->ws_bad.p, 0, sizeof(int), st));
+    roots_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(nodes, times, n, g->num_nodes, m->ws_rid.as<int32_t>(),
+                                                            m->ws_rt.as<double>(), m->ws_bad.as<int>());
+    FLID_LAUNCH_CHECK();
+    FLID_TRY(tgat_embed_ids(m, g, node_feat, edge_feat, m->ws_rid.as<int32_t>(), m->ws_rt.as<double>(),
+                            times_are_f32 ? 0 : n, n, k, out, st));
+    // out-of-range ids were clamped to the padding node; report them like the reference's IndexError
+    int hbad = 0;
+    FLID_CUDA(cudaMemcpyAsync(&hbad, m->ws_bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    FLID_CUDA(cudaStreamSynchronize(st));
+    if (hbad) {
+        set_error("flid_tgat_embed: node id outside the graph");
+        return FLID_ERR_RANGE;
+    }
+    return FLID_OK;
+}
+
+int flid_tgat_set_chunk_targets(flid_tgat* m, int64_t max_layer1_targets) {
+    using namespace flid;
+    FLID_REQUIRE(m && max_layer1_targets > 0, "flid_tgat_set_chunk_targets: bad argument");
+    m->max_l1_targets = max_layer1_targets;
+    return FLID_OK;
+}
+
+int flid_tgat_last_stats(const flid_tgat* m, int64_t stats[4]) {
+    using namespace flid;
+    FLID_REQUIRE(m && stats, "flid_tgat_last_stats: null argument");
+    unsigned long long hv = 0;
+    if (m->ws_misc.p) {
+        FLID_CUDA(cudaDeviceSynchronize());
+        FLID_CUDA(cudaMemcpy(&hv, m->ws_misc.p, sizeof(hv), cudaMemcpyDeviceToHost));
+    }
+    stats[0] = m->stats[0], stats[1] = (int64_t)hv, stats[2] = m->stats[2];
+    const flid::DevBuf* bufs[] = {&m->table, &m->ws_ids, &m->ws_times, &m->ws_nbr, &m->ws_eid, &m->ws_dt, &m->ws_h,
+                                  &m->ws_u,  &m->ws_z,   &m->ws_o,     &m->ws_a,   &m->ws_hd};
+    int64_t b = 0;
+    for (auto* x : bufs) b += (int64_t)x->cap;
+    stats[3] = b;
+    return FLID_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,43 @@
+// TGAT handle: folded weights + grow-only workspace.  See DESIGN.md for the algebra.
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+#include "graph.cuh"
+
+namespace flid {
+struct LayerDev {
+    float* mfoldT = nullptr;  // [H*kd, qd]  scale * Wk_h^T Wq_h   (u_h = mfoldT_h . [h_self | te0])
+    float* u0 = nullptr;      // [H*kd]      mfoldT[:, dn:] . te0   (the constant time part of the query)
+    float* wvoT = nullptr;    // [qd, H*kd]  Wr[:, head h] Wv_h     (residual_fc folded into the value projection)
+    float *res_b = nullptr, *ln_w = nullptr, *ln_b = nullptr;              // [qd]
+    float *fc1_w = nullptr, *fc1_b = nullptr, *fc2_w = nullptr, *fc2_b = nullptr;  // merge layer, reference layout
+};
+}  // namespace flid
+
+struct flid_tgat {
+    int dn = 0, de = 0, T = 0, L = 0, H = 0;
+    int qd = 0, kd = 0, hd = 0, zw = 0;  // zw = H * kd
+    bool have_weights = false;
+    float *time_w = nullptr, *time_b = nullptr, *te0 = nullptr;
+    std::vector<flid::LayerDev> layers;
+    flid::DevBuf raw_q, raw_k, raw_v, raw_r;  // staging for the fold
+    // cached layer-1 query fold per node-table row
+    const float* table_src = nullptr;
+    int64_t table_rows = 0;
+    flid::DevBuf table;
+    // workspace
+    int64_t max_l1_targets = 65536;
+    flid::DevBuf ws_ids, ws_times, ws_nbr, ws_eid, ws_dt, ws_h, ws_u, ws_z, ws_o, ws_a, ws_hd, ws_misc;
+    flid::DevBuf ws_rid, ws_rt, ws_bad;  // root conversion staging
+    int64_t stats[4] = {0, 0, 0, 0};
+};
+
+namespace flid {
+// run the full L-layer embedding for n roots given as int32 ids (device) -- shared by the
+// TGAT entry point and the TGN step.
+int tgat_embed_ids(flid_tgat* m, const flid_graph* g, const float* node_feat, const float* edge_feat,
+                   const int32_t* ids, const double* times, int64_t n_f64, int64_t n, int k, float* out,
+                   cudaStream_t st);
+int tgat_workspace_bytes(const flid_tgat* m);
+}  // namespace flid

@@ -1,0 +1,126 @@
+"""Whole-pass drivers: the E/200-iteration Python loops of the reference
+(``PTCL/M_step.py:454-509`` embedding pass, ``PTCL/E_step.py:305-352`` pseudo-label pass,
+``PTCL/utils.py:69-123`` filter) as one call each, plus query sharding across the GPUs of
+one box (graph / features / weights replicated, contiguous event ranges per rank, results
+all-gathered with NCCL -- SURVEY.md section 8(e)).  TGN is sequential in time and is not
+sharded ("replicas only").
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from .pseudo_label import MLPClassifier, emit_pseudo_labels, entropy_filter, prob_filter
+
+
+def shard_bounds(num_items: int, rank: int, world_size: int):
+    """Contiguous, order-preserving split; every rank gets ceil(n / W) items except the tail."""
+    per = -(-num_items // world_size) if num_items else 0
+    lo = min(rank * per, num_items)
+    return lo, min(lo + per, num_items), per
+
+
+def _dist():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist, dist.get_rank(), dist.get_world_size()
+    return None, 0, 1
+
+
+def all_gather_rows(local: torch.Tensor, num_items: int, per: int, dist_mod=None):
+    """Gather row-sharded [<=per, ...] tensors into [num_items, ...] (pads the tail shard)."""
+    dist = dist_mod or _dist()[0]
+    world = dist.get_world_size()
+    pad = per - local.shape[0]
+    if pad:
+        local = torch.cat([local, local.new_zeros((pad,) + tuple(local.shape[1:]))], dim=0)
+    out = local.new_empty((per * world,) + tuple(local.shape[1:]))
+    dist.all_gather_into_tensor(out, local.contiguous())
+    return out[:num_items]
+
+
+def embed_events(model, src_node_ids, dst_node_ids, node_interact_times, num_neighbors: int = 20, sharded=None):
+    """Embeddings of every event's source and destination node at the event time:
+    two float32 [E, dn] device tensors, rows in event order (what the reference's full pass
+    accumulates batch by batch and copies into ``src_node_embeddings`` / ``dst_node_embeddings``).
+    With torch.distributed initialised (or ``sharded=True``) each rank embeds a contiguous
+    event range and the halves are all-gathered."""
+    dist, rank, world = _dist()
+    if sharded is None:
+        sharded = world > 1
+    src = np.asarray(src_node_ids)
+    dst = np.asarray(dst_node_ids)
+    t = np.asarray(node_interact_times)
+    e = len(src)
+    if not sharded or world == 1:
+        with torch.no_grad():
+            return model.compute_src_dst_node_temporal_embeddings(src, dst, t, num_neighbors)
+    lo, hi, per = shard_bounds(e, rank, world)
+    with torch.no_grad():
+        a, b = model.compute_src_dst_node_temporal_embeddings(src[lo:hi], dst[lo:hi], t[lo:hi], num_neighbors)
+    both = torch.stack([a, b], dim=1)                       # [n_local, 2, dn]: one collective for both halves
+    full = all_gather_rows(both, e, per, dist)
+    return full[:, 0].contiguous(), full[:, 1].contiguous()
+
+
+def e_step_pass(model, decoder: MLPClassifier, src_node_ids, dst_node_ids, node_interact_times,
+                num_neighbors: int = 20, pseudo_labels_store=None, ps_filter: str = 'entropy', threshold: float = 0.9,
+                sharded=None, return_embeddings: bool = False):
+    """Embedding pass + pseudo-label emission + EST/CST filter for a single-way dataset.
+
+    Returns (pseudo_labels float32 [1, E] with -1 marks, probabilities float32 [E, C],
+    (src_emb, dst_emb) or None).  ``pseudo_labels_store`` is the reference's list of earlier
+    iterations' probabilities; this pass's probabilities are appended to it before filtering
+    (PTCL/E_step.py:351 then PTCL/utils.py:80-83).  When sharded, only (label, probs) rows are
+    all-gathered (16 B/event for C=2) unless the embeddings are requested."""
+    dist, rank, world = _dist()
+    if sharded is None:
+        sharded = world > 1
+    src = np.asarray(src_node_ids)
+    e = len(src)
+    store = pseudo_labels_store if pseudo_labels_store is not None else []
+    if not sharded or world == 1:
+        src_emb, dst_emb = embed_events(model, src, dst_node_ids, node_interact_times, num_neighbors, sharded=False)
+        labels, probs = emit_pseudo_labels(decoder, src_emb)
+        emb = (src_emb, dst_emb)
+    else:
+        lo, hi, per = shard_bounds(e, rank, world)
+        dst = np.asarray(dst_node_ids)
+        t = np.asarray(node_interact_times)
+        with torch.no_grad():
+            a, b = model.compute_src_dst_node_temporal_embeddings(src[lo:hi], dst[lo:hi], t[lo:hi], num_neighbors)
+        l_loc, p_loc = emit_pseudo_labels(decoder, a)
+        packed = torch.cat([l_loc.to(torch.float32).unsqueeze(1), p_loc], dim=1)     # [n_local, 1 + C]
+        full = all_gather_rows(packed, e, per, dist)
+        labels, probs = full[:, 0].to(torch.int64), full[:, 1:].contiguous()
+        emb = None
+        if return_embeddings:
+            both = all_gather_rows(torch.stack([a, b], dim=1), e, per, dist)
+            emb = (both[:, 0].contiguous(), both[:, 1].contiguous())
+    store.append(probs)
+    pseudo = labels.to(torch.float32).reshape(1, -1).contiguous()
+    if ps_filter == 'entropy':
+        pseudo = entropy_filter(pseudo, store, threshold)
+    elif ps_filter == 'probability':
+        pseudo = prob_filter(pseudo, store, threshold)
+    return pseudo, probs, (emb if return_embeddings or not sharded else None)
+
+
+def tgn_pass(model, src_node_ids, dst_node_ids, node_interact_times, edge_ids, batch_size: int = 200,
+             num_neighbors: int = 20):
+    """Full chronological TGN pass (PTCL/M_step.py:454-509 with model_name='TGN'): the bank is
+    reset, events are fed in batches of ``batch_size`` (the batch boundary is part of the
+    semantics) and the per-event embeddings are returned as [E, dn] x 2."""
+    src, dst = np.asarray(src_node_ids), np.asarray(dst_node_ids)
+    t, eid = np.asarray(node_interact_times), np.asarray(edge_ids)
+    e = len(src)
+    dev = model.node_raw_features.device
+    out_s = torch.empty((e, model.node_feat_dim), dtype=torch.float32, device=dev)
+    out_d = torch.empty_like(out_s)
+    model.memory_bank.__init_memory_bank__()
+    with torch.no_grad():
+        for lo in range(0, e, batch_size):
+            hi = min(lo + batch_size, e)
+            a, b = model.compute_src_dst_node_temporal_embeddings(src[lo:hi], dst[lo:hi], t[lo:hi], eid[lo:hi], True,
+                                                                  num_neighbors)
+            out_s[lo:hi], out_d[lo:hi] = a, b
+    return out_s, out_d

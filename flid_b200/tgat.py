@@ -1,0 +1,236 @@
+"""Drop-in for the reference's ``models.TGAT.TGAT`` (``models/TGAT.py``) and the building
+blocks it owns (``models/modules.py``: TimeEncoder :7-40, MultiHeadAttention :126-245,
+MergeLayer :43-69), with the same constructor, method names, error behaviour and
+``state_dict`` keys / shapes, so reference checkpoints load unchanged.
+
+Inference (``torch.no_grad()`` or ``.eval()``-time calls without grad) runs the sm_100a
+kernels through the C ABI (``flid_tgat_embed``).  The parameter-holder modules below keep
+the reference's parameter names and default initialisation only; they have no forward of
+their own on this path.  Training-mode calls that need autograd are the "next" row of
+SURVEY.md section 8(f) and raise until that row lands -- there is no silent torch fallback.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .sampler import NeighborSampler
+
+
+class TimeEncoder(nn.Module):
+    """cos(w * t + b); w initialised to 1 / 10^linspace(0, 9, T), b to 0 (models/modules.py:7-26)."""
+
+    def __init__(self, time_dim: int, parameter_requires_grad: bool = True):
+        super().__init__()
+        self.time_dim = time_dim
+        self.w = nn.Linear(1, time_dim)
+        self.w.weight = nn.Parameter(torch.from_numpy(
+            1 / 10 ** np.linspace(0, 9, time_dim, dtype=np.float32)).reshape(time_dim, -1))
+        self.w.bias = nn.Parameter(torch.zeros(time_dim))
+        if not parameter_requires_grad:
+            self.w.weight.requires_grad = False
+            self.w.bias.requires_grad = False
+
+
+class MultiHeadAttention(nn.Module):
+    """Parameter holder with the reference's names/shapes (models/modules.py:128-165)."""
+
+    def __init__(self, node_feat_dim: int, edge_feat_dim: int, time_feat_dim: int, num_heads: int = 2,
+                 dropout: float = 0.1):
+        super().__init__()
+        self.node_feat_dim, self.edge_feat_dim, self.time_feat_dim = node_feat_dim, edge_feat_dim, time_feat_dim
+        self.num_heads = num_heads
+        self.query_dim = node_feat_dim + time_feat_dim
+        self.key_dim = node_feat_dim + edge_feat_dim + time_feat_dim
+        assert self.query_dim % num_heads == 0, \
+            "The sum of node_feat_dim and time_feat_dim should be divided by num_heads!"
+        self.head_dim = self.query_dim // num_heads
+        self.query_projection = nn.Linear(self.query_dim, num_heads * self.head_dim, bias=False)
+        self.key_projection = nn.Linear(self.key_dim, num_heads * self.head_dim, bias=False)
+        self.value_projection = nn.Linear(self.key_dim, num_heads * self.head_dim, bias=False)
+        self.scaling_factor = self.head_dim ** -0.5
+        self.layer_norm = nn.LayerNorm(self.query_dim)
+        self.residual_fc = nn.Linear(num_heads * self.head_dim, self.query_dim)
+        self.dropout = nn.Dropout(dropout)
+
+
+class MergeLayer(nn.Module):
+    """fc2(relu(fc1([x1 | x2]))) parameter holder (models/modules.py:45-56)."""
+
+    def __init__(self, input_dim1: int, input_dim2: int, hidden_dim: int, output_dim: int):
+        super().__init__()
+        self.fc1 = nn.Linear(input_dim1 + input_dim2, hidden_dim)
+        self.fc2 = nn.Linear(hidden_dim, output_dim)
+        self.act = nn.ReLU()
+
+
+class _Engine:
+    """C-ABI TGAT handles (one per recursion depth actually requested) kept in sync with
+    the owning module's parameters."""
+
+    def __init__(self, node_dim, edge_dim, time_dim, num_heads):
+        self.dims = (node_dim, edge_dim, time_dim, num_heads)
+        self.handles = {}    # depth -> c_void_p
+        self.versions = {}   # depth -> parameter fingerprint
+        self.tables = {}     # depth -> (data_ptr, rows) of the cached node table
+
+    def close(self):
+        for h in self.handles.values():
+            try:
+                _lib.lib().flid_tgat_free(h)
+            except Exception:
+                pass
+        self.handles.clear()
+
+    def handle(self, depth, time_encoder, conv_layers, merge_layers, device):
+        lib = _lib.lib()
+        params = [time_encoder.w.weight, time_encoder.w.bias]
+        for l in range(depth):
+            a, m = conv_layers[l], merge_layers[l]
+            params += [a.query_projection.weight, a.key_projection.weight, a.value_projection.weight,
+                       a.layer_norm.weight, a.layer_norm.bias, a.residual_fc.weight, a.residual_fc.bias,
+                       m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias]
+        for p in params:
+            if p.device != device:
+                raise RuntimeError(f"flid_b200: parameters live on {p.device} but the feature tables are on {device}; "
+                                   "move the model with .to(device) first (no CPU fallback)")
+            if p.dtype != torch.float32:
+                raise RuntimeError("flid_b200: parameters must be float32")
+        fp = tuple((p.data_ptr(), p._version) for p in params)
+        if depth not in self.handles:
+            h = C.c_void_p(None)
+            dn, de, T, H = self.dims
+            _lib.check(lib.flid_tgat_create(dn, de, T, depth, H, C.byref(h)))
+            self.handles[depth] = h
+        h = self.handles[depth]
+        if self.versions.get(depth) != fp:
+            layers = (_lib.LayerWeights * depth)()
+            keep = []
+            for l in range(depth):
+                chunk = [p.detach().contiguous() for p in params[2 + 11 * l: 2 + 11 * (l + 1)]]
+                keep += chunk
+                for name, t in zip([f[0] for f in _lib.LayerWeights._fields_], chunk):
+                    setattr(layers[l], name, t.data_ptr())
+            tw, tb = params[0].detach().contiguous(), params[1].detach().contiguous()
+            _lib.check(lib.flid_tgat_set_weights(h, _lib.ptr(tw), _lib.ptr(tb), layers, _lib.stream()))
+            self.versions[depth] = fp
+            self.tables.pop(depth, None)
+        return h
+
+    def ensure_table(self, depth, h, node_feat):
+        """Cache the layer-1 query fold of the (static) node feature table once per weight version."""
+        key = (node_feat.data_ptr(), node_feat.shape[0], node_feat._version)
+        if self.tables.get(depth) != key:
+            _lib.check(_lib.lib().flid_tgat_cache_node_table(h, _lib.ptr(node_feat), node_feat.shape[0],
+                                                             _lib.stream()))
+            self.tables[depth] = key
+
+
+def embed_roots(engine, depth, time_encoder, conv_layers, merge_layers, sampler, node_feat, edge_feat,
+                node_ids, node_interact_times, num_neighbors, use_table=True):
+    """Shared by TGAT and MemoryModel: n root queries -> float32 [n, dn] on the device."""
+    device = node_feat.device
+    _lib.require_cuda(device)
+    if not isinstance(sampler, NeighborSampler):
+        raise TypeError("flid_b200 models need a flid_b200.NeighborSampler (device CSR); got "
+                        f"{type(sampler).__name__}")
+    if sampler.device != device:
+        raise RuntimeError(f"neighbor sampler lives on {sampler.device}, model on {device}")
+    with torch.cuda.device(device):
+        h = engine.handle(depth, time_encoder, conv_layers, merge_layers, device)
+        if use_table:
+            engine.ensure_table(depth, h, node_feat)
+        if isinstance(node_ids, torch.Tensor):
+            d_nodes = node_ids.to(device, torch.int64).contiguous()
+        else:
+            d_nodes = _lib.to_device(node_ids, np.int64, device, "e_nodes")
+        if isinstance(node_interact_times, torch.Tensor):
+            is32 = 1 if node_interact_times.dtype == torch.float32 else 0
+            d_times = node_interact_times.to(device, torch.float64).contiguous()
+        else:
+            t = np.asarray(node_interact_times)
+            is32 = 1 if t.dtype == np.float32 else 0
+            d_times = _lib.to_device(t, np.float64, device, "e_times")   # float32 -> float64 is exact
+        n = d_nodes.shape[0]
+        out = torch.empty((n, node_feat.shape[1]), dtype=torch.float32, device=device)
+        _lib.check(_lib.lib().flid_tgat_embed(h, sampler.handle, _lib.ptr(node_feat), _lib.ptr(edge_feat),
+                                              _lib.ptr(d_nodes), _lib.ptr(d_times), is32, n, int(num_neighbors),
+                                              _lib.ptr(out), _lib.stream()))
+    return out
+
+
+class TGAT(nn.Module):
+
+    def __init__(self, node_raw_features: np.ndarray, edge_raw_features: np.ndarray, neighbor_sampler: NeighborSampler,
+                 time_feat_dim: int, num_layers: int = 2, num_heads: int = 2, dropout: float = 0.1, device: str = 'cpu'):
+        """Same arguments as models/TGAT.py:11-48.  ``device`` must be a CUDA device."""
+        super().__init__()
+        self.node_raw_features = torch.from_numpy(np.ascontiguousarray(node_raw_features.astype(np.float32))).to(device)
+        self.edge_raw_features = torch.from_numpy(np.ascontiguousarray(edge_raw_features.astype(np.float32))).to(device)
+        self.neighbor_sampler = neighbor_sampler
+        self.node_feat_dim = self.node_raw_features.shape[1]
+        self.edge_feat_dim = self.edge_raw_features.shape[1]
+        self.time_feat_dim = time_feat_dim
+        self.num_layers = num_layers
+        self.num_heads = num_heads
+        self.dropout = dropout
+        self.time_encoder = TimeEncoder(time_dim=time_feat_dim)
+        self.temporal_conv_layers = nn.ModuleList([
+            MultiHeadAttention(self.node_feat_dim, self.edge_feat_dim, self.time_feat_dim, self.num_heads, self.dropout)
+            for _ in range(num_layers)])
+        self.merge_layers = nn.ModuleList([
+            MergeLayer(self.node_feat_dim + self.time_feat_dim, self.node_feat_dim, self.node_feat_dim,
+                       self.node_feat_dim) for _ in range(num_layers)])
+        self._engine = _Engine(self.node_feat_dim, self.edge_feat_dim, self.time_feat_dim, self.num_heads)
+
+    def __del__(self):
+        eng = getattr(self, "_engine", None)
+        if eng is not None:
+            eng.close()
+
+    def _check_mode(self):
+        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError(
+                "flid_b200.TGAT: the fused path is forward-only; call under torch.no_grad() or model.eval(). "
+                "Training-mode forward+backward is the next row of SURVEY.md 8(f).")
+
+    def compute_src_dst_node_temporal_embeddings(self, src_node_ids: np.ndarray, dst_node_ids: np.ndarray,
+                                                 node_interact_times: np.ndarray, num_neighbors: int = 20):
+        """models/TGAT.py:50-66 -> (Tensor[B, dn], Tensor[B, dn]) on the model's device.
+        src and dst roots are independent, so both halves go through one launch chain."""
+        b = len(src_node_ids)
+        both = self.compute_node_temporal_embeddings(
+            np.concatenate([np.asarray(src_node_ids), np.asarray(dst_node_ids)]),
+            np.concatenate([np.asarray(node_interact_times), np.asarray(node_interact_times)]),
+            self.num_layers, num_neighbors)
+        return both[:b], both[b:]
+
+    def compute_node_temporal_embeddings(self, node_ids: np.ndarray, node_interact_times: np.ndarray,
+                                         current_layer_num: int, num_neighbors: int = 20):
+        """models/TGAT.py:68-144."""
+        assert current_layer_num >= 0
+        if current_layer_num == 0:
+            idx = torch.as_tensor(np.asarray(node_ids), dtype=torch.int64, device=self.node_raw_features.device)
+            return self.node_raw_features[idx]
+        if current_layer_num > self.num_layers:
+            raise IndexError("current_layer_num exceeds num_layers")
+        self._check_mode()
+        return embed_roots(self._engine, current_layer_num, self.time_encoder, self.temporal_conv_layers,
+                           self.merge_layers, self.neighbor_sampler, self.node_raw_features, self.edge_raw_features,
+                           node_ids, node_interact_times, num_neighbors)
+
+    def set_neighbor_sampler(self, neighbor_sampler: NeighborSampler):
+        """models/TGAT.py:146-155."""
+        self.neighbor_sampler = neighbor_sampler
+        if self.neighbor_sampler.sample_neighbor_strategy in ['uniform', 'time_interval_aware']:
+            assert self.neighbor_sampler.seed is not None
+            self.neighbor_sampler.reset_random_state()
+
+    def last_stats(self, depth=None):
+        """(attention evaluations, valid neighbour slots, sampler queries, workspace bytes) of the last call."""
+        depth = depth or self.num_layers
+        out = (C.c_int64 * 4)()
+        _lib.check(_lib.lib().flid_tgat_last_stats(self._engine.handles[depth], out))
+        return tuple(out)

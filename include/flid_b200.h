@@ -1,0 +1,189 @@
+/*
+ * flid_b200 -- C ABI of the B200-native (sm_100a) temporal-embedding hot path of FLiD.
+ *
+ * The FLiD reference is pure Python and has no FFI layer; its "plugin boundary" for
+ * this path is a handful of Python methods.  Each entry point below names the
+ * reference interface (file:line under the reference tree) it replaces.  The Python
+ * classes in flid_b200/ bind these with ctypes and keep the
+ * reference's names, argument meaning and error behaviour.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; flid_last_error()
+ *     returns a thread-local, human-readable reason.  No exceptions cross the ABI.
+ *   - pointers are DEVICE pointers unless the parameter name ends in _host.
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued, not synchronised,
+ *     unless stated.  Handles are thread-compatible, not thread-safe.
+ *   - ids are int64 at the boundary (numpy's default, as the reference passes them)
+ *     and int32 internally; node id 0 / edge id 0 are the padding rows.
+ */
+#ifndef FLID_B200_H
+#define FLID_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FLID_OK 0
+#define FLID_ERR_INVALID 1   /* bad argument / unsupported shape            */
+#define FLID_ERR_CUDA 2      /* CUDA runtime error (see flid_last_error)    */
+#define FLID_ERR_RANGE 3     /* node / edge id outside the graph            */
+#define FLID_ERR_STATE 4     /* e.g. TGN "update memory to time in the past" */
+
+typedef struct flid_graph flid_graph; /* device CSR, time-sorted inside each node      */
+typedef struct flid_tgat flid_tgat;   /* folded TGAT weights + grow-only workspace      */
+typedef void* flid_stream;            /* cudaStream_t                                   */
+
+const char* flid_last_error(void);
+int flid_abi_version(void);
+/* number of kernel launches issued through this library since load (for bench.py's gpu_launches) */
+int64_t flid_launch_count(void);
+
+/* ------------------------------------------------------------------ graph ---------
+ * Replaces get_neighbor_sampler (utils/utils.py:283-302) + NeighborSampler.__init__
+ * (utils/utils.py:73-110): undirected adjacency, per node stably sorted by timestamp.
+ *
+ * flid_graph_build_events: src/dst/eid int64[E], ts float64[E] (event order; every
+ *   event is appended to src's list then to dst's list, as the reference does).
+ * flid_graph_build_entries: the adj_list form -- owner/nbr/eid/ts [M] in insertion order.
+ * `on_device` != 0 means the four input arrays are device pointers, else host.
+ * num_nodes = largest valid node id (tables have num_nodes+1 rows incl. padding id 0).
+ * Both calls synchronise the stream before returning.                                */
+int flid_graph_build_events(const int64_t* src, const int64_t* dst, const int64_t* eid, const double* ts,
+                            int64_t num_events, int64_t num_nodes, int on_device, flid_graph** out,
+                            flid_stream stream);
+int flid_graph_build_entries(const int64_t* owner, const int64_t* nbr, const int64_t* eid, const double* ts,
+                             int64_t num_entries, int64_t num_nodes, int on_device, flid_graph** out,
+                             flid_stream stream);
+void flid_graph_free(flid_graph* g);
+int flid_graph_info(const flid_graph* g, int64_t* num_nodes, int64_t* num_entries, int64_t* max_degree);
+/* copy the CSR to host arrays: indptr int64[num_nodes+2], nbr/eid int64[M], ts float64[M] (synchronous) */
+int flid_graph_export_host(const flid_graph* g, int64_t* indptr_host, int64_t* nbr_host, int64_t* eid_host,
+                           double* ts_host);
+
+/* ---------------------------------------------------------------- sampler ---------
+ * NeighborSampler.get_historical_neighbors, strategy 'recent' (utils/utils.py:149-214)
+ * on top of find_neighbors_before (utils/utils.py:130-147, searchsorted side='left').
+ * nodes int64[n]; times float64[n] or float32[n] (times_are_f32); outputs int64[n,k],
+ * int64[n,k], float32[n,k]: the last <=k strictly-earlier interactions, right-aligned,
+ * zero padded on the left, timestamps rounded float64->float32 (RN). Bit-exact.       */
+int flid_sample_recent(const flid_graph* g, const int64_t* nodes, const void* times, int times_are_f32,
+                       int64_t n, int k, int64_t* out_nbr, int64_t* out_eid, float* out_ts, flid_stream stream);
+/* find_neighbors_before / get_all_first_hop_neighbors (utils/utils.py:130-147, 254-273):
+ * per query the CSR range [start, cut) of strictly-earlier interactions.              */
+int flid_sample_cut(const flid_graph* g, const int64_t* nodes, const void* times, int times_are_f32, int64_t n,
+                    int64_t* out_start, int64_t* out_cut, flid_stream stream);
+
+/* ------------------------------------------------------------------- TGAT ---------
+ * Weights are handed over in the reference's state_dict layout ([out, in] row-major
+ * float32), see models/modules.py:126-165 (MultiHeadAttention), :43-56 (MergeLayer),
+ * :7-26 (TimeEncoder).                                                                */
+typedef struct {
+    const float* query_w; /* [qd, qd]  temporal_conv_layers.L.query_projection.weight, qd = dn + T       */
+    const float* key_w;   /* [qd, kd]  ...key_projection.weight,   kd = dn + de + T                      */
+    const float* value_w; /* [qd, kd]  ...value_projection.weight                                         */
+    const float* ln_w;    /* [qd]      ...layer_norm.weight                                               */
+    const float* ln_b;    /* [qd]      ...layer_norm.bias                                                 */
+    const float* res_w;   /* [qd, qd]  ...residual_fc.weight                                              */
+    const float* res_b;   /* [qd]      ...residual_fc.bias                                                */
+    const float* fc1_w;   /* [dn, qd + dn]  merge_layers.L.fc1.weight                                     */
+    const float* fc1_b;   /* [dn]                                                                         */
+    const float* fc2_w;   /* [dn, dn]       merge_layers.L.fc2.weight                                     */
+    const float* fc2_b;   /* [dn]                                                                         */
+} flid_tgat_layer_weights;
+
+int flid_tgat_create(int node_dim, int edge_dim, int time_dim, int num_layers, int num_heads, flid_tgat** out);
+void flid_tgat_free(flid_tgat* m);
+/* (Re)load weights; folds Wq/Wk and Wv/residual_fc.  time_w is
+ * time_encoder.w.weight [T,1] (read as T floats), time_b is time_encoder.w.bias [T]. */
+int flid_tgat_set_weights(flid_tgat* m, const float* time_w, const float* time_b,
+                          const flid_tgat_layer_weights* layers_host, flid_stream stream);
+/* Optional: cache the layer-1 query fold of every row of a node-feature table
+ * (rows = num_nodes+1).  Valid until the next set_weights or until the table changes;
+ * flid_tgat_embed uses it when called with the same node_feat pointer.               */
+int flid_tgat_cache_node_table(flid_tgat* m, const float* node_feat, int64_t rows, flid_stream stream);
+/* refresh `n` rows (int32 ids) of the cached table after node_feat changed (TGN)     */
+int flid_tgat_refresh_node_rows(flid_tgat* m, const float* node_feat, const int32_t* row_ids, int64_t n,
+                                flid_stream stream);
+/* TGAT.compute_node_temporal_embeddings (models/TGAT.py:68-144) at current_layer_num =
+ * num_layers, eval mode, for n root queries (node, time).  times float64[n], or the
+ * float32 values widened to float64 with times_are_f32 != 0 (the recursion's dtype rule,
+ * models/TGAT.py:110-125).  node_feat [N+1, dn], edge_feat [E+1, de] float32 row-major.
+ * out float32 [n, dn].  GraphAttentionEmbedding (models/MemoryModel.py:632-715) is the
+ * same call with node_feat = memory' + raw.                                            */
+int flid_tgat_embed(flid_tgat* m, const flid_graph* g, const float* node_feat, const float* edge_feat,
+                    const int64_t* nodes, const double* times, int times_are_f32, int64_t n, int k, float* out,
+                    flid_stream stream);
+/* upper bound on layer-1 targets processed per internal chunk (workspace ~7 KB per target;
+ * default 65536).  Results do not depend on it.                                        */
+int flid_tgat_set_chunk_targets(flid_tgat* m, int64_t max_layer1_targets);
+/* bytes / counts of the last flid_tgat_embed call, for the roofline report:
+ * stats[0] = attention evaluations, stats[1] = valid (non-padded) neighbour slots gathered,
+ * stats[2] = sampler queries, stats[3] = workspace bytes currently held.             */
+int flid_tgat_last_stats(const flid_tgat* m, int64_t stats[4]);
+
+/* --------------------------------------------------------------- TGN (memory) -----
+ * MemoryModel('TGN').compute_src_dst_node_temporal_embeddings (models/MemoryModel.py:96-189).
+ * All state lives in caller-owned device arrays so that the Python module can expose
+ * them under the reference's state_dict names (memory_bank.node_memories, ...).      */
+typedef struct {
+    int64_t num_rows;        /* N+1 (incl. padding node 0)                                              */
+    float* memories;         /* [rows, dn]   memory_bank.node_memories                                  */
+    float* last_updated;     /* [rows]       memory_bank.node_last_updated_times                        */
+    float* pending_msg;      /* [rows, 2dn+T+de] last raw message per node (node_raw_messages[v][-1][0]) */
+    double* pending_ts;      /* [rows]       its timestamp (node_raw_messages[v][-1][1])                */
+    uint8_t* has_pending;    /* [rows]                                                                   */
+    float* next_memories;    /* [rows, dn]   GRU(pending, memory) where pending, else memory            */
+    float* layer0;           /* [rows, dn]   next_memories + node_raw  (layer-0 / merge input table)    */
+    int32_t* scratch;        /* [rows] int32, must be -1 filled before first use                        */
+} flid_tgn_state;
+
+typedef struct {
+    const float* weight_ih; /* [3dn, 2dn+T+de]  memory_updater.memory_updater.weight_ih */
+    const float* weight_hh; /* [3dn, dn]                                                */
+    const float* bias_ih;   /* [3dn]                                                    */
+    const float* bias_hh;   /* [3dn]                                                    */
+} flid_gru_weights;
+
+/* zero the state (MemoryBank.__init_memory_bank__, models/MemoryModel.py:359-366) and
+ * set layer0 = node_raw.                                                               */
+int flid_tgn_reset(const flid_tgn_state* s, const float* node_raw, int node_dim, int msg_dim, flid_stream stream);
+/* recompute next_memories / layer0 for every row from (memories, pending) -- after a
+ * state reload or a weight change.                                                     */
+int flid_tgn_rebuild(flid_tgat* m, const flid_tgn_state* s, const flid_gru_weights* gru, const float* node_raw,
+                     flid_stream stream);
+/* one batch: embeddings for cat[src,dst] at cat[t,t], then (if positive) persist the
+ * pending updates of the batch nodes, build their new raw messages (dst role stored
+ * after src role, so it wins) and refresh next_memories/layer0.  err_flag (device int32)
+ * is set to 1 if the reference's "update memory to time in the past" assertion would fire
+ * and to 2 if a node / edge id is out of range (the id is then clamped to padding).      */
+int flid_tgn_step(flid_tgat* m, const flid_graph* g, const flid_tgn_state* s, const flid_gru_weights* gru,
+                  const float* node_raw, const float* edge_feat, const int64_t* src, const int64_t* dst,
+                  const double* times, const int64_t* eids, int64_t batch, int positive, int k,
+                  float* out /* [2*batch, dn]: src rows then dst rows */, int32_t* err_flag, flid_stream stream);
+
+/* -------------------------------------------------------- pseudo-label scoring ----
+ * MLPClassifier.forward (models/modules.py:86-97, eval) + softmax/argmax emission
+ * (PTCL/E_step.py:334-335) fused: emb float32[n, in] -> probs float32[n, C], labels int64[n]. */
+typedef struct {
+    const float* fc1_w; const float* fc1_b; /* [h1, in], [h1]  */
+    const float* fc2_w; const float* fc2_b; /* [h2, h1], [h2]  */
+    const float* fc3_w; const float* fc3_b; /* [C, h2],  [C]   */
+    int input_dim, hidden1, hidden2, num_classes;
+} flid_mlp_weights;
+int flid_pseudo_label(const flid_mlp_weights* w, const float* emb, int64_t n, float* probs, int64_t* labels,
+                      float* logits_or_null, flid_stream stream);
+/* entropy_filter (EST, PTCL/utils.py:38-54): probs_store_host = host array of num_iters
+ * device pointers to float32[n, C]; labels float32[n] are set to -1 where
+ * -sum p*log2(p+1e-10) > threshold, p = softmax(sum_iters probs).                      */
+int flid_entropy_filter(const float* const* probs_store_host, int num_iters, int64_t n, int num_classes,
+                        float threshold, float* labels, flid_stream stream);
+/* prob_filter (CST, PTCL/utils.py:56-67): labels[i] = -1 where max_c probs_last[i,c] < threshold */
+int flid_prob_filter(const float* probs_last, int64_t n, int num_classes, float threshold, float* labels,
+                     flid_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLID_B200_H */

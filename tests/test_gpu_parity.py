@@ -1,0 +1,427 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Every check goes through the C ABI
+(via the ctypes host layer) and compares against the CPU oracle (oracle/) on the same
+seeded inputs and against the golden vectors minted from the real FLiD reference.
+
+Tolerances (BASELINE.json north_star): sampler bit-exact; fp32 embeddings rel 1e-4
+(stated here as |got - want| <= 1e-4 * max(1, max|want|) elementwise, i.e. 1e-4 of the
+tensor's scale, plus a tight mean-error check); pseudo-label masks identical."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+import flid_b200
+from flid_b200 import _lib, passes, synth
+from oracle import sampler as osamp, tgat as otgat, tgn as otgn, pseudo as opseudo
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+DEV = "cuda:0"
+
+
+def load(name):
+    return np.load(os.path.join(G, name))
+
+
+def assert_fp32_close(got, want, what=""):
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    assert np.isfinite(got).all(), f"{what}: non-finite values"
+    scale = max(1.0, float(np.abs(want).max()))
+    err = np.abs(got - want)
+    assert err.max() <= 1e-4 * scale, f"{what}: max abs err {err.max():.3e} (scale {scale:.3g})"
+    assert err.mean() <= 1e-5 * scale, f"{what}: mean abs err {err.mean():.3e}"
+
+
+def make_sampler(src, dst, eid, ts, n):
+    return flid_b200.NeighborSampler(None, "recent", seed=1, device=DEV, _events=(src, dst, eid, ts, n))
+
+
+# ===================================================================== sampler
+def test_csr_build_matches_oracle_events_and_adj_list():
+    src, dst, eid, ts, n = cases.adversarial_events()
+    o = osamp.OracleSampler.from_events(src, dst, eid, ts, n)
+    s = make_sampler(src, dst, eid, ts, n)
+    indptr, nbr, e, t = s._host_csr()
+    assert np.array_equal(indptr, o.indptr) and np.array_equal(nbr, o.nbr)
+    assert np.array_equal(e, o.eid) and np.array_equal(t, o.ts)
+    adj = [[] for _ in range(n + 1)]
+    for a, b, c, d in zip(src, dst, eid, ts):
+        adj[a].append((b, c, d))
+        adj[b].append((a, c, d))
+    s2 = flid_b200.NeighborSampler(adj, "recent", seed=1, device=DEV)
+    i2, n2, e2, t2 = s2._host_csr()
+    assert np.array_equal(i2, o.indptr) and np.array_equal(n2, o.nbr) and np.array_equal(e2, o.eid)
+    assert np.array_equal(t2, o.ts)
+    assert s.max_degree == int(np.diff(o.indptr).max())
+
+
+@pytest.mark.parametrize("k", [1, 3, 20])
+@pytest.mark.parametrize("dt", ["f64", "f32"])
+def test_sampler_golden_bit_exact(k, dt):
+    g = load("sampler.npz")
+    src, dst, eid, ts, n = cases.adversarial_events()
+    s = make_sampler(src, dst, eid, ts, n)
+    nodes, times = cases.adversarial_queries()
+    if dt == "f32":
+        times = times.astype(np.float32)
+    a, b, c = s.get_historical_neighbors(nodes, times, k)
+    assert a.dtype == np.int64 and b.dtype == np.int64 and c.dtype == np.float32
+    assert np.array_equal(a, g[f"{dt}_k{k}_nbr"])
+    assert np.array_equal(b, g[f"{dt}_k{k}_eid"])
+    assert np.array_equal(c, g[f"{dt}_k{k}_ts"])
+
+
+def test_sampler_multi_hop_and_ragged_apis():
+    g = load("sampler.npz")
+    src, dst, eid, ts, n = cases.adversarial_events()
+    s = make_sampler(src, dst, eid, ts, n)
+    o = osamp.OracleSampler.from_events(src, dst, eid, ts, n)
+    nodes, times = cases.adversarial_queries()
+    nl, el, tl = s.get_multi_hop_neighbors(2, nodes[:300], times[:300], 3)
+    for h in range(2):
+        assert np.array_equal(nl[h], g[f"hop{h}_nbr"]) and np.array_equal(el[h], g[f"hop{h}_eid"])
+        assert np.array_equal(tl[h], g[f"hop{h}_ts"])
+    a, b, c = s.get_all_first_hop_neighbors(nodes[:200], times[:200])
+    wa, wb, wc = o.get_all_first_hop_neighbors(nodes[:200], times[:200])
+    for i in range(200):
+        assert np.array_equal(a[i], wa[i]) and np.array_equal(b[i], wb[i]) and np.array_equal(c[i], wc[i])
+    x = s.find_neighbors_before(1, 25.0)
+    y = o.find_neighbors_before(1, 25.0)
+    assert all(np.array_equal(p, q) for p, q in zip(x[:3], y[:3])) and x[3] is None
+
+
+def test_sampler_errors_and_edges():
+    src, dst, eid, ts, n = cases.adversarial_events()
+    s = make_sampler(src, dst, eid, ts, n)
+    with pytest.raises(AssertionError):
+        s.get_historical_neighbors(np.array([1]), np.array([5.0]), 0)
+    with pytest.raises(IndexError):
+        s.get_historical_neighbors(np.array([n + 1]), np.array([5.0]), 3)
+    a, b, c = s.get_historical_neighbors(np.zeros(0, dtype=np.int64), np.zeros(0), 4)
+    assert a.shape == (0, 4) and c.dtype == np.float32
+    # k far above 32 (GraphMixer asks for 2000 recent neighbours)
+    o = osamp.OracleSampler.from_events(src, dst, eid, ts, n)
+    nodes = np.array([1, 1, 2, 42, 0, 60], dtype=np.int64)
+    times = np.array([1e9, 20.0, 30.0, 1e9, 1e9, 1e9])
+    for k in (33, 64, 2000):
+        got, want = s.get_historical_neighbors(nodes, times, k), o.get_historical_neighbors(nodes, times, k)
+        assert all(np.array_equal(p, q) for p, q in zip(got, want))
+
+
+@pytest.mark.parametrize("shape", ["wikipedia", "dsub", "fractional"])
+def test_sampler_random_graphs_bit_exact(shape):
+    if shape == "wikipedia":
+        g = synth.wikipedia_shape(seed=3, scale=0.2)
+    elif shape == "dsub":
+        g = synth.dsub_shape(seed=4, scale=0.2)
+    else:
+        g = synth.general_graph("frac", 3000, 60000, 1e8, seed=5, exponent=0.9, integral_times=False, dim=4)
+    s = make_sampler(g.src_node_ids, g.dst_node_ids, g.edge_ids, g.node_interact_times, g.num_nodes)
+    o = osamp.OracleSampler.from_events(g.src_node_ids, g.dst_node_ids, g.edge_ids, g.node_interact_times, g.num_nodes)
+    rs = np.random.RandomState(0)
+    sel = rs.randint(0, g.num_interactions, 20000)
+    nodes = np.concatenate([g.src_node_ids[sel], g.dst_node_ids[sel], rs.randint(0, g.num_nodes + 1, 5000)])
+    times = np.concatenate([g.node_interact_times[sel], g.node_interact_times[sel],
+                            rs.uniform(0, g.node_interact_times.max() * 1.05, 5000)])
+    for k in (20, 30):
+        for tt in (times, times.astype(np.float32)):
+            got, want = s.get_historical_neighbors(nodes, tt, k), o.get_historical_neighbors(nodes, tt, k)
+            for p, q in zip(got, want):
+                assert p.dtype == q.dtype and np.array_equal(p, q)
+    # sortedness / strict-earlier properties on the device output itself
+    a, b, c = s.get_historical_neighbors(nodes, times, 20)
+    assert (np.diff(c, axis=1)[a[:, 1:] * a[:, :-1] != 0] >= 0).all()
+    assert (c[a != 0].astype(np.float64) <= np.repeat(times[:, None], 20, 1)[a != 0].astype(np.float32)).all()
+
+
+# ===================================================================== TGAT
+def tgat_pair(nf, ef, src, dst, eid, ts, L, heads, p):
+    s = make_sampler(src, dst, eid, ts, nf.shape[0] - 1)
+    m = flid_b200.TGAT(nf, ef, s, 100, L, heads, 0.1, DEV).to(DEV)
+    m.load_state_dict({k: v for k, v in p.items() if not k.startswith("_")})
+    m.eval()
+    return m, s
+
+
+TGAT_CASES = [("L1_k20", 1, 20, 2, 0.0, False), ("L2_k5", 2, 5, 2, 0.0, False), ("L2_k20_bias", 2, 20, 2, 0.5, False),
+              ("L2_k7_zeros", 2, 7, 2, 0.3, True), ("L3_k3", 3, 3, 2, 0.2, False)]
+
+
+@pytest.mark.parametrize("name,L,k,heads,bias,zeros", TGAT_CASES)
+def test_tgat_golden(name, L, k, heads, bias, zeros):
+    g = load("tgat.npz")
+    src, dst, eid, ts, nf, ef = cases.small_stream(node_zeros=zeros)
+    p = otgat.default_params(172, 172, 100, L, heads, seed=3, time_bias_scale=bias)
+    m, _ = tgat_pair(nf, ef, src, dst, eid, ts, L, heads, p)
+    sel = g[name + "_sel"]
+    with torch.no_grad():
+        a, b = m.compute_src_dst_node_temporal_embeddings(src[sel], dst[sel], ts[sel], k)
+    assert a.device.type == "cuda" and a.dtype == torch.float32 and a.shape == (len(sel), 172)
+    assert_fp32_close(a.cpu().numpy(), g[name + "_src"], name + " src")
+    assert_fp32_close(b.cpu().numpy(), g[name + "_dst"], name + " dst")
+
+
+@pytest.mark.parametrize("shape,L,k,heads", [("wikipedia", 2, 20, 2), ("dsub", 2, 30, 2), ("wikipedia", 1, 20, 4),
+                                             ("dsub", 1, 10, 1)])
+def test_tgat_vs_oracle_synthetic_shapes(shape, L, k, heads):
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    g = synth.wikipedia_shape(seed=1, scale=0.03) if shape == "wikipedia" else synth.dsub_shape(seed=2, scale=0.03)
+    p = otgat.default_params(172, 172, 100, L, heads, seed=9, time_bias_scale=0.25)
+    m, _ = tgat_pair(g.node_raw_features, g.edge_raw_features, g.src_node_ids, g.dst_node_ids, g.edge_ids,
+                     g.node_interact_times, L, heads, p)
+    o = osamp.OracleSampler.from_events(g.src_node_ids, g.dst_node_ids, g.edge_ids, g.node_interact_times, g.num_nodes)
+    e = g.num_interactions
+    nb = 60 if L == 2 else 200
+    sel = np.concatenate([np.arange(e // 2, e // 2 + nb), np.arange(e - nb, e)])
+    with torch.no_grad():
+        a, b = m.compute_src_dst_node_temporal_embeddings(g.src_node_ids[sel], g.dst_node_ids[sel],
+                                                          g.node_interact_times[sel], k)
+    wa, wb = otgat.embed_src_dst(p, torch.from_numpy(g.node_raw_features), torch.from_numpy(g.edge_raw_features), o,
+                                 g.src_node_ids[sel], g.dst_node_ids[sel], g.node_interact_times[sel], L, k)
+    assert_fp32_close(a.cpu().numpy(), wa.numpy(), f"{shape} L{L} src")
+    assert_fp32_close(b.cpu().numpy(), wb.numpy(), f"{shape} L{L} dst")
+
+
+def test_tgat_float32_root_times_and_lower_layers():
+    """compute_node_temporal_embeddings with float32 times (the recursion's call shape) and
+    current_layer_num below num_layers."""
+    src, dst, eid, ts, nf, ef = cases.small_stream()
+    p = otgat.default_params(172, 172, 100, 2, 2, seed=3, time_bias_scale=0.3)
+    m, _ = tgat_pair(nf, ef, src, dst, eid, ts, 2, 2, p)
+    o = osamp.OracleSampler.from_events(src, dst, eid, ts, nf.shape[0] - 1)
+    ids, t32 = src[300:340], ts[300:340].astype(np.float32)
+    for layer in (1, 2):
+        with torch.no_grad():
+            got = m.compute_node_temporal_embeddings(ids, t32, layer, 6)
+            want = otgat.embed(p, torch.from_numpy(nf), torch.from_numpy(ef), o, ids, t32, layer, 6)
+        assert_fp32_close(got.cpu().numpy(), want.numpy(), f"f32 layer {layer}")
+    got0 = m.compute_node_temporal_embeddings(ids, t32, 0, 6)
+    assert np.array_equal(got0.cpu().numpy(), nf[ids])
+
+
+def test_tgat_chunking_and_table_do_not_change_bits():
+    """Same kernels, different slices: chunked / unchunked and cached-table / per-target query
+    folds must be bit-identical (the property the multi-GPU sharding relies on)."""
+    g = synth.wikipedia_shape(seed=1, scale=0.03)
+    p = otgat.default_params(172, 172, 100, 2, 2, seed=9, time_bias_scale=0.25)
+    m, _ = tgat_pair(g.node_raw_features, g.edge_raw_features, g.src_node_ids, g.dst_node_ids, g.edge_ids,
+                     g.node_interact_times, 2, 2, p)
+    sel = np.arange(g.num_interactions - 500, g.num_interactions)
+    args = (g.src_node_ids[sel], g.dst_node_ids[sel], g.node_interact_times[sel], 20)
+    with torch.no_grad():
+        a0, b0 = m.compute_src_dst_node_temporal_embeddings(*args)
+        h = m._engine.handles[2]
+        _lib.check(_lib.lib().flid_tgat_set_chunk_targets(h, 21 * 37))
+        a1, b1 = m.compute_src_dst_node_temporal_embeddings(*args)
+        _lib.check(_lib.lib().flid_tgat_set_chunk_targets(h, 65536))
+        a2 = torch.cat([m.compute_src_dst_node_temporal_embeddings(args[0][i:i + 125], args[1][i:i + 125],
+                                                                     args[2][i:i + 125], 20)[0]
+                        for i in range(0, 500, 125)])
+    assert torch.equal(a0, a1) and torch.equal(b0, b1) and torch.equal(a0, a2)
+    st = m.last_stats()
+    assert st[0] == 125 * 2 * 22 and st[2] == 125 * 2 * 22 and 0 < st[1] <= st[0] * 20
+
+
+def test_tgat_weight_update_is_picked_up():
+    src, dst, eid, ts, nf, ef = cases.small_stream()
+    p = otgat.default_params(172, 172, 100, 1, 2, seed=3)
+    m, _ = tgat_pair(nf, ef, src, dst, eid, ts, 1, 2, p)
+    o = osamp.OracleSampler.from_events(src, dst, eid, ts, nf.shape[0] - 1)
+    sel = np.arange(400, 420)
+    with torch.no_grad():
+        a0, _ = m.compute_src_dst_node_temporal_embeddings(src[sel], dst[sel], ts[sel], 5)
+        p2 = otgat.default_params(172, 172, 100, 1, 2, seed=4, time_bias_scale=0.2)
+        m.load_state_dict({k: v for k, v in p2.items() if not k.startswith("_")})
+        a1, _ = m.compute_src_dst_node_temporal_embeddings(src[sel], dst[sel], ts[sel], 5)
+    w1, _ = otgat.embed_src_dst(p2, torch.from_numpy(nf), torch.from_numpy(ef), o, src[sel], dst[sel], ts[sel], 1, 5)
+    assert not torch.equal(a0, a1)
+    assert_fp32_close(a1.cpu().numpy(), w1.numpy(), "after load_state_dict")
+
+
+def test_tgat_errors():
+    src, dst, eid, ts, nf, ef = cases.small_stream()
+    p = otgat.default_params(172, 172, 100, 1, 2, seed=3)
+    m, _ = tgat_pair(nf, ef, src, dst, eid, ts, 1, 2, p)
+    with torch.no_grad():
+        with pytest.raises(IndexError):
+            m.compute_src_dst_node_temporal_embeddings(np.array([10 ** 6]), np.array([1]), np.array([5.0]), 5)
+        with pytest.raises(AssertionError):
+            m.compute_src_dst_node_temporal_embeddings(np.array([1]), np.array([1]), np.array([5.0]), 0)
+    m.train()
+    with pytest.raises(NotImplementedError):
+        m.compute_src_dst_node_temporal_embeddings(np.array([1]), np.array([1]), np.array([5.0]), 5)
+
+
+# ===================================================================== TGN
+TGN_CASES = [("L1_k5", 1, 5, 25, 12, 0.3), ("L2_k4", 2, 4, 20, 8, 0.0)]
+
+
+def tgn_model(nf, ef, src, dst, eid, ts, L, p):
+    s = make_sampler(src, dst, eid, ts, nf.shape[0] - 1)
+    m = flid_b200.MemoryModel(nf, ef, s, 100, "TGN", L, 2, 0.1, device=DEV).to(DEV)
+    missing = m.load_state_dict({k: v for k, v in p.items() if not k.startswith("_")}, strict=False)
+    assert not missing.unexpected_keys
+    m.eval()
+    m.memory_bank.__init_memory_bank__()
+    return m
+
+
+@pytest.mark.parametrize("name,L,k,bs,nb,bias", TGN_CASES)
+def test_tgn_golden(name, L, k, bs, nb, bias):
+    g = load("tgn.npz")
+    src, dst, eid, ts, nf, ef = cases.small_stream(num_nodes=30, num_edges=400, seed=11, t_max=2.0e6)
+    p = otgn.default_params(172, 172, 100, L, 2, seed=5, time_bias_scale=bias)
+    m = tgn_model(nf, ef, src, dst, eid, ts, L, p)
+    with torch.no_grad():
+        for b in range(nb):
+            lo, hi = b * bs, (b + 1) * bs
+            a, c = m.compute_src_dst_node_temporal_embeddings(src[lo:hi], dst[lo:hi], ts[lo:hi], eid[lo:hi], True, k)
+            assert_fp32_close(torch.cat([a, c]).cpu().numpy(), g[name + "_emb"][b], f"{name} batch {b}")
+        a, c = m.compute_src_dst_node_temporal_embeddings(src[hi:hi + bs], dst[hi:hi + bs][::-1].copy(),
+                                                          ts[hi:hi + bs], eid[hi:hi + bs], False, k)
+        assert_fp32_close(torch.cat([a, c]).cpu().numpy(), g[name + "_neg"], f"{name} negative edges")
+    assert_fp32_close(m.memory_bank.node_memories.cpu().numpy(), g[name + "_mem"], "bank memories")
+    assert np.array_equal(m.memory_bank.node_last_updated_times.cpu().numpy(), g[name + "_lastupd"])
+    msgs = m.memory_bank.node_raw_messages
+    pend = sorted(v for v, l in msgs.items() if len(l) > 0)
+    assert np.array_equal(np.array(pend), g[name + "_pend_ids"])
+    assert_fp32_close(np.stack([msgs[v][-1][0].cpu().numpy() for v in pend]), g[name + "_pend_msg"], "raw messages")
+    assert np.array_equal(np.array([msgs[v][-1][1] for v in pend]), g[name + "_pend_ts"])
+
+
+def test_tgn_state_round_trips_and_pass_driver():
+    """backup/reload, state_dict + node_raw_messages checkpoint round trip, and the full-pass
+    driver all reproduce the straight run bit for bit; long run vs the oracle."""
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    src, dst, eid, ts, nf, ef = cases.small_stream(num_nodes=60, num_edges=1200, seed=13, t_max=3.0e6)
+    p = otgn.default_params(172, 172, 100, 1, 2, seed=6, time_bias_scale=0.1)
+    m = tgn_model(nf, ef, src, dst, eid, ts, 1, p)
+    bs, k = 40, 10
+    ref_s, ref_d = passes.tgn_pass(m, src, dst, ts, eid, bs, k)
+    # oracle over the same 30 batches (state carry across >= 30 consecutive batches)
+    o = otgn.OracleTGN(p, torch.from_numpy(nf), torch.from_numpy(ef),
+                       osamp.OracleSampler.from_events(src, dst, eid, ts, nf.shape[0] - 1), 1, k)
+    for lo in range(0, 1200, bs):
+        a, c = o.step(src[lo:lo + bs], dst[lo:lo + bs], ts[lo:lo + bs], eid[lo:lo + bs], True)
+        assert_fp32_close(ref_s[lo:lo + bs].cpu().numpy(), a.numpy(), f"tgn src batch {lo // bs}")
+        assert_fp32_close(ref_d[lo:lo + bs].cpu().numpy(), c.numpy(), f"tgn dst batch {lo // bs}")
+    assert_fp32_close(m.memory_bank.node_memories.cpu().numpy(), o.mem.numpy(), "final memories")
+    # replay with a backup / detour / reload in the middle, and a checkpoint round trip
+    m.memory_bank.__init_memory_bank__()
+    outs = []
+    with torch.no_grad():
+        for lo in range(0, 1200, bs):
+            if lo == 400:
+                bk = m.memory_bank.backup_memory_bank()
+                m.compute_src_dst_node_temporal_embeddings(src[800:840], dst[800:840], ts[800:840], eid[800:840], True, k)
+                m.memory_bank.reload_memory_bank(bk)
+            if lo == 800:
+                sd = {kk: v.clone() for kk, v in m.state_dict().items()}
+                raw = m.memory_bank.node_raw_messages
+                m.memory_bank.__init_memory_bank__()
+                m.load_state_dict(sd)
+                m.memory_bank.node_raw_messages = raw
+            a, c = m.compute_src_dst_node_temporal_embeddings(src[lo:lo + bs], dst[lo:lo + bs], ts[lo:lo + bs],
+                                                              eid[lo:lo + bs], True, k)
+            outs.append(a)
+    assert torch.equal(torch.cat(outs), ref_s)
+
+
+def test_tgn_time_travel_is_rejected():
+    src, dst, eid, ts, nf, ef = cases.small_stream(num_nodes=30, num_edges=400, seed=11, t_max=2.0e6)
+    p = otgn.default_params(172, 172, 100, 1, 2, seed=5)
+    m = tgn_model(nf, ef, src, dst, eid, ts, 1, p)
+    with torch.no_grad():
+        m.compute_src_dst_node_temporal_embeddings(src[200:220], dst[200:220], ts[200:220], eid[200:220], True, 5)
+        m.compute_src_dst_node_temporal_embeddings(src[220:240], dst[220:240], ts[220:240], eid[220:240], True, 5)
+        with pytest.raises(AssertionError, match="time in the past"):
+            for lo in (0, 20, 40, 60):
+                m.compute_src_dst_node_temporal_embeddings(src[lo:lo + 20], dst[lo:lo + 20], ts[lo:lo + 20],
+                                                           eid[lo:lo + 20], True, 5)
+
+
+# ===================================================================== pseudo labels
+@pytest.mark.parametrize("C", [2, 5])
+def test_pseudo_label_golden(C):
+    g = load("pseudo.npz")
+    rs = np.random.RandomState(21)
+    emb = None
+    for c in (2, 5):
+        e = rs.standard_normal((700, 172)).astype(np.float32) * 2.0
+        if c == C:
+            emb = e
+            break
+        rs.standard_normal((2, 700, c)), rs.randint(0, c, 700), rs.uniform(0, 1000, 700), rs.rand(700)
+    p = opseudo.default_decoder_params(172, C, seed=C)
+    dec = flid_b200.MLPClassifier(172, 0.1, C).to(DEV)
+    dec.load_state_dict(p)
+    dec.eval()
+    x = torch.from_numpy(emb).to(DEV)
+    with torch.no_grad():
+        logits = dec(x)
+    assert_fp32_close(logits.cpu().numpy(), g[f"C{C}_logits"], "decoder logits")
+    labels, probs = flid_b200.emit_pseudo_labels(dec, x)
+    assert_fp32_close(probs.cpu().numpy(), g[f"C{C}_probs"], "probabilities")
+    margin = np.sort(g[f"C{C}_probs"], axis=1)
+    clear = (margin[:, -1] - margin[:, -2]) > 1e-5
+    assert np.array_equal(labels.cpu().numpy()[clear], g[f"C{C}_labels"][clear]) and clear.mean() > 0.99
+    # masks from the reference's own fp32 probabilities: must be identical
+    store = [torch.from_numpy(s).to(DEV) for s in g[f"C{C}_store"]]
+    glab = torch.from_numpy(g[f"C{C}_labels"]).to(torch.float32)
+    for thr in (0.3, 0.6, 0.9):
+        ps = glab.reshape(1, -1).clone().to(DEV)
+        assert np.array_equal(flid_b200.entropy_filter(ps, store, thr).cpu().numpy(), g[f"C{C}_est_{thr}"])
+        ps = glab.reshape(1, -1).clone().to(DEV)
+        assert np.array_equal(flid_b200.prob_filter(ps, store, thr).cpu().numpy(), g[f"C{C}_cst_{thr}"])
+    ps = glab.reshape(2, 350).clone().to(DEV)
+    store2 = [s.reshape(2, 350, C) for s in store]
+    assert np.array_equal(flid_b200.entropy_filter(ps, store2, 0.6).cpu().numpy(), g[f"C{C}_est2_0.6"])
+
+    class D:
+        pass
+    full = D()
+    full.labels, full.labels_time, full.node_interact_times = g[f"C{C}_true"], g[f"C{C}_lt"], g[f"C{C}_it"]
+    for ut in (0, 1):
+        ps = glab.reshape(1, -1).clone().to(DEV)
+        data = {"full_data": full, "val_offest": np.int64(400), "dataset_name": "wikipedia"}
+        r = flid_b200.update_pseudo_labels(data, ps, store, [], "ps", use_transductive=ut, threshold=0.6,
+                                           ps_filter="entropy")
+        assert np.array_equal(r.cpu().numpy(), g[f"C{C}_upd_ut{ut}"])
+
+
+def test_e_step_pass_matches_oracle_pipeline():
+    """configs[2] in miniature: TGAT L=2 k=20 embeddings -> decoder -> EST filter over 3 stored
+    iterations, against the oracle pipeline.  Masks are compared where the oracle's entropy is
+    not within 1e-4 of the threshold (embeddings carry fp32 tolerance, not bit equality)."""
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    g = synth.reddit_shape(seed=0, scale=0.01)
+    o = osamp.OracleSampler.from_events(g.src_node_ids, g.dst_node_ids, g.edge_ids, g.node_interact_times, g.num_nodes)
+    sel = np.arange(g.num_interactions - 150, g.num_interactions)
+    src, dst, ts = g.src_node_ids[sel], g.dst_node_ids[sel], g.node_interact_times[sel]
+    store_gpu, store_cpu = [], []
+    for it in range(3):
+        p = otgat.default_params(172, 172, 100, 2, 2, seed=it)
+        pd = opseudo.default_decoder_params(172, 2, seed=it)
+        m, _ = tgat_pair(g.node_raw_features, g.edge_raw_features, g.src_node_ids, g.dst_node_ids, g.edge_ids,
+                         g.node_interact_times, 2, 2, p)
+        dec = flid_b200.MLPClassifier(172, 0.1, 2).to(DEV)
+        dec.load_state_dict(pd)
+        dec.eval()
+        pseudo, probs, emb = passes.e_step_pass(m, dec, src, dst, ts, 20, store_gpu, "entropy", 0.9,
+                                                return_embeddings=True)
+        wa, _ = otgat.embed_src_dst(p, torch.from_numpy(g.node_raw_features), torch.from_numpy(g.edge_raw_features),
+                                    o, src, dst, ts, 2, 20)
+        assert_fp32_close(emb[0].cpu().numpy(), wa.numpy(), f"iteration {it} embeddings")
+        wl, wp = opseudo.emit(pd, wa)
+        store_cpu.append(wp)
+        assert_fp32_close(probs.cpu().numpy(), wp.numpy(), f"iteration {it} probs")
+        want = opseudo.entropy_filter(wl.to(torch.float32).reshape(1, -1).clone(), store_cpu, 0.9)
+        acc = torch.softmax(torch.stack(store_cpu).sum(0), dim=1)
+        ent = -(acc * torch.log2(acc + 1e-10)).sum(1)
+        clear = ((ent - 0.9).abs() > 1e-4) & ((wp[:, 0] - wp[:, 1]).abs() > 1e-4)
+        assert clear.float().mean() > 0.95
+        assert torch.equal(pseudo.cpu()[0][clear], want[0][clear])
+    assert len(store_gpu) == 3
