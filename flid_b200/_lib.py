@@ -58,6 +58,8 @@ _SIGNATURES = {
     "flid_tgat_embed": (C.c_int, [c_void, c_void, c_void, c_void, c_void, c_void, C.c_int, C.c_int64, C.c_int,
                                   c_void, c_void]),
     "flid_tgat_set_chunk_targets": (C.c_int, [c_void, C.c_int64]),
+    "flid_tgat_profile": (C.c_int, [c_void, C.c_int]),
+    "flid_tgat_profile_read": (C.c_int, [c_void, C.POINTER(C.c_double), c_i64p]),
     "flid_tgat_last_stats": (C.c_int, [c_void, c_i64p]),
     "flid_tgn_reset": (C.c_int, [C.POINTER(TgnState), c_void, C.c_int, C.c_int, c_void]),
     "flid_tgn_rebuild": (C.c_int, [c_void, C.POINTER(TgnState), C.POINTER(GruWeights), c_void, c_void]),

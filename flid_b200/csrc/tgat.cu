@@ -442,6 +442,7 @@ int tgat_embed_ids(flid_tgat* m, const flid_graph* g, const float* node_feat, co
         FLID_CUDA(cudaMemcpyAsync(w_times + o[L], times + r0, sizeof(double) * nc, cudaMemcpyDeviceToDevice, st));
         // top-down sampling
         for (int l = L; l >= 1; --l) {
+            ProfScope prof(m, PROF_SAMPLE, st);
             level_sample_kernel<<<(unsigned)ceil_div(c[l] * 32, 256), 256, 0, st>>>(
                 g->indptr, g->adj, g->ts, w_ids + o[l], w_times + o[l], c[l], nf, k, w_nbr + o[l] * k,
                 w_eid + o[l] * k, w_dt + o[l] * k, l > 1 ? w_ids + o[l - 1] : nullptr,
@@ -464,6 +465,7 @@ int tgat_embed_ids(flid_tgat* m, const flid_graph* g, const float* node_feat, co
                 if (use_table) {
                     a.u_base = m->table.as<float>(), a.u_index = lids;
                 } else {
+                    ProfScope prof(m, PROF_QFOLD, st);
                     FLID_TRY(query_fold(m, 0, node_feat, lids, nl, U, st));
                     a.u_base = U, a.u_index = nullptr;
                 }
@@ -471,14 +473,23 @@ int tgat_embed_ids(flid_tgat* m, const flid_graph* g, const float* node_feat, co
                 self_base = node_feat, self_idx = lids;
             } else {
                 const float* hprev = w_h + ho[l - 1] * m->dn;  // [c[l-1], dn]: first nl rows = self, then nl*k nbr rows
-                FLID_TRY(query_fold(m, l - 1, hprev, nullptr, nl, U, st));
+                {
+                    ProfScope prof(m, PROF_QFOLD, st);
+                    FLID_TRY(query_fold(m, l - 1, hprev, nullptr, nl, U, st));
+                }
                 a.u_base = U, a.u_index = nullptr;
                 a.hrow_base = hprev, a.hrow_by_id = 0, a.hrow_offset = nl;
                 self_base = hprev, self_idx = nullptr;
             }
-            FLID_TRY(launch_attn(a, m->H, st));
+            {
+                ProfScope prof(m, PROF_ATTN, st);
+                FLID_TRY(launch_attn(a, m->H, st));
+            }
             float* dst = (l == L) ? out + r0 * m->dn : w_h + ho[l] * m->dn;
-            FLID_TRY(output_chain(m, l - 1, nl, Z, self_base, self_idx, node_feat, lids, O, A, Hd, dst, st));
+            {
+                ProfScope prof(m, PROF_OUT, st);
+                FLID_TRY(output_chain(m, l - 1, nl, Z, self_base, self_idx, node_feat, lids, O, A, Hd, dst, st));
+            }
             evals += nl;
         }
     }
@@ -522,6 +533,7 @@ void flid_tgat_free(flid_tgat* m) {
         cudaFree(l.mfoldT), cudaFree(l.u0), cudaFree(l.wvoT), cudaFree(l.res_b), cudaFree(l.ln_w), cudaFree(l.ln_b);
         cudaFree(l.fc1_w), cudaFree(l.fc1_b), cudaFree(l.fc2_w), cudaFree(l.fc2_b);
     }
+    for (auto e : m->prof_ev) cudaEventDestroy(e);
     flid::DevBuf* bufs[] = {&m->raw_q, &m->raw_k, &m->raw_v, &m->raw_r, &m->table, &m->ws_ids, &m->ws_times,
                             &m->ws_nbr, &m->ws_eid, &m->ws_dt, &m->ws_h, &m->ws_u, &m->ws_z, &m->ws_o,
                             &m->ws_a, &m->ws_hd, &m->ws_misc, &m->ws_rid, &m->ws_rt, &m->ws_bad};
@@ -638,6 +650,29 @@ int flid_tgat_set_chunk_targets(flid_tgat* m, int64_t max_layer1_targets) {
     using namespace flid;
     FLID_REQUIRE(m && max_layer1_targets > 0, "flid_tgat_set_chunk_targets: bad argument");
     m->max_l1_targets = max_layer1_targets;
+    return FLID_OK;
+}
+
+int flid_tgat_profile(flid_tgat* m, int enable) {
+    using namespace flid;
+    FLID_REQUIRE(m != nullptr, "flid_tgat_profile: null handle");
+    m->prof_on = enable != 0;
+    m->prof_used = 0;
+    return FLID_OK;
+}
+
+int flid_tgat_profile_read(flid_tgat* m, double ms[4], int64_t launches[4]) {
+    using namespace flid;
+    FLID_REQUIRE(m && ms && launches, "flid_tgat_profile_read: null argument");
+    for (int c = 0; c < PROF_CLASSES; ++c) ms[c] = 0.0, launches[c] = 0;
+    FLID_CUDA(cudaDeviceSynchronize());
+    for (size_t s = 0; s + 1 < m->prof_used; s += 2) {
+        float t = 0.f;
+        FLID_CUDA(cudaEventElapsedTime(&t, m->prof_ev[s], m->prof_ev[s + 1]));
+        ms[m->prof_cls[s / 2]] += t;
+        launches[m->prof_cls[s / 2]] += 1;
+    }
+    m->prof_used = 0;
     return FLID_OK;
 }
 

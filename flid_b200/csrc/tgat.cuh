@@ -31,6 +31,11 @@ struct flid_tgat {
     flid::DevBuf ws_ids, ws_times, ws_nbr, ws_eid, ws_dt, ws_h, ws_u, ws_z, ws_o, ws_a, ws_hd, ws_misc;
     flid::DevBuf ws_rid, ws_rt, ws_bad;  // root conversion staging
     int64_t stats[4] = {0, 0, 0, 0};
+    // optional per-kernel-class CUDA-event timing (bench.py's roofline numbers)
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_ev;  // pairs (begin, end)
+    std::vector<int> prof_cls;
+    size_t prof_used = 0;
 };
 
 namespace flid {
@@ -39,5 +44,29 @@ namespace flid {
 int tgat_embed_ids(flid_tgat* m, const flid_graph* g, const float* node_feat, const float* edge_feat,
                    const int32_t* ids, const double* times, int64_t n_f64, int64_t n, int k, float* out,
                    cudaStream_t st);
-int tgat_workspace_bytes(const flid_tgat* m);
+
+// classes for the event timer
+enum { PROF_SAMPLE = 0, PROF_QFOLD = 1, PROF_ATTN = 2, PROF_OUT = 3, PROF_CLASSES = 4 };
+struct ProfScope {
+    flid_tgat* m;
+    cudaStream_t st;
+    size_t slot = 0;
+    bool on;
+    ProfScope(flid_tgat* m_, int cls, cudaStream_t st_) : m(m_), st(st_), on(m_->prof_on) {
+        if (!on) return;
+        if (m->prof_used + 2 > m->prof_ev.size()) {
+            cudaEvent_t a, b;
+            cudaEventCreate(&a), cudaEventCreate(&b);
+            m->prof_ev.push_back(a), m->prof_ev.push_back(b);
+            m->prof_cls.push_back(cls);
+        }
+        slot = m->prof_used;
+        m->prof_cls[slot / 2] = cls;
+        m->prof_used += 2;
+        cudaEventRecord(m->prof_ev[slot], st);
+    }
+    ~ProfScope() {
+        if (on) cudaEventRecord(m->prof_ev[slot + 1], st);
+    }
+};
 }  // namespace flid

@@ -118,6 +118,13 @@ int flid_tgat_embed(flid_tgat* m, const flid_graph* g, const float* node_feat, c
 /* upper bound on layer-1 targets processed per internal chunk (workspace ~7 KB per target;
  * default 65536).  Results do not depend on it.                                        */
 int flid_tgat_set_chunk_targets(flid_tgat* m, int64_t max_layer1_targets);
+/* Per-kernel-class CUDA-event timing of flid_tgat_embed (events recorded on the launch
+ * stream around each launch group).  Classes: 0 level sampler, 1 query-fold GEMM,
+ * 2 attention stream, 3 out-projection + LayerNorm + MergeLayer chain.
+ * flid_tgat_profile_read synchronises, returns summed milliseconds / event-pair counts
+ * since the last read, and resets.                                                      */
+int flid_tgat_profile(flid_tgat* m, int enable);
+int flid_tgat_profile_read(flid_tgat* m, double ms[4], int64_t launches[4]);
 /* bytes / counts of the last flid_tgat_embed call, for the roofline report:
  * stats[0] = attention evaluations, stats[1] = valid (non-padded) neighbour slots gathered,
  * stats[2] = sampler queries, stats[3] = workspace bytes currently held.             */
