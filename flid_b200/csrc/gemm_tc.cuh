@@ -1,0 +1,43 @@
+// tcgen05 (5th-gen tensor core) "NT" GEMM with fp32-grade accuracy via the 3xTF32 split:
+//   C[m, n] = sum_k A[m, k] * W[n, k] (+ bias[n]) (ReLU),  A = [A0 | A1] (two column segments,
+//   each optionally row-gathered), accumulators in TMEM, operands staged in shared memory in
+//   the UMMA canonical K-major no-swizzle layout.
+// x = hi + lo with hi = x & 0xffffe000 (exact tf32), lo = x - hi (exact fp32, truncated to tf32
+// by the tensor core): A.W ~= Ahi.Whi + Ahi.Wlo + Alo.Whi, error ~2^-21 relative per product.
+#pragma once
+#include "common.cuh"
+
+namespace flid {
+
+constexpr int TC_KC = 16;  // K floats per pipeline stage (2 UMMA k-steps of 8)
+
+// weight pre-split into (hi, lo) and pre-tiled so that one (n-block, k-chunk) stage is a
+// single contiguous copy:  [n_block][k_chunk][half][c4 = 4][n_tile][4 floats]
+struct TcWeight {
+    float* buf = nullptr;
+    int N = 0, K = 0, n_tile = 0, n_blocks = 0, k_chunks = 0;
+    size_t bytes() const { return (size_t)n_blocks * k_chunks * 2 * 4 * n_tile * 16; }
+};
+
+struct TcGemmArgs {
+    const float* A0 = nullptr;
+    int64_t lda0 = 0;
+    const int32_t* idx0 = nullptr;
+    int w0 = 0;  // columns [0, w0) come from segment 0
+    const float* A1 = nullptr;
+    int64_t lda1 = 0;
+    const int32_t* idx1 = nullptr;
+    int w1 = 0;  // columns [w0, w0 + w1) from segment 1 (0 = unused)
+    float* C = nullptr;
+    int64_t ldc = 0;
+    const float* bias = nullptr;
+    int64_t M = 0;
+    int relu = 0;
+};
+
+// (re)build the tiled hi/lo image of W[N, K] (row stride ldw); allocates w->buf on first use
+int tc_prepare_weight(const float* W, int64_t ldw, int N, int K, TcWeight* w, cudaStream_t st);
+void tc_free_weight(TcWeight* w);
+int tc_gemm(const TcGemmArgs& g, const TcWeight& w, cudaStream_t st);
+
+}  // namespace flid

@@ -40,6 +40,13 @@ int flid_abi_version(void);
 /* number of kernel launches issued through this library since load (for bench.py's gpu_launches) */
 int64_t flid_launch_count(void);
 
+/* Self-test hook for the two projection-GEMM back ends (used by tests/ only):
+ * C[M,N] = [A0 | A1][M, w0+w1] . W[N, w0+w1]^T + bias, optional ReLU, optional int32 row gather
+ * of A0.  backend 0 = fp32 SIMT, 1 = tcgen05 3xTF32.  All pointers device.              */
+int flid_debug_gemm(int backend, const float* a0, int64_t lda0, const int32_t* idx0, int w0, const float* a1,
+                    int64_t lda1, int w1, const float* w, int64_t ldw, const float* bias, float* c, int64_t ldc,
+                    int64_t m, int n, int relu, flid_stream stream);
+
 /* ------------------------------------------------------------------ graph ---------
  * Replaces get_neighbor_sampler (utils/utils.py:283-302) + NeighborSampler.__init__
  * (utils/utils.py:73-110): undirected adjacency, per node stably sorted by timestamp.
