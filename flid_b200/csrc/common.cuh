@@ -92,28 +92,39 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
-// cos(x) for any float32 x with |x| < ~3e9, accurate to ~1 ulp.
-// The time-encoder argument fma(dt, w, b) reaches 1e6..1e8 rad, where
-// __cosf is useless and cosf() takes the slow Payne-Hanek path.  The argument is
-// reduced in float64 with a two-term pi/2 (error < 1e-16 * |n|), then the Cephes
-// single-precision minimax polynomials on [-pi/4, pi/4] are evaluated in float32.
+// cos(x) for any float32 x with |x| < ~3e9, absolute error <= ~2e-7.
+// The time-encoder argument fma(dt, w, b) reaches 1e6..1e8 rad, where __cosf is
+// useless and cosf() takes the slow Payne-Hanek path.  cos(x) = (-1)^k cos(x - k*pi):
+//   |x| < 4e6 : float32 only.  k = rint(x / pi) by the 1.5*2^23 magic-number trick (one FMA, no
+//               conversion instructions), r = x - k*pi by a two-term Cody-Waite with FMAs.
+//               fl(1/pi) is only good to 2^-25, so k can be off by one next to a half-way point
+//               and |r| can reach ~1.75; the even Taylor polynomial to r^12 is good to 4e-8 there.
+//   otherwise : the reduction is done in float64.
 __device__ __forceinline__ float cos_accurate(float x) {
-    const double xd = (double)x;
-    const double q = rint(xd * 0.63661977236758134308);
-    double r = fma(q, -1.57079632679489655800, xd);
-    r = fma(q, -6.12323399573676603587e-17, r);
-    const int n = (int)q;
-    const float rf = (float)r;
+    float rf;
+    int n;
+    if (fabsf(x) < 4.0e6f) {
+        const float t = fmaf(x, 0.31830987334251404f, 12582912.0f);
+        n = __float_as_int(t);
+        const float kf = t - 12582912.0f;
+        rf = fmaf(kf, -3.1415927410125732f, x);
+        rf = fmaf(kf, 8.742277657347586e-08f, rf);
+    } else {
+        const double xd = (double)x;
+        const double q = rint(xd * 0.31830988618379067154);
+        double r = fma(q, -3.14159265358979311600, xd);
+        r = fma(q, -1.2246467991473532072e-16, r);
+        n = (int)q;
+        rf = (float)r;
+    }
     const float r2 = rf * rf;
-    float sp = fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f);
-    sp = fmaf(sp, r2, -1.6666654611e-1f);
-    const float s = fmaf(rf * r2, sp, rf);
-    float cp = fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f);
-    cp = fmaf(cp, r2, 4.166664568298827e-2f);
-    const float c = fmaf(r2 * r2, cp, fmaf(r2, -0.5f, 1.0f));
-    float v = (n & 1) ? s : c;
-    // n mod 4: 0 -> c, 1 -> -s, 2 -> -c, 3 -> s
-    return (((n + 1) & 2) != 0) ? -v : v;
+    float p = fmaf(r2, 2.08767569878680990e-9f, -2.75573192239858907e-7f);
+    p = fmaf(p, r2, 2.48015873015873016e-5f);
+    p = fmaf(p, r2, -1.38888888888888889e-3f);
+    p = fmaf(p, r2, 4.16666666666666667e-2f);
+    p = fmaf(p, r2, -0.5f);
+    p = fmaf(p, r2, 1.0f);
+    return __int_as_float(__float_as_int(p) ^ (n << 31));  // (-1)^k
 }
 
 // TimeEncoder (models/modules.py:35-38): cos of the single-rounded fma(dt, w, b).

@@ -16,19 +16,20 @@
 
 #include <algorithm>
 
+#include "attn.cuh"
 #include "gemm.cuh"
 
 namespace flid {
 
 // ------------------------------------------------------------------ weight folding
 __global__ void fold_qk_kernel(const float* __restrict__ wq, const float* __restrict__ wk, int qd, int kd, int H,
-                               float scale, float* __restrict__ mfoldT) {
+                               double scale, float* __restrict__ mfoldT) {
     const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (idx >= (int64_t)H * kd * qd) return;
     const int row = (int)(idx / qd), b = (int)(idx % qd), h = row / kd, a = row % kd, hd = qd / H;
     double s = 0.0;
     for (int r = 0; r < hd; ++r) s += (double)wk[(int64_t)(h * hd + r) * kd + a] * (double)wq[(int64_t)(h * hd + r) * qd + b];
-    mfoldT[idx] = (float)(s * (double)scale);
+    mfoldT[idx] = (float)(s * scale);
 }
 
 __global__ void fold_vo_kernel(const float* __restrict__ wr, const float* __restrict__ wv, int qd, int kd, int H,
@@ -113,196 +114,6 @@ __global__ void __launch_bounds__(256) level_sample_kernel(
     }
     __syncthreads();
     if (threadIdx.x == 0 && s_cnt) atomicAdd(valid_slots, (unsigned long long)s_cnt);
-}
-
-// ------------------------------------------------------------------ attention stream
-struct AttnArgs {
-    const float* u_base;      // query folds, row stride zw
-    const int32_t* u_index;   // nullable: u row of target i is u_base[u_index[i]] (per-node table) else row i
-    const float* hrow_base;   // neighbour layer-(l-1) rows, row stride dn
-    int hrow_by_id;           // 1: row = neighbour id (feature table); 0: row = hrow_offset + i*k + j
-    int64_t hrow_offset;
-    const float* edge_feat;   // [E+1, de]
-    const int32_t* nbr;       // [n, k]
-    const int32_t* eid;
-    const float* dt;
-    const float* time_w;
-    const float* time_b;
-    float* z;                 // [n, zw]
-    int64_t n;
-    int k, dn, de, T;
-};
-
-// One warp per target.  Lane l owns float4 chunks l, l+32, ... of the concatenated
-// [node row | edge row] and time channels l, l+32, ...; u and the z accumulators live in
-// registers; neighbour rows stream through registers once (online softmax), the next
-// slot's row is in flight while the current one is reduced.
-template <int H, int NV, int TC>
-__global__ void __launch_bounds__(256) attn_kernel(AttnArgs a) {
-    const int lane = threadIdx.x & 31;
-    const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    if (i >= a.n) return;
-    const int k = a.k, dn = a.dn, de = a.de, T = a.T;
-    const int nv4 = dn >> 2, tot4 = (dn + de) >> 2, kd = dn + de + T;
-
-    int nb_l = 0, e_l = 0;
-    float dt_l = 0.f;
-    if (lane < k) {
-        nb_l = __ldg(a.nbr + i * k + lane);
-        e_l = __ldg(a.eid + i * k + lane);
-        dt_l = __ldg(a.dt + i * k + lane);
-    }
-    const unsigned valid = __ballot_sync(FULL, lane < k && nb_l != 0);
-    const bool all_masked = (valid == 0u);  // softmax over k equal -1e10 scores == uniform 1/k
-    unsigned todo = all_masked ? (k >= 32 ? FULL : ((1u << k) - 1u)) : valid;
-
-    const float* u = a.u_base + (a.u_index ? (int64_t)__ldg(a.u_index + i) : i) * (int64_t)(H * kd);
-    float4 uh[H][NV];
-    float ut[H][TC], tw[TC], tb[TC];
-#pragma unroll
-    for (int h = 0; h < H; ++h) {
-#pragma unroll
-        for (int r = 0; r < NV; ++r) {
-            const int f = lane + 32 * r;
-            uh[h][r] = f < tot4 ? __ldg(reinterpret_cast<const float4*>(u + h * kd) + f) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int r = 0; r < TC; ++r) {
-            const int c = lane + 32 * r;
-            ut[h][r] = c < T ? __ldg(u + h * kd + dn + de + c) : 0.f;
-        }
-    }
-#pragma unroll
-    for (int r = 0; r < TC; ++r) {
-        const int c = lane + 32 * r;
-        tw[r] = c < T ? __ldg(a.time_w + c) : 0.f;
-        tb[r] = c < T ? __ldg(a.time_b + c) : 0.f;
-    }
-
-    float4 acc[H][NV];
-    float acct[H][TC], mx[H], den[H];
-#pragma unroll
-    for (int h = 0; h < H; ++h) {
-        mx[h] = -INFINITY, den[h] = 0.f;
-#pragma unroll
-        for (int r = 0; r < NV; ++r) acc[h][r] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int r = 0; r < TC; ++r) acct[h][r] = 0.f;
-    }
-
-    auto load_slot = [&](int j, float4 (&x)[NV]) {
-        const int nb = __shfl_sync(FULL, nb_l, j);
-        const int e = __shfl_sync(FULL, e_l, j);
-        const float* hrow = a.hrow_base + (a.hrow_by_id ? (int64_t)nb : a.hrow_offset + i * k + j) * (int64_t)dn;
-        const float* erow = a.edge_feat + (int64_t)e * de;
-#pragma unroll
-        for (int r = 0; r < NV; ++r) {
-            const int f = lane + 32 * r;
-            if (f < nv4)
-                x[r] = __ldg(reinterpret_cast<const float4*>(hrow) + f);
-            else if (f < tot4)
-                x[r] = __ldg(reinterpret_cast<const float4*>(erow) + (f - nv4));
-            else
-                x[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    };
-
-    float4 xc[NV], xn[NV];
-    int j = __ffs(todo) - 1;
-    todo &= todo - 1;
-    load_slot(j, xc);
-    while (true) {
-        int jn = -1;
-        if (todo) {
-            jn = __ffs(todo) - 1;
-            todo &= todo - 1;
-            load_slot(jn, xn);
-        }
-        const float d = __shfl_sync(FULL, dt_l, j);
-        float xt[TC];
-#pragma unroll
-        for (int r = 0; r < TC; ++r) xt[r] = (lane + 32 * r < T) ? time_channel(d, tw[r], tb[r]) : 0.f;
-#pragma unroll
-        for (int h = 0; h < H; ++h) {
-            float s = -1e10f;  // masked_fill value (models/modules.py:220)
-            if (!all_masked) {
-                float p = 0.f;
-#pragma unroll
-                for (int r = 0; r < NV; ++r) {
-                    p = fmaf(xc[r].x, uh[h][r].x, p);
-                    p = fmaf(xc[r].y, uh[h][r].y, p);
-                    p = fmaf(xc[r].z, uh[h][r].z, p);
-                    p = fmaf(xc[r].w, uh[h][r].w, p);
-                }
-#pragma unroll
-                for (int r = 0; r < TC; ++r) p = fmaf(xt[r], ut[h][r], p);
-                s = warp_sum(p);
-            }
-            const float mnew = fmaxf(mx[h], s);
-            const float corr = expf(mx[h] - mnew);
-            const float w = expf(s - mnew);
-            mx[h] = mnew;
-            den[h] = fmaf(den[h], corr, w);
-#pragma unroll
-            for (int r = 0; r < NV; ++r) {
-                acc[h][r].x = fmaf(acc[h][r].x, corr, w * xc[r].x);
-                acc[h][r].y = fmaf(acc[h][r].y, corr, w * xc[r].y);
-                acc[h][r].z = fmaf(acc[h][r].z, corr, w * xc[r].z);
-                acc[h][r].w = fmaf(acc[h][r].w, corr, w * xc[r].w);
-            }
-#pragma unroll
-            for (int r = 0; r < TC; ++r) acct[h][r] = fmaf(acct[h][r], corr, w * xt[r]);
-        }
-        if (jn < 0) break;
-#pragma unroll
-        for (int r = 0; r < NV; ++r) xc[r] = xn[r];
-        j = jn;
-    }
-
-    float* z = a.z + i * (int64_t)(H * kd);
-#pragma unroll
-    for (int h = 0; h < H; ++h) {
-        const float inv = 1.0f / den[h];
-#pragma unroll
-        for (int r = 0; r < NV; ++r) {
-            const int f = lane + 32 * r;
-            if (f < tot4)
-                reinterpret_cast<float4*>(z + h * kd)[f] =
-                    make_float4(acc[h][r].x * inv, acc[h][r].y * inv, acc[h][r].z * inv, acc[h][r].w * inv);
-        }
-#pragma unroll
-        for (int r = 0; r < TC; ++r) {
-            const int c = lane + 32 * r;
-            if (c < T) z[h * kd + dn + de + c] = acct[h][r] * inv;
-        }
-    }
-}
-
-template <int H>
-static int launch_attn_h(const AttnArgs& a, int nv, int tc, cudaStream_t st) {
-    const unsigned blocks = (unsigned)ceil_div(a.n * 32, 256);
-#define FLID_ATTN_CASE(NV_, TC_)                              \
-    if (nv <= NV_ && tc <= TC_) {                             \
-        attn_kernel<H, NV_, TC_><<<blocks, 256, 0, st>>>(a);  \
-        FLID_LAUNCH_CHECK();                                  \
-        return FLID_OK;                                       \
-    }
-    FLID_ATTN_CASE(3, 4)
-    FLID_ATTN_CASE(6, 4)
-#undef FLID_ATTN_CASE
-    set_error("attention kernel: unsupported feature widths (node+edge floats <= 768, time dim <= 128)");
-    return FLID_ERR_INVALID;
-}
-
-static int launch_attn(const AttnArgs& a, int H, cudaStream_t st) {
-    if (a.n <= 0) return FLID_OK;
-    const int nv = (int)ceil_div((a.dn + a.de) / 4, 32), tc = (int)ceil_div(a.T, 32);
-    switch (H) {
-        case 1: return launch_attn_h<1>(a, nv, tc, st);
-        case 2: return launch_attn_h<2>(a, nv, tc, st);
-        case 4: return launch_attn_h<4>(a, nv, tc, st);
-        default: set_error("attention kernel: num_heads must be 1, 2 or 4 (got %d)", H); return FLID_ERR_INVALID;
-    }
 }
 
 // ------------------------------------------------------------------ residual + LayerNorm
@@ -538,7 +349,7 @@ int flid_tgat_create(int node_dim, int edge_dim, int time_dim, int num_layers, i
     FLID_REQUIRE((node_dim + time_dim) % num_heads == 0,
                  "The sum of node_feat_dim and time_feat_dim should be divided by num_heads!");
     FLID_REQUIRE(num_heads == 1 || num_heads == 2 || num_heads == 4, "flid_tgat_create: num_heads must be 1, 2 or 4");
-    FLID_REQUIRE(node_dim + edge_dim <= 768 && time_dim <= 128 && node_dim + time_dim <= 512,
+    FLID_REQUIRE(node_dim + edge_dim <= (num_heads == 4 ? 384 : 768) && time_dim <= 128 && node_dim + time_dim <= 512,
                  "flid_tgat_create: feature widths above kernel limits");
     flid_tgat* m = new flid_tgat();
     m->dn = node_dim, m->de = edge_dim, m->T = time_dim, m->L = num_layers, m->H = num_heads;
@@ -580,7 +391,8 @@ int flid_tgat_set_weights(flid_tgat* m, const float* time_w, const float* time_b
     te0_kernel<<<(unsigned)ceil_div(T, 128), 128, 0, st>>>(m->time_w, m->time_b, T, m->te0);
     FLID_LAUNCH_CHECK();
     // python: head_dim ** -0.5 is a float64; multiplying a float32 tensor by it uses its float32 value
-    const float scale = (float)pow((double)m->hd, -0.5);
+    // the stream kernel evaluates softmax with exp2, so log2(e) is folded into the scale here
+    const double scale = (double)(float)pow((double)m->hd, -0.5) * 1.4426950408889634074;
     for (int l = 0; l < m->L; ++l) {
         const flid_tgat_layer_weights& w = layers_host[l];
         LayerDev& d = m->layers[l];
