@@ -60,7 +60,8 @@ __global__ void __launch_bounds__(128, (H * NV <= 6) ? 3 : 2) attn_kernel(AttnAr
     const bool all_masked = (valid == 0u);
     unsigned todo = all_masked ? (k >= 32 ? FULL : ((1u << k) - 1u)) : valid;
     // per-slot row numbers (lane j holds slot j)
-    const int64_t hrow_l = a.hrow_by_id ? (int64_t)nb_l : a.hrow_offset + i * k + lane;
+    int64_t hrow_l = a.hrow_by_id ? (int64_t)nb_l : a.hrow_offset + i * k + lane;
+    if (a.hrow_idx != nullptr && lane < k) hrow_l = (int64_t)__ldg(a.hrow_idx + i * k + lane);
     const int hlo = (int)(hrow_l & 0xffffffff), hhi = (int)(hrow_l >> 32);
 
     const float* u = a.u_base + (a.u_index ? (int64_t)__ldg(a.u_index + i) : i) * (int64_t)(H * kd);

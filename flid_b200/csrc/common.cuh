@@ -100,23 +100,7 @@ __device__ __forceinline__ float warp_max(float v) {
 //               fl(1/pi) is only good to 2^-25, so k can be off by one next to a half-way point
 //               and |r| can reach ~1.75; the even Taylor polynomial to r^12 is good to 4e-8 there.
 //   otherwise : the reduction is done in float64.
-__device__ __forceinline__ float cos_accurate(float x) {
-    float rf;
-    int n;
-    if (fabsf(x) < 4.0e6f) {
-        const float t = fmaf(x, 0.31830987334251404f, 12582912.0f);
-        n = __float_as_int(t);
-        const float kf = t - 12582912.0f;
-        rf = fmaf(kf, -3.1415927410125732f, x);
-        rf = fmaf(kf, 8.742277657347586e-08f, rf);
-    } else {
-        const double xd = (double)x;
-        const double q = rint(xd * 0.31830988618379067154);
-        double r = fma(q, -3.14159265358979311600, xd);
-        r = fma(q, -1.2246467991473532072e-16, r);
-        n = (int)q;
-        rf = (float)r;
-    }
+__device__ __forceinline__ float cos_poly_signed(float rf, int n) {
     const float r2 = rf * rf;
     float p = fmaf(r2, 2.08767569878680990e-9f, -2.75573192239858907e-7f);
     p = fmaf(p, r2, 2.48015873015873016e-5f);
@@ -126,6 +110,22 @@ __device__ __forceinline__ float cos_accurate(float x) {
     p = fmaf(p, r2, 1.0f);
     return __int_as_float(__float_as_int(p) ^ (n << 31));  // (-1)^k
 }
+constexpr float COS_FAST_LIMIT = 4.0e6f;
+__device__ __forceinline__ float cos_fast(float x) {  // |x| < COS_FAST_LIMIT
+    const float t = fmaf(x, 0.31830987334251404f, 12582912.0f);
+    const float kf = t - 12582912.0f;
+    float rf = fmaf(kf, -3.1415927410125732f, x);
+    rf = fmaf(kf, 8.742277657347586e-08f, rf);
+    return cos_poly_signed(rf, __float_as_int(t));
+}
+__device__ __forceinline__ float cos_slow(float x) {
+    const double xd = (double)x;
+    const double q = rint(xd * 0.31830988618379067154);
+    double r = fma(q, -3.14159265358979311600, xd);
+    r = fma(q, -1.2246467991473532072e-16, r);
+    return cos_poly_signed((float)r, (int)q);
+}
+__device__ __forceinline__ float cos_accurate(float x) { return fabsf(x) < COS_FAST_LIMIT ? cos_fast(x) : cos_slow(x); }
 
 // TimeEncoder (models/modules.py:35-38): cos of the single-rounded fma(dt, w, b).
 __device__ __forceinline__ float time_channel(float dt, float w, float b) { return cos_accurate(fmaf(dt, w, b)); }

@@ -43,7 +43,14 @@ __global__ void fold_vo_kernel(const float* __restrict__ wr, const float* __rest
     wvoT[idx] = (float)s;
 }
 
-__global__ void te0_kernel(const float* __restrict__ w, const float* __restrict__ b, int T, float* __restrict__ te0) {
+// te0 = cos(b) (time encoding of dt = 0) and the bounds the stream kernel uses to pick its cosine path
+__global__ void te0_kernel(const float* __restrict__ w, const float* __restrict__ b, int T, float* __restrict__ te0,
+                           float* __restrict__ bound) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        float wm = 0.f, bm = 0.f;
+        for (int c = 0; c < T; ++c) wm = fmaxf(wm, fabsf(w[c])), bm = fmaxf(bm, fabsf(b[c]));
+        bound[0] = wm, bound[1] = bm;
+    }
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < T) te0[c] = time_channel(0.f, w[c], b[c]);
 }
@@ -81,7 +88,8 @@ __global__ void __launch_bounds__(256) level_sample_kernel(
     const int64_t* __restrict__ indptr, const int2* __restrict__ adj, const double* __restrict__ ts,
     const int32_t* __restrict__ ids, const double* __restrict__ times, int64_t n, int64_t n_f64, int k,
     int32_t* __restrict__ nbr, int32_t* __restrict__ eid, float* __restrict__ dt, int32_t* __restrict__ next_ids,
-    double* __restrict__ next_times, unsigned long long* __restrict__ valid_slots) {
+    double* __restrict__ next_times, int32_t* __restrict__ pos, int32_t pad_pos,
+    unsigned long long* __restrict__ valid_slots) {
     __shared__ int s_cnt;
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
@@ -98,16 +106,17 @@ __global__ void __launch_bounds__(256) level_sample_kernel(
         const bool f64_rule = q < n_f64;
         const float tf = (float)t;
         for (int j = lane; j < k; j += 32) {
-            int a = 0, e = 0;
+            int a = 0, e = 0, pp = pad_pos;
             float tsf = 0.f;
             if (j >= k - cnt) {
                 const int64_t p = cut - k + j;
                 const int2 ne = __ldg(adj + p);
-                a = ne.x, e = ne.y, tsf = (float)__ldg(ts + p);
+                a = ne.x, e = ne.y, tsf = (float)__ldg(ts + p), pp = (int32_t)p;
             }
             const float d = f64_rule ? (float)(t - (double)tsf) : (tf - tsf);
             const int64_t o = q * k + j;
             nbr[o] = a, eid[o] = e, dt[o] = d;
+            if (pos) pos[o] = pp;
             if (next_ids) next_ids[n + o] = a, next_times[n + o] = (double)tsf;
         }
         if (lane == 0) atomicAdd(&s_cnt, cnt);
@@ -280,7 +289,7 @@ int tgat_embed_ids(flid_tgat* m, const flid_graph* g, const float* node_feat, co
             level_sample_kernel<<<(unsigned)ceil_div(c[l] * 32, 256), 256, 0, st>>>(
                 g->indptr, g->adj, g->ts, w_ids + o[l], w_times + o[l], c[l], nf, k, w_nbr + o[l] * k,
                 w_eid + o[l] * k, w_dt + o[l] * k, l > 1 ? w_ids + o[l - 1] : nullptr,
-                l > 1 ? w_times + o[l - 1] : nullptr, d_valid);
+                l > 1 ? w_times + o[l - 1] : nullptr, nullptr, 0, d_valid);
             FLID_LAUNCH_CHECK();
             queries += c[l];
         }
@@ -291,7 +300,7 @@ int tgat_embed_ids(flid_tgat* m, const flid_graph* g, const float* node_feat, co
             AttnArgs a;
             a.edge_feat = edge_feat;
             a.nbr = w_nbr + o[l] * k, a.eid = w_eid + o[l] * k, a.dt = w_dt + o[l] * k;
-            a.time_w = m->time_w, a.time_b = m->time_b;
+            a.time_w = m->time_w, a.time_b = m->time_b, a.time_bound = m->time_bound;
             a.z = Z, a.n = nl, a.k = k, a.dn = m->dn, a.de = m->de, a.T = m->T;
             const float* self_base;
             const int32_t* self_idx;
@@ -329,7 +338,163 @@ int tgat_embed_ids(flid_tgat* m, const flid_graph* g, const float* node_feat, co
     }
     m->stats[0] = evals;
     m->stats[2] = queries;
-    m->stats[1] = -1;  // fetched lazily by flid_tgat_last_stats
+    m->stats[1] = -1, m->valid_mult = 1;  // fetched lazily by flid_tgat_last_stats
+    return FLID_OK;
+}
+
+
+// ------------------------------------------------------------------ layer memo
+// h_l(a, float32(ts)) of a neighbour slot depends only on the CSR entry it was sampled from
+// (owner -> a at ts): the reference recomputes it for every root whose neighbourhood holds
+// that entry (models/TGAT.py:108-113), a bulk pass needs it once.  memo_l is a table
+// [M + 1, dn] indexed by CSR position (row M = the padded slot's query (node 0, t = 0.0)).
+// A target's k neighbour rows are then k consecutive table rows, and the layer-(l-1)
+// feature of target p itself is memo_{l-1}[p] (same key).
+__global__ void memo_targets_kernel(const int2* __restrict__ adj, const double* __restrict__ ts, int64_t M,
+                                    int64_t lo, int64_t n, int32_t* __restrict__ ids, double* __restrict__ times) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t p = lo + i;
+    ids[i] = p < M ? __ldg(adj + p).x : 0;
+    times[i] = p < M ? (double)(float)__ldg(ts + p) : 0.0;  // the float32 neighbour time the recursion passes down
+}
+
+struct LayerCall {
+    int64_t n = 0;
+    const int32_t* ids = nullptr;  // target node ids [n]
+    const int32_t *nbr = nullptr, *eid = nullptr, *pos = nullptr;
+    const float* dt = nullptr;
+    const float* hrow_base = nullptr;  // layer-(l-1) rows of the neighbours: by node id (pos == nullptr) or by CSR position
+    const float* self_base = nullptr;  // layer-(l-1) rows of the targets
+    const int32_t* self_idx = nullptr; // nullable: self row i = self_base[self_idx[i]]
+    bool u_from_table = false;         // layer 1 with the cached per-node query fold
+    float* out = nullptr;              // [n, dn]
+};
+
+// one attention layer (1-based `layer`) for n targets: query fold -> stream -> out chain
+static int layer_eval(flid_tgat* m, int layer, const LayerCall& c, const float* node_feat, const float* edge_feat,
+                      int k, cudaStream_t st) {
+    float *U = m->ws_u.as<float>(), *Z = m->ws_z.as<float>(), *O = m->ws_o.as<float>(), *A = m->ws_a.as<float>(),
+          *Hd = m->ws_hd.as<float>();
+    AttnArgs a;
+    a.edge_feat = edge_feat;
+    a.nbr = c.nbr, a.eid = c.eid, a.dt = c.dt;
+    a.time_w = m->time_w, a.time_b = m->time_b, a.time_bound = m->time_bound;
+    a.z = Z, a.n = c.n, a.k = k, a.dn = m->dn, a.de = m->de, a.T = m->T;
+    a.hrow_base = c.hrow_base, a.hrow_by_id = c.pos ? 0 : 1, a.hrow_offset = 0, a.hrow_idx = c.pos;
+    if (c.u_from_table) {
+        a.u_base = m->table.as<float>(), a.u_index = c.ids;
+    } else {
+        ProfScope prof(m, PROF_QFOLD, st);
+        FLID_TRY(query_fold(m, layer - 1, c.self_base, c.self_idx, c.n, U, st));
+        a.u_base = U, a.u_index = nullptr;
+    }
+    {
+        ProfScope prof(m, PROF_ATTN, st);
+        FLID_TRY(launch_attn(a, m->H, st));
+    }
+    ProfScope prof(m, PROF_OUT, st);
+    return output_chain(m, layer - 1, c.n, Z, c.self_base, c.self_idx, node_feat, c.ids, O, A, Hd, c.out, st);
+}
+
+static int reserve_layer_ws(flid_tgat* m, int64_t n, int k, bool need_u) {
+    FLID_TRY(m->ws_ids.reserve(sizeof(int32_t) * n));
+    FLID_TRY(m->ws_times.reserve(sizeof(double) * n));
+    FLID_TRY(m->ws_nbr.reserve(sizeof(int32_t) * n * k));
+    FLID_TRY(m->ws_eid.reserve(sizeof(int32_t) * n * k));
+    FLID_TRY(m->ws_dt.reserve(sizeof(float) * n * k));
+    FLID_TRY(m->ws_pos.reserve(sizeof(int32_t) * n * k));
+    if (need_u) FLID_TRY(m->ws_u.reserve(sizeof(float) * n * m->zw));
+    FLID_TRY(m->ws_z.reserve(sizeof(float) * n * m->zw));
+    FLID_TRY(m->ws_o.reserve(sizeof(float) * n * m->qd));
+    FLID_TRY(m->ws_a.reserve(sizeof(float) * n * m->qd));
+    FLID_TRY(m->ws_hd.reserve(sizeof(float) * n * m->dn));
+    FLID_TRY(m->ws_misc.reserve(64));
+    return FLID_OK;
+}
+
+int tgat_memo_build(flid_tgat* m, const flid_graph* g, const float* node_feat, const float* edge_feat, int k, int level,
+                    const float* memo_prev, int64_t row_lo, int64_t row_hi, float* memo_out, cudaStream_t st) {
+    const int64_t M = g->num_entries;
+    const bool use_table = level == 1 && (m->table_src == node_feat && m->table_rows > 0);
+    const int64_t chunk = std::max<int64_t>(1, m->max_l1_targets);
+    FLID_TRY(reserve_layer_ws(m, std::min(chunk, row_hi - row_lo), k, !use_table));
+    unsigned long long* d_valid = m->ws_misc.as<unsigned long long>();
+    FLID_CUDA(cudaMemsetAsync(d_valid, 0, sizeof(unsigned long long), st));
+    int32_t* w_ids = m->ws_ids.as<int32_t>();
+    double* w_times = m->ws_times.as<double>();
+    int64_t evals = 0;
+    for (int64_t c0 = row_lo; c0 < row_hi; c0 += chunk) {
+        const int64_t n = std::min(chunk, row_hi - c0);
+        {
+            ProfScope prof(m, PROF_SAMPLE, st);
+            memo_targets_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(g->adj, g->ts, M, c0, n, w_ids, w_times);
+            FLID_LAUNCH_CHECK();
+            level_sample_kernel<<<(unsigned)ceil_div(n * 32, 256), 256, 0, st>>>(
+                g->indptr, g->adj, g->ts, w_ids, w_times, n, 0, k, m->ws_nbr.as<int32_t>(), m->ws_eid.as<int32_t>(),
+                m->ws_dt.as<float>(), nullptr, nullptr, level > 1 ? m->ws_pos.as<int32_t>() : nullptr, (int32_t)M,
+                d_valid);
+            FLID_LAUNCH_CHECK();
+        }
+        LayerCall c;
+        c.n = n, c.ids = w_ids;
+        c.nbr = m->ws_nbr.as<int32_t>(), c.eid = m->ws_eid.as<int32_t>(), c.dt = m->ws_dt.as<float>();
+        if (level == 1) {
+            c.hrow_base = node_feat, c.self_base = node_feat, c.self_idx = w_ids, c.u_from_table = use_table;
+        } else {
+            c.pos = m->ws_pos.as<int32_t>();
+            c.hrow_base = memo_prev, c.self_base = memo_prev + c0 * m->dn;
+        }
+        c.out = memo_out + c0 * m->dn;
+        FLID_TRY(layer_eval(m, level, c, node_feat, edge_feat, k, st));
+        evals += n;
+    }
+    m->stats[0] = evals, m->stats[2] = evals, m->stats[1] = -1, m->valid_mult = 1;
+    return FLID_OK;
+}
+
+// roots with the lower layers memoised: one sampling pass, L attention evaluations per root
+int tgat_embed_memo(flid_tgat* m, const flid_graph* g, const float* node_feat, const float* edge_feat,
+                    const float* const* memo, const int32_t* ids, const double* times, int64_t n_f64, int64_t n, int k,
+                    float* out, cudaStream_t st) {
+    const int L = m->L;
+    const int64_t M = g->num_entries;
+    const bool use_table = (m->table_src == node_feat && m->table_rows > 0);
+    const int64_t chunk = std::max<int64_t>(1, m->max_l1_targets);
+    const int64_t nmax = std::min(chunk, n);
+    FLID_TRY(reserve_layer_ws(m, nmax, k, L > 1 || !use_table));
+    if (L > 1) FLID_TRY(m->ws_h.reserve(sizeof(float) * 2 * nmax * m->dn));
+    unsigned long long* d_valid = m->ws_misc.as<unsigned long long>();
+    FLID_CUDA(cudaMemsetAsync(d_valid, 0, sizeof(unsigned long long), st));
+    int64_t evals = 0;
+    for (int64_t r0 = 0; r0 < n; r0 += chunk) {
+        const int64_t nc = std::min(chunk, n - r0);
+        const int64_t nf = std::max<int64_t>(0, std::min(nc, n_f64 - r0));
+        {
+            ProfScope prof(m, PROF_SAMPLE, st);
+            level_sample_kernel<<<(unsigned)ceil_div(nc * 32, 256), 256, 0, st>>>(
+                g->indptr, g->adj, g->ts, ids + r0, times + r0, nc, nf, k, m->ws_nbr.as<int32_t>(),
+                m->ws_eid.as<int32_t>(), m->ws_dt.as<float>(), nullptr, nullptr,
+                L > 1 ? m->ws_pos.as<int32_t>() : nullptr, (int32_t)M, d_valid);
+            FLID_LAUNCH_CHECK();
+        }
+        float* hbuf[2] = {m->ws_h.as<float>(), L > 1 ? m->ws_h.as<float>() + nmax * m->dn : nullptr};
+        for (int l = 1; l <= L; ++l) {
+            LayerCall c;
+            c.n = nc, c.ids = ids + r0;
+            c.nbr = m->ws_nbr.as<int32_t>(), c.eid = m->ws_eid.as<int32_t>(), c.dt = m->ws_dt.as<float>();
+            if (l == 1) {
+                c.hrow_base = node_feat, c.self_base = node_feat, c.self_idx = ids + r0, c.u_from_table = use_table;
+            } else {
+                c.pos = m->ws_pos.as<int32_t>();
+                c.hrow_base = memo[l - 2], c.self_base = hbuf[l & 1];
+            }
+            c.out = (l == L) ? out + r0 * m->dn : hbuf[(l + 1) & 1];
+            FLID_TRY(layer_eval(m, l, c, node_feat, edge_feat, k, st));
+            evals += nc;
+        }
+    }
+    m->stats[0] = evals, m->stats[2] = n, m->stats[1] = -1, m->valid_mult = L;
     return FLID_OK;
 }
 
@@ -364,7 +529,7 @@ int flid_tgat_create(int node_dim, int edge_dim, int time_dim, int num_layers, i
 
 void flid_tgat_free(flid_tgat* m) {
     if (!m) return;
-    cudaFree(m->time_w), cudaFree(m->time_b), cudaFree(m->te0);
+    cudaFree(m->time_w), cudaFree(m->time_b), cudaFree(m->te0), cudaFree(m->time_bound);
     for (auto& l : m->layers) {
         cudaFree(l.mfoldT), cudaFree(l.u0), cudaFree(l.wvoT), cudaFree(l.res_b), cudaFree(l.ln_w), cudaFree(l.ln_b);
         cudaFree(l.fc1_w), cudaFree(l.fc1_b), cudaFree(l.fc2_w), cudaFree(l.fc2_b);
@@ -374,7 +539,7 @@ void flid_tgat_free(flid_tgat* m) {
     for (auto e : m->prof_ev) cudaEventDestroy(e);
     flid::DevBuf* bufs[] = {&m->raw_q, &m->raw_k, &m->raw_v, &m->raw_r, &m->table, &m->ws_ids, &m->ws_times,
                             &m->ws_nbr, &m->ws_eid, &m->ws_dt, &m->ws_h, &m->ws_u, &m->ws_z, &m->ws_o,
-                            &m->ws_a, &m->ws_hd, &m->ws_misc, &m->ws_rid, &m->ws_rt, &m->ws_bad};
+                            &m->ws_a, &m->ws_hd, &m->ws_misc, &m->ws_rid, &m->ws_rt, &m->ws_bad, &m->ws_pos};
     for (auto* b : bufs) b->release();
     delete m;
 }
@@ -388,7 +553,8 @@ int flid_tgat_set_weights(flid_tgat* m, const float* time_w, const float* time_b
     FLID_TRY(dev_copy(&m->time_w, time_w, T, st));
     FLID_TRY(dev_copy(&m->time_b, time_b, T, st));
     if (!m->te0) FLID_CUDA(cudaMalloc((void**)&m->te0, sizeof(float) * T));
-    te0_kernel<<<(unsigned)ceil_div(T, 128), 128, 0, st>>>(m->time_w, m->time_b, T, m->te0);
+    if (!m->time_bound) FLID_CUDA(cudaMalloc((void**)&m->time_bound, sizeof(float) * 2));
+    te0_kernel<<<(unsigned)ceil_div(T, 128), 128, 0, st>>>(m->time_w, m->time_b, T, m->te0, m->time_bound);
     FLID_LAUNCH_CHECK();
     // python: head_dim ** -0.5 is a float64; multiplying a float32 tensor by it uses its float32 value
     // the stream kernel evaluates softmax with exp2, so log2(e) is folded into the scale here
@@ -489,6 +655,57 @@ int flid_tgat_embed(flid_tgat* m, const flid_graph* g, const float* node_feat, c
     return FLID_OK;
 }
 
+int flid_tgat_memo_build(flid_tgat* m, const flid_graph* g, const float* node_feat, const float* edge_feat, int k,
+                         int level, const float* memo_prev, int64_t row_lo, int64_t row_hi, float* memo_out,
+                         flid_stream stream) {
+    using namespace flid;
+    FLID_REQUIRE(m && g && node_feat && edge_feat && memo_out, "flid_tgat_memo_build: null argument");
+    FLID_REQUIRE(m->have_weights, "flid_tgat_memo_build: weights not set");
+    FLID_REQUIRE(k > 0 && k <= 32, "flid_tgat_memo_build: num_neighbors must be in 1..32");
+    FLID_REQUIRE(level >= 1 && level <= m->L, "flid_tgat_memo_build: level %d outside 1..%d", level, m->L);
+    FLID_REQUIRE(level == 1 || memo_prev != nullptr, "flid_tgat_memo_build: level %d needs the level-%d table", level,
+                 level - 1);
+    FLID_REQUIRE(g->num_entries < 0x7fffffffLL, "flid_tgat_memo_build: more than 2^31 adjacency entries");
+    FLID_REQUIRE(row_lo >= 0 && row_lo <= row_hi && row_hi <= g->num_entries + 1,
+                 "flid_tgat_memo_build: row range outside [0, entries + 1]");
+    if (row_lo == row_hi) return FLID_OK;
+    return tgat_memo_build(m, g, node_feat, edge_feat, k, level, memo_prev, row_lo, row_hi, memo_out,
+                           (cudaStream_t)stream);
+}
+
+int flid_tgat_embed_memo(flid_tgat* m, const flid_graph* g, const float* node_feat, const float* edge_feat,
+                         const float* const* memo_tables_host, const int64_t* nodes, const double* times,
+                         int times_are_f32, int64_t n, int k, float* out, flid_stream stream) {
+    using namespace flid;
+    FLID_REQUIRE(m && g && node_feat && edge_feat, "flid_tgat_embed_memo: null argument");
+    FLID_REQUIRE(m->have_weights, "flid_tgat_embed_memo: weights not set");
+    FLID_REQUIRE(k > 0, "Number of sampled neighbors for each node should be greater than 0!");
+    FLID_REQUIRE(k <= 32, "flid_tgat_embed_memo: num_neighbors above 32 is not supported by the attention kernel");
+    FLID_REQUIRE(m->L == 1 || memo_tables_host != nullptr, "flid_tgat_embed_memo: memo tables missing");
+    for (int l = 0; l + 1 < m->L; ++l)
+        FLID_REQUIRE(memo_tables_host[l] != nullptr, "flid_tgat_embed_memo: memo table of layer %d is null", l + 1);
+    if (n <= 0) return FLID_OK;
+    FLID_REQUIRE(nodes && times && out, "flid_tgat_embed_memo: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    FLID_TRY(m->ws_rid.reserve(sizeof(int32_t) * n));
+    FLID_TRY(m->ws_rt.reserve(sizeof(double) * n));
+    FLID_TRY(m->ws_bad.reserve(sizeof(int)));
+    FLID_CUDA(cudaMemsetAsync(m->ws_bad.p, 0, sizeof(int), st));
+    roots_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(nodes, times, n, g->num_nodes, m->ws_rid.as<int32_t>(),
+                                                            m->ws_rt.as<double>(), m->ws_bad.as<int>());
+    FLID_LAUNCH_CHECK();
+    FLID_TRY(tgat_embed_memo(m, g, node_feat, edge_feat, memo_tables_host, m->ws_rid.as<int32_t>(),
+                             m->ws_rt.as<double>(), times_are_f32 ? 0 : n, n, k, out, st));
+    int hbad = 0;
+    FLID_CUDA(cudaMemcpyAsync(&hbad, m->ws_bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    FLID_CUDA(cudaStreamSynchronize(st));
+    if (hbad) {
+        set_error("flid_tgat_embed_memo: node id outside the graph");
+        return FLID_ERR_RANGE;
+    }
+    return FLID_OK;
+}
+
 int flid_tgat_set_chunk_targets(flid_tgat* m, int64_t max_layer1_targets) {
     using namespace flid;
     FLID_REQUIRE(m && max_layer1_targets > 0, "flid_tgat_set_chunk_targets: bad argument");
@@ -527,9 +744,9 @@ int flid_tgat_last_stats(const flid_tgat* m, int64_t stats[4]) {
         FLID_CUDA(cudaDeviceSynchronize());
         FLID_CUDA(cudaMemcpy(&hv, m->ws_misc.p, sizeof(hv), cudaMemcpyDeviceToHost));
     }
-    stats[0] = m->stats[0], stats[1] = (int64_t)hv, stats[2] = m->stats[2];
+    stats[0] = m->stats[0], stats[1] = (int64_t)hv * m->valid_mult, stats[2] = m->stats[2];
     const flid::DevBuf* bufs[] = {&m->table, &m->ws_ids, &m->ws_times, &m->ws_nbr, &m->ws_eid, &m->ws_dt, &m->ws_h,
-                                  &m->ws_u,  &m->ws_z,   &m->ws_o,     &m->ws_a,   &m->ws_hd};
+                                  &m->ws_u,  &m->ws_z,   &m->ws_o,     &m->ws_a,   &m->ws_hd, &m->ws_pos};
     int64_t b = 0;
     for (auto* x : bufs) b += (int64_t)x->cap;
     stats[3] = b;

@@ -22,7 +22,7 @@ struct flid_tgat {
     int qd = 0, kd = 0, hd = 0, zw = 0;  // zw = H * kd
     bool have_weights = false;
     bool use_tc = true;  // projection GEMMs on tcgen05 (3xTF32); false = fp32 SIMT (FLID_GEMM=simt)
-    float *time_w = nullptr, *time_b = nullptr, *te0 = nullptr;
+    float *time_w = nullptr, *time_b = nullptr, *te0 = nullptr, *time_bound = nullptr;
     std::vector<flid::LayerDev> layers;
     flid::DevBuf raw_q, raw_k, raw_v, raw_r;  // staging for the fold
     // cached layer-1 query fold per node-table row
@@ -31,9 +31,10 @@ struct flid_tgat {
     flid::DevBuf table;
     // workspace
     int64_t max_l1_targets = 65536;
-    flid::DevBuf ws_ids, ws_times, ws_nbr, ws_eid, ws_dt, ws_h, ws_u, ws_z, ws_o, ws_a, ws_hd, ws_misc;
+    flid::DevBuf ws_ids, ws_times, ws_nbr, ws_eid, ws_dt, ws_h, ws_u, ws_z, ws_o, ws_a, ws_hd, ws_misc, ws_pos;
     flid::DevBuf ws_rid, ws_rt, ws_bad;  // root conversion staging
     int64_t stats[4] = {0, 0, 0, 0};
+    int64_t valid_mult = 1;  // attention evaluations that consume each sampled neighbour list
     // optional per-kernel-class CUDA-event timing (bench.py's roofline numbers)
     bool prof_on = false;
     std::vector<cudaEvent_t> prof_ev;  // pairs (begin, end)

@@ -38,6 +38,23 @@ def all_gather_rows(local: torch.Tensor, num_items: int, per: int, dist_mod=None
     return out[:num_items]
 
 
+def prepare_layer_memo(model, num_roots: int, num_neighbors: int, sharded: bool):
+    """Build the layer memo (flid_tgat_memo_build) ahead of a bulk pass when it pays off:
+    a pass over ``num_roots`` root queries costs sum_l (1+k)^(L-l) attention evaluations per
+    root without it and L per root plus (L-1)(entries+1) with it.  When ``sharded`` every rank
+    builds a contiguous slice of the table rows and the slices are all-gathered (NCCL)."""
+    build = getattr(model, "build_layer_memo", None)
+    depth = getattr(model, "num_layers", 1)
+    if build is None or depth < 2 or not model._engine.memo_mode or not (0 < num_neighbors <= 32):
+        return False
+    plain = sum((1 + num_neighbors) ** (depth - l) for l in range(1, depth + 1))
+    cost = (depth - 1) * (model.neighbor_sampler.num_entries + 1)
+    if num_roots * (plain - depth) < cost:
+        return False
+    build(num_neighbors, sharded=sharded)
+    return True
+
+
 def embed_events(model, src_node_ids, dst_node_ids, node_interact_times, num_neighbors: int = 20, sharded=None):
     """Embeddings of every event's source and destination node at the event time:
     two float32 [E, dn] device tensors, rows in event order (what the reference's full pass
@@ -53,9 +70,11 @@ def embed_events(model, src_node_ids, dst_node_ids, node_interact_times, num_nei
     e = len(src)
     if not sharded or world == 1:
         with torch.no_grad():
+            prepare_layer_memo(model, 2 * e, num_neighbors, False)
             return model.compute_src_dst_node_temporal_embeddings(src, dst, t, num_neighbors)
     lo, hi, per = shard_bounds(e, rank, world)
     with torch.no_grad():
+        prepare_layer_memo(model, 2 * e, num_neighbors, True)
         a, b = model.compute_src_dst_node_temporal_embeddings(src[lo:hi], dst[lo:hi], t[lo:hi], num_neighbors)
     both = torch.stack([a, b], dim=1)                       # [n_local, 2, dn]: one collective for both halves
     full = all_gather_rows(both, e, per, dist)
@@ -87,6 +106,7 @@ def e_step_pass(model, decoder: MLPClassifier, src_node_ids, dst_node_ids, node_
         dst = np.asarray(dst_node_ids)
         t = np.asarray(node_interact_times)
         with torch.no_grad():
+            prepare_layer_memo(model, 2 * e, num_neighbors, True)
             a, b = model.compute_src_dst_node_temporal_embeddings(src[lo:hi], dst[lo:hi], t[lo:hi], num_neighbors)
         l_loc, p_loc = emit_pseudo_labels(decoder, a)
         packed = torch.cat([l_loc.to(torch.float32).unsqueeze(1), p_loc], dim=1)     # [n_local, 1 + C]

@@ -75,6 +75,9 @@ class _Engine:
         self.handles = {}    # depth -> c_void_p
         self.versions = {}   # depth -> parameter fingerprint
         self.tables = {}     # depth -> (data_ptr, rows) of the cached node table
+        self.memo = {}       # depth -> (key, [level tables])   layer memo of bulk passes
+        self.memo_mode = "auto"   # False | True | "auto"
+        self.served = {}     # depth -> (key, root queries answered without a memo)
 
     def close(self):
         for h in self.handles.values():
@@ -117,6 +120,7 @@ class _Engine:
             _lib.check(lib.flid_tgat_set_weights(h, _lib.ptr(tw), _lib.ptr(tb), layers, _lib.stream()))
             self.versions[depth] = fp
             self.tables.pop(depth, None)
+            self.memo.pop(depth, None)
         return h
 
     def ensure_table(self, depth, h, node_feat):
@@ -128,8 +132,79 @@ class _Engine:
             self.tables[depth] = key
 
 
+def _memo_key(engine, depth, sampler, node_feat, edge_feat, k):
+    return (engine.versions.get(depth), int(sampler.handle.value or 0), node_feat.data_ptr(), node_feat._version,
+            edge_feat.data_ptr(), edge_feat._version, int(k))
+
+
+def build_layer_memo(engine, depth, time_encoder, conv_layers, merge_layers, sampler, node_feat, edge_feat,
+                     num_neighbors, sharded=False):
+    """Fill the layer memo (include/flid_b200.h, flid_tgat_memo_build) for levels 1..depth-1.
+    ``sharded`` (torch.distributed initialised, called by every rank): each rank builds a
+    contiguous range of table rows and the ranges are all-gathered in place over NCCL."""
+    if depth < 2:
+        return None
+    device = node_feat.device
+    lib = _lib.lib()
+    with torch.cuda.device(device):
+        h = engine.handle(depth, time_encoder, conv_layers, merge_layers, device)
+        engine.ensure_table(depth, h, node_feat)
+        key = _memo_key(engine, depth, sampler, node_feat, edge_feat, num_neighbors)
+        have = engine.memo.get(depth)
+        if have is not None and have[0] == key:
+            return have[1]
+        engine.memo.pop(depth, None)
+        rows = sampler.num_entries + 1
+        rank, world, dist = 0, 1, None
+        if sharded:
+            import torch.distributed as dist
+            rank, world = dist.get_rank(), dist.get_world_size()
+        per = -(-rows // world)
+        dn = node_feat.shape[1]
+        tables = []
+        prev = None
+        for level in range(1, depth):
+            t = torch.empty((per * world, dn), dtype=torch.float32, device=device)
+            lo, hi = min(rank * per, rows), min((rank + 1) * per, rows)
+            _lib.check(lib.flid_tgat_memo_build(h, sampler.handle, _lib.ptr(node_feat), _lib.ptr(edge_feat),
+                                                int(num_neighbors), level, _lib.ptr(prev), lo, hi, _lib.ptr(t),
+                                                _lib.stream()))
+            if world > 1:
+                dist.all_gather_into_tensor(t, t[rank * per:(rank + 1) * per])     # in place
+            tables.append(t)
+            prev = t
+        engine.memo[depth] = (key, tables)
+        return tables
+
+
+def _memo_for_call(engine, depth, time_encoder, conv_layers, merge_layers, sampler, node_feat, edge_feat, k, n):
+    """The valid memo tables for this call, or None.  In "auto" mode the memo is built once
+    the root queries answered at this weight version would have paid for it: a plain root
+    costs sum_l (1+k)^(depth-l) attention evaluations, a memoised one ``depth``, the build
+    (depth-1) * (entries+1) (break-even rule, at most 2x the optimum)."""
+    mode = engine.memo_mode
+    if depth < 2 or not mode:
+        return None
+    key = _memo_key(engine, depth, sampler, node_feat, edge_feat, k)
+    have = engine.memo.get(depth)
+    if have is not None and have[0] == key:
+        return have[1]
+    if mode == "auto":
+        skey, served = engine.served.get(depth, (None, 0))
+        if skey != key:
+            served = 0
+        plain = sum((1 + k) ** (depth - l) for l in range(1, depth + 1))
+        build_cost = (depth - 1) * (sampler.num_entries + 1)
+        need = build_cost * node_feat.shape[1] * 4
+        free = torch.cuda.mem_get_info(node_feat.device)[0]
+        if (served + n) * (plain - depth) < build_cost or need > free // 2:
+            engine.served[depth] = (key, served + n)
+            return None
+    return build_layer_memo(engine, depth, time_encoder, conv_layers, merge_layers, sampler, node_feat, edge_feat, k)
+
+
 def embed_roots(engine, depth, time_encoder, conv_layers, merge_layers, sampler, node_feat, edge_feat,
-                node_ids, node_interact_times, num_neighbors, use_table=True):
+                node_ids, node_interact_times, num_neighbors, use_table=True, use_memo=False):
     """Shared by TGAT and MemoryModel: n root queries -> float32 [n, dn] on the device."""
     device = node_feat.device
     _lib.require_cuda(device)
@@ -155,9 +230,19 @@ def embed_roots(engine, depth, time_encoder, conv_layers, merge_layers, sampler,
             d_times = _lib.to_device(t, np.float64, device, "e_times")   # float32 -> float64 is exact
         n = d_nodes.shape[0]
         out = torch.empty((n, node_feat.shape[1]), dtype=torch.float32, device=device)
-        _lib.check(_lib.lib().flid_tgat_embed(h, sampler.handle, _lib.ptr(node_feat), _lib.ptr(edge_feat),
-                                              _lib.ptr(d_nodes), _lib.ptr(d_times), is32, n, int(num_neighbors),
-                                              _lib.ptr(out), _lib.stream()))
+        memo = None
+        if use_memo and 0 < int(num_neighbors) <= 32:
+            memo = _memo_for_call(engine, depth, time_encoder, conv_layers, merge_layers, sampler, node_feat,
+                                  edge_feat, int(num_neighbors), n)
+        if memo is not None:
+            tabs = (C.c_void_p * len(memo))(*[t.data_ptr() for t in memo])
+            _lib.check(_lib.lib().flid_tgat_embed_memo(h, sampler.handle, _lib.ptr(node_feat), _lib.ptr(edge_feat),
+                                                       tabs, _lib.ptr(d_nodes), _lib.ptr(d_times), is32, n,
+                                                       int(num_neighbors), _lib.ptr(out), _lib.stream()))
+        else:
+            _lib.check(_lib.lib().flid_tgat_embed(h, sampler.handle, _lib.ptr(node_feat), _lib.ptr(edge_feat),
+                                                  _lib.ptr(d_nodes), _lib.ptr(d_times), is32, n, int(num_neighbors),
+                                                  _lib.ptr(out), _lib.stream()))
     return out
 
 
@@ -219,7 +304,22 @@ class TGAT(nn.Module):
         self._check_mode()
         return embed_roots(self._engine, current_layer_num, self.time_encoder, self.temporal_conv_layers,
                            self.merge_layers, self.neighbor_sampler, self.node_raw_features, self.edge_raw_features,
-                           node_ids, node_interact_times, num_neighbors)
+                           node_ids, node_interact_times, num_neighbors, use_memo=True)
+
+    # ---- layer memo of bulk passes (not in the reference API; see include/flid_b200.h) ----
+    def set_layer_memo(self, mode="auto"):
+        """False: never memoise; True: build on the next call; "auto" (default): build once the
+        root queries answered at the current weights would have paid for the build."""
+        assert mode in (False, True, "auto")
+        self._engine.memo_mode = mode
+        if not mode:
+            self._engine.memo.clear()
+
+    def build_layer_memo(self, num_neighbors: int = 20, sharded: bool = False):
+        """Explicitly (re)build the memo for full-depth calls; collective when ``sharded``."""
+        return build_layer_memo(self._engine, self.num_layers, self.time_encoder, self.temporal_conv_layers,
+                                self.merge_layers, self.neighbor_sampler, self.node_raw_features,
+                                self.edge_raw_features, num_neighbors, sharded)
 
     def set_neighbor_sampler(self, neighbor_sampler: NeighborSampler):
         """models/TGAT.py:146-155."""

@@ -122,6 +122,26 @@ int flid_tgat_refresh_node_rows(flid_tgat* m, const float* node_feat, const int3
 int flid_tgat_embed(flid_tgat* m, const flid_graph* g, const float* node_feat, const float* edge_feat,
                     const int64_t* nodes, const double* times, int times_are_f32, int64_t n, int k, float* out,
                     flid_stream stream);
+/* Layer memo for bulk passes (the E/200-iteration loops of PTCL/E_step.py:305-352,
+ * PTCL/M_step.py:454-509): the layer-l embedding of a neighbour slot, h_l(nbr, float32(ts)),
+ * is a function of the adjacency entry it was sampled from, yet models/TGAT.py:108-113
+ * recomputes it for every root whose neighbourhood contains the entry.  memo_l is a
+ * caller-owned float32 table [entries + 1, dn] indexed by CSR position (row `entries` is the
+ * padded slot's query (node 0, t = 0.0)); it is valid while weights, graph, feature tables
+ * and k are unchanged.  flid_tgat_memo_build fills rows [row_lo, row_hi) of level `level`
+ * (1-based, needs the complete level-1 table `memo_prev` when level > 1; null for level 1),
+ * so ranks can build disjoint row ranges and all-gather them.  Rows are bit-identical to
+ * what flid_tgat_embed computes internally for the same slot.                            */
+int flid_tgat_memo_build(flid_tgat* m, const flid_graph* g, const float* node_feat, const float* edge_feat, int k,
+                         int level, const float* memo_prev, int64_t row_lo, int64_t row_hi, float* memo_out,
+                         flid_stream stream);
+/* flid_tgat_embed with the lower num_layers-1 levels read from memo tables
+ * (memo_tables_host = host array of num_layers-1 device pointers, level 1 first): one
+ * sampling pass and num_layers attention evaluations per root instead of
+ * sum_l (1+k)^(L-l).  Same results, bit for bit.                                         */
+int flid_tgat_embed_memo(flid_tgat* m, const flid_graph* g, const float* node_feat, const float* edge_feat,
+                         const float* const* memo_tables_host, const int64_t* nodes, const double* times,
+                         int times_are_f32, int64_t n, int k, float* out, flid_stream stream);
 /* upper bound on layer-1 targets processed per internal chunk (workspace ~7 KB per target;
  * default 65536).  Results do not depend on it.                                        */
 int flid_tgat_set_chunk_targets(flid_tgat* m, int64_t max_layer1_targets);
@@ -133,7 +153,7 @@ int flid_tgat_set_chunk_targets(flid_tgat* m, int64_t max_layer1_targets);
 int flid_tgat_profile(flid_tgat* m, int enable);
 int flid_tgat_profile_read(flid_tgat* m, double ms[4], int64_t launches[4]);
 /* bytes / counts of the last flid_tgat_embed call, for the roofline report:
- * stats[0] = attention evaluations, stats[1] = valid (non-padded) neighbour slots gathered,
+ * stats[0] = attention evaluations, stats[1] = valid (non-padded) neighbour rows gathered by them,
  * stats[2] = sampler queries, stats[3] = workspace bytes currently held.             */
 int flid_tgat_last_stats(const flid_tgat* m, int64_t stats[4]);
 

@@ -138,11 +138,12 @@ def test_sampler_random_graphs_bit_exact(shape):
 
 
 # ===================================================================== TGAT
-def tgat_pair(nf, ef, src, dst, eid, ts, L, heads, p):
+def tgat_pair(nf, ef, src, dst, eid, ts, L, heads, p, memo=False):
     s = make_sampler(src, dst, eid, ts, nf.shape[0] - 1)
     m = flid_b200.TGAT(nf, ef, s, 100, L, heads, 0.1, DEV).to(DEV)
     m.load_state_dict({k: v for k, v in p.items() if not k.startswith("_")})
     m.eval()
+    m.set_layer_memo(memo)
     return m, s
 
 
@@ -150,12 +151,13 @@ TGAT_CASES = [("L1_k20", 1, 20, 2, 0.0, False), ("L2_k5", 2, 5, 2, 0.0, False), 
               ("L2_k7_zeros", 2, 7, 2, 0.3, True), ("L3_k3", 3, 3, 2, 0.2, False)]
 
 
+@pytest.mark.parametrize("memo", [False, True])
 @pytest.mark.parametrize("name,L,k,heads,bias,zeros", TGAT_CASES)
-def test_tgat_golden(name, L, k, heads, bias, zeros):
+def test_tgat_golden(name, L, k, heads, bias, zeros, memo):
     g = load("tgat.npz")
     src, dst, eid, ts, nf, ef = cases.small_stream(node_zeros=zeros)
     p = otgat.default_params(172, 172, 100, L, heads, seed=3, time_bias_scale=bias)
-    m, _ = tgat_pair(nf, ef, src, dst, eid, ts, L, heads, p)
+    m, _ = tgat_pair(nf, ef, src, dst, eid, ts, L, heads, p, memo)
     sel = g[name + "_sel"]
     with torch.no_grad():
         a, b = m.compute_src_dst_node_temporal_embeddings(src[sel], dst[sel], ts[sel], k)
@@ -223,6 +225,86 @@ def test_tgat_chunking_and_table_do_not_change_bits():
     assert torch.equal(a0, a1) and torch.equal(b0, b1) and torch.equal(a0, a2)
     st = m.last_stats()
     assert st[0] == 125 * 2 * 22 and st[2] == 125 * 2 * 22 and 0 < st[1] <= st[0] * 20
+
+
+@pytest.mark.parametrize("shape,L,k", [("wikipedia", 2, 20), ("dsub", 2, 30), ("fractional", 3, 4)])
+def test_tgat_layer_memo_is_bit_identical(shape, L, k):
+    """The memoised bulk path (one evaluation per adjacency entry and level, flid_tgat_embed_memo)
+    returns exactly the bits of the recursive path, for float64 roots and float32 roots, and
+    row ranges built separately (the multi-GPU split) give the same table."""
+    if shape == "fractional":
+        src, dst, eid, ts, nf, ef = cases.small_stream()
+        ts = ts + np.random.RandomState(5).rand(len(ts)) * 0.37 + 2.0 ** 24       # float32 rounding matters
+        ts.sort()
+        n_nodes = nf.shape[0] - 1
+    else:
+        g = synth.wikipedia_shape(seed=1, scale=0.03) if shape == "wikipedia" else synth.dsub_shape(seed=2, scale=0.03)
+        src, dst, eid, ts, nf, ef = (g.src_node_ids, g.dst_node_ids, g.edge_ids, g.node_interact_times,
+                                     g.node_raw_features, g.edge_raw_features)
+    p = otgat.default_params(172, 172, 100, L, 2, seed=11, time_bias_scale=0.25)
+    m, s = tgat_pair(nf, ef, src, dst, eid, ts, L, 2, p, memo=False)
+    e = len(src)
+    sel = np.arange(e - 300, e)
+    nodes = np.concatenate([src[sel], dst[sel]])
+    times = np.concatenate([ts[sel], ts[sel]])
+    with torch.no_grad():
+        plain64 = m.compute_node_temporal_embeddings(nodes, times, L, k)
+        plain32 = m.compute_node_temporal_embeddings(nodes, times.astype(np.float32), L, k)
+        m.set_layer_memo(True)
+        memo64 = m.compute_node_temporal_embeddings(nodes, times, L, k)
+        memo32 = m.compute_node_temporal_embeddings(nodes, times.astype(np.float32), L, k)
+    assert L in m._engine.memo
+    assert torch.equal(plain64, memo64) and torch.equal(plain32, memo32)
+    st = m.last_stats()
+    assert st[0] == len(nodes) * L and st[2] == len(nodes)
+    # split build == whole build
+    tables = m._engine.memo[L][1]
+    rows = s.num_entries + 1
+    h, lib = m._engine.handles[L], _lib.lib()
+    prev = None
+    for level, whole in enumerate(tables, start=1):
+        part = torch.full_like(whole, float("nan"))
+        for lo, hi in ((0, rows // 3), (rows // 3, rows - 1), (rows - 1, rows)):
+            _lib.check(lib.flid_tgat_memo_build(h, s.handle, _lib.ptr(m.node_raw_features), _lib.ptr(m.edge_raw_features),
+                                                k, level, _lib.ptr(prev), lo, hi, _lib.ptr(part), _lib.stream()))
+        assert torch.equal(part[:rows], whole[:rows])
+        prev = whole
+
+
+def test_tgat_layer_memo_auto_and_invalidation():
+    src, dst, eid, ts, nf, ef = cases.small_stream()
+    p = otgat.default_params(172, 172, 100, 2, 2, seed=3, time_bias_scale=0.1)
+    m, s = tgat_pair(nf, ef, src, dst, eid, ts, 2, 2, p, memo="auto")
+    o = osamp.OracleSampler.from_events(src, dst, eid, ts, nf.shape[0] - 1)
+    k = 6
+    need = (s.num_entries + 1) // ((1 + k) + 1 - 2) + 1          # break-even number of roots
+    sel = np.arange(len(src) - 40, len(src))
+    with torch.no_grad():
+        calls = 0
+        while 2 not in m._engine.memo:
+            a, _ = m.compute_src_dst_node_temporal_embeddings(src[sel], dst[sel], ts[sel], k)
+            calls += 1
+            assert calls * 80 <= need + 80, "auto mode never built the memo"
+        assert calls > 1, "auto mode built the memo before it paid off"
+        a2, _ = m.compute_src_dst_node_temporal_embeddings(src[sel], dst[sel], ts[sel], k)
+        assert torch.equal(a, a2)
+        # a different k, new weights or a new sampler must not reuse the table
+        b, _ = m.compute_src_dst_node_temporal_embeddings(src[sel], dst[sel], ts[sel], k + 1)
+        wb, _ = otgat.embed_src_dst(p, torch.from_numpy(nf), torch.from_numpy(ef), o, src[sel], dst[sel], ts[sel], 2, k + 1)
+        assert_fp32_close(b.cpu().numpy(), wb.numpy(), "memo, other k")
+        p2 = otgat.default_params(172, 172, 100, 2, 2, seed=4, time_bias_scale=0.2)
+        m.load_state_dict({kk: v for kk, v in p2.items() if not kk.startswith("_")})
+        m.set_layer_memo(True)
+        c, _ = m.compute_src_dst_node_temporal_embeddings(src[sel], dst[sel], ts[sel], k)
+        wc, _ = otgat.embed_src_dst(p2, torch.from_numpy(nf), torch.from_numpy(ef), o, src[sel], dst[sel], ts[sel], 2, k)
+        assert_fp32_close(c.cpu().numpy(), wc.numpy(), "memo after load_state_dict")
+        half = len(src) // 2
+        s2 = make_sampler(src[:half], dst[:half], eid[:half], ts[:half], nf.shape[0] - 1)
+        m.set_neighbor_sampler(s2)
+        o2 = osamp.OracleSampler.from_events(src[:half], dst[:half], eid[:half], ts[:half], nf.shape[0] - 1)
+        d, _ = m.compute_src_dst_node_temporal_embeddings(src[sel], dst[sel], ts[sel], k)
+        wd, _ = otgat.embed_src_dst(p2, torch.from_numpy(nf), torch.from_numpy(ef), o2, src[sel], dst[sel], ts[sel], 2, k)
+        assert_fp32_close(d.cpu().numpy(), wd.numpy(), "memo after set_neighbor_sampler")
 
 
 def test_tgat_weight_update_is_picked_up():
