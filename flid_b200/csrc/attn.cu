@@ -246,7 +246,7 @@ static int launch_attn_h(const AttnArgs& a, int nv, int tc, cudaStream_t st) {
     return FLID_ERR_INVALID;
 }
 
-int launch_attn(const AttnArgs& a, int H, cudaStream_t st) {
+int launch_attn_scalar(const AttnArgs& a, int H, cudaStream_t st) {
     if (a.n <= 0) return FLID_OK;
     const int nv = (int)ceil_div((a.dn + a.de) / 4, 32), tc = (int)ceil_div(a.T, 32);
     switch (H) {

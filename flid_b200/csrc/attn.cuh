@@ -23,6 +23,7 @@ struct AttnArgs {
     int k, dn, de, T;
 };
 
-int launch_attn(const AttnArgs& a, int H, cudaStream_t st);
+int launch_attn(const AttnArgs& a, int H, cudaStream_t st);         // packed-pair kernel (attn_packed.cu)
+int launch_attn_scalar(const AttnArgs& a, int H, cudaStream_t st);  // scalar-FFMA predecessor, FLID_ATTN=scalar
 
 }  // namespace flid
