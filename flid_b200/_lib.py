@@ -42,6 +42,9 @@ _SIGNATURES = {
     "flid_launch_count": (C.c_int64, []),
     "flid_debug_gemm": (C.c_int, [C.c_int, c_void, C.c_int64, c_void, C.c_int, c_void, C.c_int64, C.c_int, c_void,
                                   C.c_int64, c_void, c_void, C.c_int64, C.c_int64, C.c_int, C.c_int, c_void]),
+    "flid_debug_gemm_time": (C.c_int, [c_void, C.c_int64, c_void, C.c_int, c_void, C.c_int64, C.c_int, c_void,
+                                       C.c_int64, c_void, c_void, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int,
+                                       C.POINTER(C.c_float), c_void]),
     "flid_graph_build_events": (C.c_int, [c_void, c_void, c_void, c_void, C.c_int64, C.c_int64, C.c_int,
                                           C.POINTER(c_void), c_void]),
     "flid_graph_build_entries": (C.c_int, [c_void, c_void, c_void, c_void, C.c_int64, C.c_int64, C.c_int,

@@ -47,3 +47,32 @@ extern "C" int flid_debug_gemm(int backend, const float* a0, int64_t lda0, const
     tc_free_weight(&tw);
     return status;
 }
+
+// Timing hook for tools/gemm_probe.py: tile the weight once, launch the tcgen05 GEMM `reps`
+// times on `stream` and return the mean device time per launch (CUDA events on that stream).
+extern "C" int flid_debug_gemm_time(const float* a0, int64_t lda0, const int32_t* idx0, int w0, const float* a1,
+                                    int64_t lda1, int w1, const float* w, int64_t ldw, const float* bias, float* c,
+                                    int64_t ldc, int64_t m, int n, int relu, int reps, float* ms_per_launch,
+                                    flid_stream stream) {
+    using namespace flid;
+    FLID_REQUIRE(reps > 0 && ms_per_launch, "flid_debug_gemm_time: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    TcWeight tw;
+    FLID_TRY(tc_prepare_weight(w, ldw, n, w0 + w1, &tw, st));
+    TcGemmArgs g;
+    g.A0 = a0, g.lda0 = lda0, g.idx0 = idx0, g.w0 = w0, g.A1 = a1, g.lda1 = lda1, g.w1 = w1;
+    g.C = c, g.ldc = ldc, g.bias = bias, g.M = m, g.relu = relu;
+    int status = tc_gemm(g, tw, st);  // warm-up
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0), cudaEventCreate(&e1);
+    cudaEventRecord(e0, st);
+    for (int r = 0; r < reps && status == FLID_OK; ++r) status = tc_gemm(g, tw, st);
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    cudaEventElapsedTime(ms_per_launch, e0, e1);
+    *ms_per_launch /= (float)reps;
+    cudaEventDestroy(e0), cudaEventDestroy(e1);
+    tc_free_weight(&tw);
+    return status;
+}
+

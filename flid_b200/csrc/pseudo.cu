@@ -4,7 +4,10 @@
 // Reads 4*in bytes per event and writes 4*C + 8: HBM-bound and tiny next to the embedding.
 #include <math.h>
 
+#include <algorithm>
+
 #include "common.cuh"
+#include "gemm_tc.cuh"
 
 namespace flid {
 
@@ -129,6 +132,83 @@ __global__ void prob_filter_kernel(const float* __restrict__ probs, int64_t n, i
 
 static DevBuf g_ptrs;
 
+// Bulk path: fc1 (in -> hidden1, ReLU) runs on the tcgen05 GEMM, this kernel finishes the row:
+// fc2 (ReLU) -> fc3 -> softmax / argmax.  128 rows per block, the h1 tile and the two small
+// weight matrices staged in shared memory, one thread per row.
+constexpr int TAIL_ROWS = 128, MAXH2 = 32;
+__global__ void __launch_bounds__(TAIL_ROWS) pseudo_tail_kernel(flid_mlp_weights w, const float* __restrict__ h1,
+                                                                int64_t n, float* __restrict__ probs,
+                                                                int64_t* __restrict__ labels,
+                                                                float* __restrict__ logits) {
+    extern __shared__ float sm[];
+    const int H1 = w.hidden1, H2 = w.hidden2, C = w.num_classes, ld = H1 + 1;
+    float* tile = sm;                       // [TAIL_ROWS][H1 + 1]
+    float* w2 = tile + TAIL_ROWS * ld;      // [H2][H1]
+    float* b2 = w2 + H2 * H1;               // [H2]
+    float* w3 = b2 + H2;                    // [C][H2]
+    float* b3 = w3 + C * H2;                // [C]
+    const int64_t r0 = (int64_t)blockIdx.x * TAIL_ROWS;
+    const int rows = (int)min((int64_t)TAIL_ROWS, n - r0);
+    for (int i = threadIdx.x; i < rows * H1; i += TAIL_ROWS) tile[(i / H1) * ld + (i % H1)] = __ldg(h1 + r0 * H1 + i);
+    for (int i = threadIdx.x; i < H2 * H1; i += TAIL_ROWS) w2[i] = __ldg(w.fc2_w + i);
+    for (int i = threadIdx.x; i < H2; i += TAIL_ROWS) b2[i] = __ldg(w.fc2_b + i);
+    for (int i = threadIdx.x; i < C * H2; i += TAIL_ROWS) w3[i] = __ldg(w.fc3_w + i);
+    for (int i = threadIdx.x; i < C; i += TAIL_ROWS) b3[i] = __ldg(w.fc3_b + i);
+    __syncthreads();
+    if ((int)threadIdx.x >= rows) return;
+    const float* x = tile + threadIdx.x * ld;
+    float h2[MAXH2];
+#pragma unroll
+    for (int o = 0; o < MAXH2; ++o) {
+        h2[o] = 0.f;
+        if (o < H2) {
+            float p0 = 0.f, p1 = 0.f;
+            int c = 0;
+            for (; c + 1 < H1; c += 2) p0 = fmaf(x[c], w2[o * H1 + c], p0), p1 = fmaf(x[c + 1], w2[o * H1 + c + 1], p1);
+            if (c < H1) p0 = fmaf(x[c], w2[o * H1 + c], p0);
+            h2[o] = fmaxf(p0 + p1 + b2[o], 0.f);
+        }
+    }
+    float lg[MAXC];
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+        lg[c] = -INFINITY;
+        if (c < C) {
+            float p = b3[c];
+#pragma unroll
+            for (int o = 0; o < MAXH2; ++o)
+                if (o < H2) p = fmaf(h2[o], w3[c * H2 + o], p);
+            lg[c] = p;
+        }
+    }
+    const int64_t i = r0 + threadIdx.x;
+    float mx = -INFINITY;
+    int arg = 0;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c)
+        if (c < C && lg[c] > mx) mx = lg[c], arg = c;
+    float den = 0.f, e[MAXC];
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+        e[c] = c < C ? expf(lg[c] - mx) : 0.f;
+        den += e[c];
+    }
+    float pm = -1.f;  // argmax over the probabilities, first index on ties (as in pseudo_label_kernel)
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+        if (c < C) {
+            const float pr = e[c] / den;
+            if (pr > pm) pm = pr, arg = c;
+            probs[i * C + c] = pr;
+            if (logits) logits[i * C + c] = lg[c];
+        }
+    }
+    labels[i] = arg;
+}
+
+static TcWeight g_fc1;
+static DevBuf g_h1;
+
 }  // namespace flid
 
 extern "C" {
@@ -141,9 +221,31 @@ int flid_pseudo_label(const flid_mlp_weights* w, const float* emb, int64_t n, fl
                      w->num_classes > 0 && w->num_classes <= MAXC,
                  "flid_pseudo_label: unsupported decoder shape (input<=512, hidden1<=256, classes<=16)");
     if (n <= 0) return FLID_OK;
-    pseudo_label_kernel<<<(unsigned)ceil_div(n * 32, 256), 256, 0, (cudaStream_t)stream>>>(*w, emb, n, probs, labels,
-                                                                                         logits_or_null);
-    FLID_LAUNCH_CHECK();
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t tail_smem = sizeof(float) * ((size_t)TAIL_ROWS * (w->hidden1 + 1) + (size_t)w->hidden2 * (w->hidden1 + 1) +
+                                              (size_t)w->num_classes * (w->hidden2 + 1));
+    const bool bulk = n >= 4096 && (w->input_dim % 4) == 0 && (w->hidden1 % 4) == 0 && w->hidden2 <= MAXH2 &&
+                      tail_smem <= 48 * 1024;
+    if (!bulk) {  // per-batch calls (B = 200): one warp per row, no workspace
+        pseudo_label_kernel<<<(unsigned)ceil_div(n * 32, 256), 256, 0, st>>>(*w, emb, n, probs, labels, logits_or_null);
+        FLID_LAUNCH_CHECK();
+        return FLID_OK;
+    }
+    // weights may have changed since the last call: re-tile fc1 (a few KB) every time
+    FLID_TRY(tc_prepare_weight(w->fc1_w, w->input_dim, w->hidden1, w->input_dim, &g_fc1, st));
+    const int64_t chunk = 262144;
+    FLID_TRY(g_h1.reserve(sizeof(float) * (size_t)std::min<int64_t>(chunk, n) * w->hidden1));
+    for (int64_t r0 = 0; r0 < n; r0 += chunk) {
+        const int64_t nc = std::min<int64_t>(chunk, n - r0);
+        TcGemmArgs a;
+        a.A0 = emb + r0 * w->input_dim, a.lda0 = w->input_dim, a.w0 = w->input_dim;
+        a.C = g_h1.as<float>(), a.ldc = w->hidden1, a.bias = w->fc1_b, a.M = nc, a.relu = 1;
+        FLID_TRY(tc_gemm(a, g_fc1, st));
+        pseudo_tail_kernel<<<(unsigned)ceil_div(nc, TAIL_ROWS), TAIL_ROWS, tail_smem, st>>>(
+            *w, g_h1.as<float>(), nc, probs + r0 * w->num_classes, labels + r0,
+            logits_or_null ? logits_or_null + r0 * w->num_classes : nullptr);
+        FLID_LAUNCH_CHECK();
+    }
     return FLID_OK;
 }
 

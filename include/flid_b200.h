@@ -47,6 +47,12 @@ int flid_debug_gemm(int backend, const float* a0, int64_t lda0, const int32_t* i
                     int64_t lda1, int w1, const float* w, int64_t ldw, const float* bias, float* c, int64_t ldc,
                     int64_t m, int n, int relu, flid_stream stream);
 
+/* same shapes, tcgen05 back end only: mean device milliseconds per launch over `reps` launches
+ * (CUDA events on `stream`; tools/gemm_probe.py)                                          */
+int flid_debug_gemm_time(const float* a0, int64_t lda0, const int32_t* idx0, int w0, const float* a1, int64_t lda1,
+                         int w1, const float* w, int64_t ldw, const float* bias, float* c, int64_t ldc, int64_t m,
+                         int n, int relu, int reps, float* ms_per_launch, flid_stream stream);
+
 /* ------------------------------------------------------------------ graph ---------
  * Replaces get_neighbor_sampler (utils/utils.py:283-302) + NeighborSampler.__init__
  * (utils/utils.py:73-110): undirected adjacency, per node stably sorted by timestamp.

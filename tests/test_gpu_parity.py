@@ -474,6 +474,30 @@ def test_pseudo_label_golden(C):
         assert np.array_equal(r.cpu().numpy(), g[f"C{C}_upd_ut{ut}"])
 
 
+@pytest.mark.parametrize("C", [2, 5])
+def test_pseudo_label_bulk_path_matches_oracle_and_row_kernel(C):
+    """n >= 4096 goes through the tensor-core fc1 + tail kernel; it must agree with the oracle and
+    with the one-warp-per-row kernel used for per-batch calls."""
+    rs = np.random.RandomState(33)
+    emb = (rs.standard_normal((9001, 172)) * 1.5).astype(np.float32)
+    p = opseudo.default_decoder_params(172, C, seed=7 + C)
+    dec = flid_b200.MLPClassifier(172, 0.1, C).to(DEV)
+    dec.load_state_dict(p)
+    dec.eval()
+    x = torch.from_numpy(emb).to(DEV)
+    labels, probs = flid_b200.emit_pseudo_labels(dec, x)
+    parts = [flid_b200.emit_pseudo_labels(dec, x[i:i + 1000]) for i in range(0, len(emb), 1000)]
+    l_small, p_small = torch.cat([a for a, _ in parts]), torch.cat([b for _, b in parts])
+    wl, wp = opseudo.emit(p, torch.from_numpy(emb))
+    assert_fp32_close(probs.cpu().numpy(), wp.numpy(), "bulk probabilities vs oracle")
+    assert_fp32_close(probs.cpu().numpy(), p_small.cpu().numpy(), "bulk vs row kernel")
+    margin = np.sort(wp.numpy(), axis=1)
+    clear = (margin[:, -1] - margin[:, -2]) > 1e-5
+    assert clear.mean() > 0.99
+    assert np.array_equal(labels.cpu().numpy()[clear], wl.numpy()[clear])
+    assert np.array_equal(labels.cpu().numpy()[clear], l_small.cpu().numpy()[clear])
+
+
 def test_e_step_pass_matches_oracle_pipeline():
     """configs[2] in miniature: TGAT L=2 k=20 embeddings -> decoder -> EST filter over 3 stored
     iterations, against the oracle pipeline.  Masks are compared where the oracle's entropy is
