@@ -308,12 +308,14 @@ def run_ours(args, rank, world, local_rank):
         # roofline of the dominant kernel (attention stream) on rank 0's shard
         roots_loc = 2 * n_loc
         if use_memo:
-            evals_l1, evals_l2 = pass_stats["build"][0] + roots_loc, roots_loc
+            # memo rows (layer 1) + per root: layer 2, and layer 1 only for roots that are not graph events
+            evals_l2 = roots_loc
+            evals_l1 = pass_stats["build"][0] + pass_stats["embed"][0] - roots_loc
             valid = pass_stats["build"][1] + pass_stats["embed"][1]
         else:
             evals_l1, evals_l2 = roots_loc * (1 + K_NBR), roots_loc
             valid = pass_stats["embed"][1]
-        assert evals_l1 + evals_l2 == pass_stats["embed"][0] + (pass_stats["build"][0] if use_memo else 0)
+            assert evals_l1 + evals_l2 == pass_stats["embed"][0]
         alg = algorithmic_bytes(evals_l1, evals_l2, valid, K_NBR)                # per step, rank 0
         attn_ms, attn_n = prof_ms[2], prof_n[2]
         peak, peak_src = measured_peaks()

@@ -66,6 +66,7 @@ _SIGNATURES = {
                                        c_void, c_void]),
     "flid_tgat_embed_memo": (C.c_int, [c_void, c_void, c_void, c_void, C.POINTER(c_void), c_void, c_void, C.c_int,
                                        C.c_int64, C.c_int, c_void, c_void]),
+    "flid_tgat_set_self_from_memo": (C.c_int, [c_void, C.c_int]),
     "flid_tgat_set_chunk_targets": (C.c_int, [c_void, C.c_int64]),
     "flid_tgat_profile": (C.c_int, [c_void, C.c_int]),
     "flid_tgat_profile_read": (C.c_int, [c_void, C.POINTER(C.c_double), c_i64p]),

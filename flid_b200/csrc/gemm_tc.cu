@@ -1,26 +1,38 @@
-// tcgen05 / TMEM GEMM (see gemm_tc.cuh): persistent, warp-specialised.
+// tcgen05 / TMEM GEMM (see gemm_tc.cuh): persistent, warp-specialised, L2-traffic aware.
 //
-//   warps 0-3  producers : coalesced fp32 loads of the A tile (row gather fused), hi/lo tf32
-//                          split, st.shared into the UMMA canonical K-major layout; thread 0
-//                          also launches the bulk-async copy (cp.async.bulk, SASS UBLKCP) of the
-//                          pre-tiled weight chunk, completing on the stage's mbarrier
-//   warps 4-7  epilogue  : tcgen05.ld their 32 TMEM lanes, bias / ReLU, store C
-//   warp  8    issuer    : one thread waits "stage full", issues 12 tcgen05.mma.kind::tf32
-//                          (4 k-steps x {lo.hi, hi.lo, hi.hi}) and tcgen05.commit's the stage's
-//                          "empty" mbarrier; after the last K chunk it commits "accumulator full"
+//   warps 0-7   producers : two groups of four warps that take alternate pipeline stages:
+//                           coalesced fp32 loads of the A rows (row gather fused), hi/lo tf32
+//                           split, st.shared into the UMMA canonical K-major layout.  The
+//                           per-stage tail (drain stores, fence.proxy.async, mbarrier arrive)
+//                           of one group overlaps the loads and stores of the other.
+//   warps 8-11  epilogue  : tcgen05.ld their 32 TMEM lanes, bias / ReLU, store C
+//   warp  12    issuer    : one thread waits "stage full", issues the tcgen05.mma.kind::tf32
+//                           triples {lo.hi, hi.lo, hi.hi} and tcgen05.commit's the stage's "empty"
+//                           mbarrier; after the last K chunk it commits "accumulators full"
+//   warp  13    loader    : one thread bulk-copies (cp.async.bulk, SASS UBLKCP) the pre-tiled
+//                           weight chunk of every stage as soon as the stage is free
 //
-// Ring of `stages` shared-memory stages (32 K-floats each) + two TMEM accumulators, so the
-// producers, the tensor core and the epilogue of the previous tile all overlap.  One CTA per
-// SM, tiles (128 rows x n_tile columns) are dealt round-robin.
+// What bounds this kernel is not the tensor pipe but L2 -> SM traffic: with hi/lo images the
+// weights are 8 B per element and every 128-row tile re-streams all of them (out-projection:
+// 1.9 MB per tile, 2.25x the bytes of the A tile itself; measured: the bare barrier/copy
+// skeleton without loads, stores or MMAs ran at 107 us of a 250 us launch, profiles/).  So one
+// CTA work item is a group of MS 128-row sub-tiles that share every weight stage (MS
+// accumulators side by side in TMEM), which divides the weight traffic by MS.  K is streamed in
+// chunks of 16 floats through a ring of shared-memory stages; when two accumulator sets fit in
+// the 512 TMEM columns the epilogue of one group overlaps the MMAs of the next.
 #include "gemm_tc.cuh"
+
+#include <stdlib.h>
 
 namespace flid {
 
-constexpr int KC = TC_KC;                 // 32 floats per stage
+constexpr int KC = TC_KC;                 // 16 floats per stage
 constexpr int C4 = KC / 4;                // 16-byte chunks per row per stage
-constexpr uint32_t A_CSTRIDE = 129 * 16;  // byte stride between K chunks of A (odd in 16 B units: conflict-free stores)
+constexpr uint32_t A_CSTRIDE = 130 * 16;  // byte stride between the K chunks of a sub-tile (== 2 mod 8 in 16 B units:
+                                          // the 8 rows x 4 chunks of a warp store hit 32 distinct bank groups)
 constexpr uint32_t A_HALF = C4 * A_CSTRIDE;
-constexpr int NPROD = 128, NEPI = 128, NTHREADS = 288;
+constexpr uint32_t A_SUB = 2 * A_HALF;    // hi + lo image of one 128-row sub-tile
+constexpr int NPROD = 128, NEPI = 128, NTHREADS = 448, MAX_STAGES = 8;  // NPROD: threads of ONE producer group
 
 // ---------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -51,6 +63,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
+}
+// arrive + expect_tx in one operation: the phase cannot complete before the byte count is registered
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -95,7 +111,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
 // ---------------------------------------------------------------- weight tiling
-// image layout: [n_block][k_chunk][half][c4 = 8][n_tile] float4
+// image layout: [n_block][k_chunk][half][c4][n_tile] float4
 __global__ void tc_prep_kernel(const float* __restrict__ W, int64_t ldw, int N, int K, int n_tile, int n_blocks,
                                int k_chunks, float4* __restrict__ out) {
     const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -124,26 +140,34 @@ __global__ void tc_prep_kernel(const float* __restrict__ W, int64_t ldw, int N, 
 // ---------------------------------------------------------------- the GEMM
 struct TcShape {
     int N, n_tile, n_blocks, k_chunks, stages;
-    int64_t m_tiles;
-    uint32_t tmem_stride;  // columns between the two accumulators
+    int acc_bufs;          // 2 when two accumulator sets fit in TMEM (epilogue overlaps the next group)
+    uint32_t acc_stride;   // TMEM columns per accumulator set (MS * n_tile)
+    int64_t m_groups;      // groups of MS * 128 rows
+    int reps;              // weight image replicas in use (<= TC_REPLICAS)
+    int64_t rep_stride;    // float4 per replica
+    long long* trace;      // FLID_GEMM_TRACE (development): per-stage clock64 stamps of CTA 0, [6][TRACE_Q]
 };
+constexpr int TRACE_Q = 512;
+#define TRACE(role, q) do { if (sh.trace && blockIdx.x == 0 && (q) < TRACE_Q) sh.trace[(role) * TRACE_Q + (q)] = clock64(); } while (0)
 
+template <int MS>
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(TcGemmArgs g, const float4* __restrict__ wbuf, TcShape sh) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bar_full[4], bar_empty[4], bar_acc_full[2], bar_acc_empty[2];
+    __shared__ __align__(8) uint64_t bar_full[MAX_STAGES], bar_empty[MAX_STAGES], bar_acc_full[2], bar_acc_empty[2];
     __shared__ uint32_t tmem_slot;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t b_half = (uint32_t)C4 * sh.n_tile * 16;
-    const uint32_t stage_bytes = 2 * A_HALF + 2 * b_half;
-    const int64_t work = sh.m_tiles * sh.n_blocks;
+    const uint32_t stage_bytes = MS * A_SUB + 2 * b_half;
+    const uint32_t nblk = (uint32_t)sh.n_blocks;
+    const uint32_t work = (uint32_t)(sh.m_groups * sh.n_blocks);  // host guarantees < 2^31
 
     if (tid == 0) {
-        for (int s = 0; s < sh.stages; ++s) mbar_init(&bar_full[s], NPROD), mbar_init(&bar_empty[s], 1);
+        for (int s = 0; s < sh.stages; ++s) mbar_init(&bar_full[s], NPROD + 1), mbar_init(&bar_empty[s], 1);
         for (int a = 0; a < 2; ++a) mbar_init(&bar_acc_full[a], 1), mbar_init(&bar_acc_empty[a], NEPI);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 8) {
+    if (warp == 12) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
                      "r"(512u));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -154,101 +178,140 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(TcGemmArgs g, cons
     const uint32_t tmem = tmem_slot;
     const int ktot = g.w0 + g.w1;
 
-    if (warp < 4) {
-        // ===================================================== producers
-        const int rsub = lane >> 3, c = lane & 7;  // 4 rows x 8 float4 per warp instruction
-        uint32_t q = 0;                             // chunk counter across tiles
-        for (int64_t t = blockIdx.x; t < work; t += gridDim.x) {
-            const int nb = (int)(t % sh.n_blocks);
-            const int64_t m0 = (t / sh.n_blocks) * 128;
-            const float* p0[8];
-            const float* p1[8];
+    if (warp < 8) {
+        // ===================================================== producers (two alternating groups)
+        // The (row group, K chunk) sequence of this CTA is flattened; producer group `pg` takes
+        // chunks pg, pg + 2, ...  The global loads of a group's next chunk are in flight
+        // (registers) while its current one is split and stored.  Everything that depends on the
+        // work item only (row pointers, validity, n-block) is recomputed when the item changes
+        // (once per k_chunks chunks); the per-chunk path is an add and a compare per load.
+        constexpr int NL = MS * 4;                  // 16-byte loads per thread per chunk
+        const int pg = warp >> 2, pw = warp & 3;
+        const int rsub = lane >> 2, c = lane & 3;   // 8 rows x 4 float4 (64 B of K) per warp instruction
+        const uint32_t dq = gridDim.x / nblk, dr = gridDim.x % nblk;  // work item stride as (row group, n block)
+        struct Cursor {
+            uint32_t t, mg, nb;  // work item (>= work when exhausted), its row group and n block
+            int kc;
+        };
+        auto next_item = [&](Cursor& cu) {
+            cu.t += gridDim.x, cu.mg += dq, cu.nb += dr;
+            if (cu.nb >= nblk) cu.nb -= nblk, cu.mg += 1;
+        };
+        // ---- load cursor
+        Cursor lc{blockIdx.x, blockIdx.x / nblk, blockIdx.x % nblk, pg};
+        const float* p0[NL];
+        const float* p1[NL];
+        uint32_t okmask = 0;
+        auto bind_rows = [&]() {  // row pointers of the load cursor's work item
+            okmask = 0;
+            const int64_t m0 = (int64_t)lc.mg * (MS * 128);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int64_t row = m0 + warp * 32 + i * 4 + rsub;
-                p0[i] = nullptr, p1[i] = nullptr;
-                if (row < g.M) {
+            for (int i = 0; i < NL; ++i) {
+                const int64_t row = m0 + i * 32 + pw * 8 + rsub;
+                p0[i] = g.A0, p1[i] = g.A1;
+                if (lc.t < work && row < g.M) {
+                    okmask |= 1u << i;
                     p0[i] = g.A0 + (g.idx0 ? (int64_t)__ldg(g.idx0 + row) : row) * g.lda0;
                     if (g.w1 > 0) p1[i] = g.A1 + (g.idx1 ? (int64_t)__ldg(g.idx1 + row) : row) * g.lda1;
                 }
             }
-            const float4* wsrc = wbuf + ((int64_t)nb * sh.k_chunks) * (2 * C4 * sh.n_tile);
-            auto load_chunk = [&](int kc, float4 (&v)[8]) {
-                const int k = kc * KC + c * 4;
+        };
+        if (lc.kc >= sh.k_chunks) lc.kc -= sh.k_chunks, next_item(lc);  // k_chunks == 1: group 1 starts on the next item
+        bind_rows();
+        auto load_next = [&](float4 (&v)[NL]) {
+            const int k = lc.kc * KC + c * 4;
+            const bool seg0 = k < g.w0;
+            const int koff = seg0 ? k : k - g.w0;
+            const bool kin = k < ktot;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (p0[i] != nullptr && k < ktot) {
-                        if (k < g.w0)
-                            v[i] = __ldg(reinterpret_cast<const float4*>(p0[i] + k));
-                        else
-                            v[i] = __ldg(reinterpret_cast<const float4*>(p1[i] + (k - g.w0)));
-                    }
-                }
-            };
-            float4 cur[8], nxt[8];
-            load_chunk(0, cur);
-            for (int kc = 0; kc < sh.k_chunks; ++kc, ++q) {
-                if (kc + 1 < sh.k_chunks) load_chunk(kc + 1, nxt);  // in flight while this chunk is split / stored
-                const uint32_t s = q % sh.stages, use = q / sh.stages;
-                mbar_wait(&bar_empty[s], (use & 1) ^ 1);
-                uint8_t* st = smem + (size_t)s * stage_bytes;
-                if (tid == 0) {
-                    mbar_expect_tx(&bar_full[s], 2 * b_half);
-                    bulk_g2s(st + 2 * A_HALF, wsrc + (int64_t)kc * (2 * C4 * sh.n_tile), 2 * b_half, &bar_full[s]);
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r = warp * 32 + i * 4 + rsub;
-                    const float4 v = cur[i];
-                    const float4 hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-                    uint8_t* dst = st + c * A_CSTRIDE + r * 16;
-                    *reinterpret_cast<float4*>(dst) = hi;
-                    *reinterpret_cast<float4*>(dst + A_HALF) = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
-                }
-                fence_async_smem();
-                mbar_arrive(&bar_full[s]);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+            for (int i = 0; i < NL; ++i) {
+                const float* src = (seg0 ? p0[i] : p1[i]) + koff;
+                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (kin && ((okmask >> i) & 1u)) v[i] = __ldg(reinterpret_cast<const float4*>(src));
             }
+            lc.kc += 2;
+            if (lc.kc >= sh.k_chunks) {  // next work item (rare path)
+                lc.kc -= sh.k_chunks;
+                next_item(lc);
+                if (lc.kc >= sh.k_chunks) lc.kc -= sh.k_chunks, next_item(lc);  // k_chunks == 1
+                bind_rows();
+            }
+        };
+        // ---- store cursor: only the stage ring and the remaining chunk count matter
+        const uint32_t my_items = work > blockIdx.x ? (work - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        const uint32_t total_q = my_items * (uint32_t)sh.k_chunks;
+        uint32_t sq = (uint32_t)pg;  // chunk index of this group within the CTA's sequence
+        uint32_t stage = (uint32_t)pg % (uint32_t)sh.stages, phase = 0;
+        auto store_next = [&](const float4 (&v)[NL]) {
+            if (pw == 0 && lane == 0) TRACE(0, sq);
+            mbar_wait(&bar_empty[stage], phase ^ 1);
+            if (pw == 0 && lane == 0) TRACE(1, sq);
+            uint8_t* st = smem + (size_t)stage * stage_bytes + c * A_CSTRIDE + (pw * 8 + rsub) * 16;
+#pragma unroll
+            for (int i = 0; i < NL; ++i) {
+                const float4 x = v[i];
+                const float4 hi = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
+                uint8_t* dst = st + (i >> 2) * A_SUB + (i & 3) * (32 * 16);  // sub-tile i / 4, rows (i % 4) * 32 + ...
+                *reinterpret_cast<float4*>(dst) = hi;
+                *reinterpret_cast<float4*>(dst + A_HALF) = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
+            }
+            fence_async_smem();
+            mbar_arrive(&bar_full[stage]);
+            if (pw == 0 && lane == 0) TRACE(2, sq);
+            sq += 2;
+            stage += 2;
+            if (stage >= (uint32_t)sh.stages) stage -= (uint32_t)sh.stages, phase ^= 1;
+        };
+        float4 ra[NL], rb[NL];
+        load_next(ra);
+        while (sq < total_q) {
+            load_next(rb);
+            store_next(ra);
+            if (sq >= total_q) break;
+            load_next(ra);
+            store_next(rb);
         }
-    } else if (warp < 8) {
+    } else if (warp < 12) {
         // ===================================================== epilogue
-        const int ew = warp - 4;  // TMEM lane quarter == warp id % 4
+        const int ew = warp - 8;  // TMEM lane quarter == warp id % 4
         uint32_t it = 0;
-        for (int64_t t = blockIdx.x; t < work; t += gridDim.x, ++it) {
-            const int nb = (int)(t % sh.n_blocks);
-            const int64_t row = (t / sh.n_blocks) * 128 + ew * 32 + lane;
-            const uint32_t acc = it & 1;
-            mbar_wait(&bar_acc_full[acc], (it >> 1) & 1);
+        for (uint32_t t = blockIdx.x; t < work; t += gridDim.x, ++it) {
+            const uint32_t mg = t / nblk, nb = t - mg * nblk;
+            const uint32_t acc = sh.acc_bufs == 2 ? (it & 1) : 0;
+            const uint32_t par = sh.acc_bufs == 2 ? ((it >> 1) & 1) : (it & 1);
+            mbar_wait(&bar_acc_full[acc], par);
             tc_fence_after();
-            const uint32_t taddr = tmem + acc * sh.tmem_stride + ((uint32_t)(ew * 32) << 16);
-            float* crow = (row < g.M) ? g.C + row * g.ldc : nullptr;
-            for (int c0 = 0; c0 < sh.n_tile; c0 += 16) {
-                float v[16];
-                tmem_ld16(taddr + (uint32_t)c0, v);
-                const int n0 = nb * sh.n_tile + c0;
-                if (crow != nullptr) {
-                    if (n0 + 16 <= sh.N && (g.ldc & 3) == 0) {
 #pragma unroll
-                        for (int i = 0; i < 16; i += 4) {
-                            float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                            if (g.bias) {
-                                const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + i));
-                                o.x += b.x, o.y += b.y, o.z += b.z, o.w += b.w;
+            for (int ms = 0; ms < MS; ++ms) {
+                const int64_t row = (int64_t)mg * (MS * 128) + ms * 128 + ew * 32 + lane;
+                const uint32_t taddr = tmem + acc * sh.acc_stride + ms * sh.n_tile + ((uint32_t)(ew * 32) << 16);
+                float* crow = (row < g.M) ? g.C + row * g.ldc : nullptr;
+                for (int c0 = 0; c0 < sh.n_tile; c0 += 16) {
+                    float v[16];
+                    tmem_ld16(taddr + (uint32_t)c0, v);
+                    const int n0 = nb * sh.n_tile + c0;
+                    if (crow != nullptr) {
+                        if (n0 + 16 <= sh.N && (g.ldc & 3) == 0) {
+#pragma unroll
+                            for (int i = 0; i < 16; i += 4) {
+                                float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                                if (g.bias) {
+                                    const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + i));
+                                    o.x += b.x, o.y += b.y, o.z += b.z, o.w += b.w;
+                                }
+                                if (g.relu) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
+                                *reinterpret_cast<float4*>(crow + n0 + i) = o;
                             }
-                            if (g.relu) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
-                            *reinterpret_cast<float4*>(crow + n0 + i) = o;
-                        }
-                    } else {
+                        } else {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const int n = n0 + i;
-                            if (n < sh.N) {
-                                float x = v[i];
-                                if (g.bias) x += __ldg(g.bias + n);
-                                if (g.relu) x = fmaxf(x, 0.f);
-                                crow[n] = x;
+                            for (int i = 0; i < 16; ++i) {
+                                const int n = n0 + i;
+                                if (n < sh.N) {
+                                    float x = v[i];
+                                    if (g.bias) x += __ldg(g.bias + n);
+                                    if (g.relu) x = fmaxf(x, 0.f);
+                                    crow[n] = x;
+                                }
                             }
                         }
                     }
@@ -257,41 +320,68 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(TcGemmArgs g, cons
             tc_fence_before();
             mbar_arrive(&bar_acc_empty[acc]);
         }
-    } else if (lane == 0) {
+    } else if (warp == 12 && lane == 0) {
         // ===================================================== MMA issuer (one thread)
         // instruction descriptor: D=f32, A=B=tf32, K-major both, N = n_tile, M = 128
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(sh.n_tile >> 3) << 17) | (8u << 24);
         const uint32_t smem_base = smem_u32(smem);
-        uint32_t q = 0, it = 0;
-        for (int64_t t = blockIdx.x; t < work; t += gridDim.x, ++it) {
-            const uint32_t acc = it & 1;
-            mbar_wait(&bar_acc_empty[acc], ((it >> 1) & 1) ^ 1);
+        const uint32_t b_lbo = (uint32_t)sh.n_tile * 16;
+        uint32_t it = 0, s = 0, ph = 0, tq = 0;
+        for (uint32_t t = blockIdx.x; t < work; t += gridDim.x, ++it) {
+            const uint32_t acc = sh.acc_bufs == 2 ? (it & 1) : 0;
+            const uint32_t par = sh.acc_bufs == 2 ? ((it >> 1) & 1) : (it & 1);
+            mbar_wait(&bar_acc_empty[acc], par ^ 1);
             tc_fence_after();
-            const uint32_t d = tmem + acc * sh.tmem_stride;
-            for (int kc = 0; kc < sh.k_chunks; ++kc, ++q) {
-                const uint32_t s = q % sh.stages, use = q / sh.stages;
-                mbar_wait(&bar_full[s], use & 1);
+            const uint32_t d0 = tmem + acc * sh.acc_stride;
+            for (int kc = 0; kc < sh.k_chunks; ++kc) {
+                mbar_wait(&bar_full[s], ph);
+                TRACE(3, tq);
                 tc_fence_after();
                 const uint32_t sa = smem_base + s * stage_bytes;
-                const uint32_t sb = sa + 2 * A_HALF;
+                const uint32_t sb = sa + MS * A_SUB;
 #pragma unroll
                 for (int j = 0; j < KC / 8; ++j) {
-                    const uint64_t d_ahi = umma_desc(sa + (2 * j) * A_CSTRIDE, A_CSTRIDE, 128);
-                    const uint64_t d_alo = umma_desc(sa + A_HALF + (2 * j) * A_CSTRIDE, A_CSTRIDE, 128);
-                    const uint64_t d_bhi = umma_desc(sb + (2 * j) * (sh.n_tile * 16), sh.n_tile * 16, 128);
-                    const uint64_t d_blo = umma_desc(sb + b_half + (2 * j) * (sh.n_tile * 16), sh.n_tile * 16, 128);
-                    umma_tf32(d, d_alo, d_bhi, idesc, (kc | j) ? 1u : 0u);  // small terms first
-                    umma_tf32(d, d_ahi, d_blo, idesc, 1u);
-                    umma_tf32(d, d_ahi, d_bhi, idesc, 1u);
+                    const uint64_t d_bhi = umma_desc(sb + (2 * j) * b_lbo, b_lbo, 128);
+                    const uint64_t d_blo = umma_desc(sb + b_half + (2 * j) * b_lbo, b_lbo, 128);
+#pragma unroll
+                    for (int ms = 0; ms < MS; ++ms) {
+                        const uint32_t a0 = sa + ms * A_SUB + (2 * j) * A_CSTRIDE;
+                        const uint64_t d_ahi = umma_desc(a0, A_CSTRIDE, 128);
+                        const uint64_t d_alo = umma_desc(a0 + A_HALF, A_CSTRIDE, 128);
+                        const uint32_t d = d0 + ms * sh.n_tile;
+                        umma_tf32(d, d_alo, d_bhi, idesc, (kc | j) ? 1u : 0u);  // small terms first
+                        umma_tf32(d, d_ahi, d_blo, idesc, 1u);
+                        umma_tf32(d, d_ahi, d_bhi, idesc, 1u);
+                    }
                 }
                 tc_commit(&bar_empty[s]);  // frees the smem stage when these MMAs have read it
+                TRACE(4, tq);
+                ++tq;
+                if (++s == (uint32_t)sh.stages) s = 0, ph ^= 1;
             }
-            tc_commit(&bar_acc_full[acc]);  // accumulator complete -> epilogue
+            tc_commit(&bar_acc_full[acc]);  // accumulators complete -> epilogue
+        }
+    } else if (warp == 13 && lane == 0) {
+        // ===================================================== weight loader (one thread)
+        uint32_t s = 0, ph = 0, tq = 0;
+        const int64_t chunk4 = (int64_t)2 * C4 * sh.n_tile;  // float4 per (n block, K chunk)
+        for (uint32_t t = blockIdx.x; t < work; t += gridDim.x) {
+            const uint32_t nb = t % nblk;
+            const float4* wsrc = wbuf + (int64_t)(blockIdx.x % sh.reps) * sh.rep_stride + (int64_t)nb * sh.k_chunks * chunk4;
+            for (int kc = 0; kc < sh.k_chunks; ++kc) {
+                mbar_wait(&bar_empty[s], ph ^ 1);
+                TRACE(5, tq);
+                ++tq;
+                uint8_t* st = smem + (size_t)s * stage_bytes + MS * A_SUB;
+                mbar_arrive_expect_tx(&bar_full[s], 2 * b_half);
+                bulk_g2s(st, wsrc + kc * chunk4, 2 * b_half, &bar_full[s]);
+                if (++s == (uint32_t)sh.stages) s = 0, ph ^= 1;
+            }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
+    if (warp == 12) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
 }
 
 // ---------------------------------------------------------------- host side
@@ -318,6 +408,9 @@ int tc_prepare_weight(const float* W, int64_t ldw, int N, int K, TcWeight* w, cu
     tc_prep_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(W, ldw, N, K, n_tile, n_blocks, k_chunks,
                                                                   reinterpret_cast<float4*>(w->buf));
     FLID_LAUNCH_CHECK();
+    for (int r = 1; r < TC_REPLICAS; ++r)
+        FLID_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(w->buf) + r * w->image_bytes(), w->buf, w->image_bytes(),
+                                  cudaMemcpyDeviceToDevice, st));
     return FLID_OK;
 }
 
@@ -326,34 +419,96 @@ void tc_free_weight(TcWeight* w) {
     if (w) w->buf = nullptr;
 }
 
+template <int MS>
+static int launch_ms(const TcGemmArgs& g, const TcWeight& w, TcShape sh, int sm_count, int smem_max, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        FLID_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max - 1024));
+        attr_set = true;
+    }
+    const size_t stage = (size_t)MS * A_SUB + 2 * (size_t)C4 * w.n_tile * 16;
+    int stages = (int)((size_t)(smem_max - 1024) / stage);
+    sh.stages = stages > MAX_STAGES ? MAX_STAGES : stages;
+    sh.m_groups = ceil_div(g.M, MS * 128);
+    sh.acc_stride = (uint32_t)(MS * w.n_tile);
+    sh.acc_bufs = 2 * sh.acc_stride <= 512 ? 2 : 1;
+    const int64_t work = sh.m_groups * sh.n_blocks;
+    FLID_REQUIRE(work < (1LL << 31) - 65536, "tc_gemm: too many tiles for one launch (M = %lld)", (long long)g.M);
+    const unsigned grid = (unsigned)(work < sm_count ? work : sm_count);
+    gemm_tc_kernel<MS><<<grid, NTHREADS, sh.stages * stage, st>>>(g, reinterpret_cast<const float4*>(w.buf), sh);
+    FLID_LAUNCH_CHECK();
+    return FLID_OK;
+}
+
 int tc_gemm(const TcGemmArgs& g, const TcWeight& w, cudaStream_t st) {
     if (g.M <= 0) return FLID_OK;
     FLID_REQUIRE(w.buf != nullptr, "tc_gemm: weight not prepared");
     FLID_REQUIRE(g.w0 > 0 && g.w0 + g.w1 == w.K, "tc_gemm: A width %d+%d != weight K %d", g.w0, g.w1, w.K);
     FLID_REQUIRE((g.w0 % 4) == 0 && (g.w1 % 4) == 0 && (g.lda0 % 4) == 0 && (g.lda1 % 4) == 0,
                  "tc_gemm: segment widths / row strides must be multiples of 4 floats");
-    static int sm_count = 0, smem_max = 0;
+    static int sm_count = 0, smem_max = 0, ms_cap = 2;
     if (sm_count == 0) {
         int dev = 0;
         FLID_CUDA(cudaGetDevice(&dev));
         FLID_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
         FLID_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-        FLID_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max - 1024));
+        const char* e = getenv("FLID_GEMM_MS");  // development knob: cap the sub-tiles per work item
+        if (e && e[0] >= '1' && e[0] <= '3') ms_cap = e[0] - '0';
     }
     TcShape sh;
+    sh.trace = nullptr;
+    static long long* d_trace = nullptr;
+    if (getenv("FLID_GEMM_TRACE")) {
+        if (!d_trace) cudaMalloc((void**)&d_trace, sizeof(long long) * 6 * TRACE_Q);
+        cudaMemsetAsync(d_trace, 0, sizeof(long long) * 6 * TRACE_Q, st);
+        sh.trace = d_trace;
+    }
+    {
+        static int reps = 0;
+        if (reps == 0) {
+            const char* e = getenv("FLID_GEMM_REPS");  // development knob
+            reps = e ? atoi(e) : TC_REPLICAS;
+            if (reps < 1 || reps > TC_REPLICAS) reps = TC_REPLICAS;
+        }
+        sh.reps = reps, sh.rep_stride = (int64_t)(w.image_bytes() / 16);
+    }
     sh.N = w.N, sh.n_tile = w.n_tile, sh.n_blocks = w.n_blocks, sh.k_chunks = w.k_chunks;
-    sh.m_tiles = ceil_div(g.M, 128);
-    sh.tmem_stride = 256;
-    const size_t stage = 2 * (size_t)A_HALF + 2 * (size_t)C4 * w.n_tile * 16;
-    int stages = (int)((size_t)(smem_max - 1024) / stage);
-    stages = stages > 4 ? 4 : stages;
-    FLID_REQUIRE(stages >= 2, "tc_gemm: tile does not fit in shared memory");
-    sh.stages = stages;
-    const int64_t work = sh.m_tiles * sh.n_blocks;
-    const unsigned grid = (unsigned)(work < sm_count ? work : sm_count);
-    gemm_tc_kernel<<<grid, NTHREADS, stages * stage, st>>>(g, reinterpret_cast<const float4*>(w.buf), sh);
-    FLID_LAUNCH_CHECK();
-    return FLID_OK;
+    // Sub-tiles per work item: minimise a small cost model of cycles per row -- per K chunk the
+    // slower of the MMAs (3 per 8 K-elements, n_tile / 2 cycles each) and the L2 -> SM traffic
+    // (A rows + the hi/lo weight chunk at ~43 B/cycle/SM, the chip-wide L2 cap shared by 148 SMs),
+    // plus the epilogue when the accumulators cannot be double-buffered in the 512 TMEM columns.
+    int ms = 1;
+    double best = 1e30;
+    for (int cand = 1; cand <= ms_cap; ++cand) {
+        const size_t stage = (size_t)cand * A_SUB + 2 * (size_t)C4 * w.n_tile * 16;
+        const bool fits = cand * w.n_tile <= 512 && (size_t)(smem_max - 1024) / stage >= 3;
+        const bool fills = cand == 1 || ceil_div(g.M, cand * 128) * w.n_blocks >= (int64_t)sm_count;
+        if (!fits || !fills) continue;
+        const double mma = cand * (KC / 8) * 3 * (w.n_tile / 2.0);
+        const double l2 = (cand * 128.0 * KC * 4 + 2.0 * C4 * w.n_tile * 16) / 43.0;
+        const double epi = 2 * cand * w.n_tile <= 512 ? 0.0 : cand * (w.n_tile / 16.0) * 150.0;
+        const double per_row = (w.k_chunks * (mma > l2 ? mma : l2) + epi) / (cand * 128.0);
+        if (per_row < best * 0.97) best = per_row, ms = cand;  // prefer fewer sub-tiles on near-ties
+    }
+    int rc;
+    switch (ms) {
+        case 3: rc = launch_ms<3>(g, w, sh, sm_count, smem_max, st); break;
+        case 2: rc = launch_ms<2>(g, w, sh, sm_count, smem_max, st); break;
+        default: rc = launch_ms<1>(g, w, sh, sm_count, smem_max, st); break;
+    }
+    if (sh.trace && rc == FLID_OK) {  // development: dump the stamps of the launch as text
+        static long long h[6 * TRACE_Q];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost);
+        FILE* f = fopen(getenv("FLID_GEMM_TRACE"), "w");
+        if (f) {
+            fprintf(f, "# ms=%d n_tile=%d k_chunks=%d stages? q p_wait0 p_wait1 p_arrive i_full i_commit l_empty\n", ms, w.n_tile, w.k_chunks);
+            for (int q = 0; q < TRACE_Q; ++q)
+                fprintf(f, "%d %lld %lld %lld %lld %lld %lld\n", q, h[q], h[TRACE_Q + q], h[2 * TRACE_Q + q], h[3 * TRACE_Q + q], h[4 * TRACE_Q + q], h[5 * TRACE_Q + q]);
+            fclose(f);
+        }
+    }
+    return rc;
 }
 
 }  // namespace flid

@@ -80,6 +80,19 @@ __global__ void place_kernel(const uint32_t* __restrict__ perm, const int32_t* _
     atomicAdd(counts + owner_sorted[i], 1ull);
 }
 
+// Entries 2i and 2i+1 of the insertion order belong to the same event: after the sort, each
+// entry learns where its partner went (used by the layer memo: the partner's table row is the
+// layer embedding of this entry's owner at the event time).
+__global__ void inverse_perm_kernel(const uint32_t* __restrict__ perm, int64_t M, int32_t* __restrict__ inv) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < M) inv[perm[i]] = (int32_t)i;
+}
+__global__ void mirror_kernel(const uint32_t* __restrict__ perm, const int32_t* __restrict__ inv, int64_t M,
+                              int32_t* __restrict__ mirror) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < M) mirror[i] = inv[perm[i] ^ 1u];
+}
+
 __global__ void max_kernel(const unsigned long long* __restrict__ counts, int64_t n, unsigned long long* out) {
     unsigned long long m = 0;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -88,7 +101,7 @@ __global__ void max_kernel(const unsigned long long* __restrict__ counts, int64_
 }
 
 static int build_sorted(flid_graph* g, int32_t* owner, int2* adj_in, unsigned long long* tkey, int64_t M,
-                        cudaStream_t st) {
+                        bool paired, cudaStream_t st) {
     const int64_t N1 = g->num_nodes + 1;
     const int T = 256;
     const unsigned B = (unsigned)ceil_div(M > 0 ? M : 1, T);
@@ -127,6 +140,13 @@ static int build_sorted(flid_graph* g, int32_t* owner, int2* adj_in, unsigned lo
         count_launch(4);
         place_kernel<<<B, T, 0, st>>>(perm_a, own_b, adj_in, tkey, M, g->adj, g->ts, counts);
         FLID_LAUNCH_CHECK();
+        if (paired && M < 0x7fffffffLL) {
+            FLID_CUDA(cudaMalloc(&g->mirror, sizeof(int32_t) * M));
+            inverse_perm_kernel<<<B, T, 0, st>>>(perm_a, M, own_a);  // own_a is free again: reuse as the inverse
+            FLID_LAUNCH_CHECK();
+            mirror_kernel<<<B, T, 0, st>>>(perm_a, own_a, M, g->mirror);
+            FLID_LAUNCH_CHECK();
+        }
     }
     // indptr = exclusive scan of counts over N1 + 1 slots (last slot = M)
     size_t scan_bytes = 0;
@@ -196,7 +216,7 @@ static int build_common(const int64_t* a, const int64_t* b, const int64_t* eid, 
         set_error("flid_graph_build: node id outside [0, %lld] or edge id outside int32", (long long)num_nodes);
         status = FLID_ERR_RANGE;
     } else {
-        status = build_sorted(g, owner, adj_in, tkey, M, st);
+        status = build_sorted(g, owner, adj_in, tkey, M, events, st);
     }
     for (int i = 0; i < 4; ++i) cudaFree(staged[i]);
     cudaFree(owner), cudaFree(adj_in), cudaFree(tkey), cudaFree(bad);
@@ -227,7 +247,7 @@ int flid_graph_build_entries(const int64_t* owner, const int64_t* nbr, const int
 
 void flid_graph_free(flid_graph* g) {
     if (!g) return;
-    cudaFree(g->indptr), cudaFree(g->adj), cudaFree(g->ts);
+    cudaFree(g->indptr), cudaFree(g->adj), cudaFree(g->ts), cudaFree(g->mirror);
     delete g;
 }
 

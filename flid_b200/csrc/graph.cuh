@@ -9,6 +9,8 @@ struct flid_graph {
     int64_t* indptr = nullptr;  // [num_nodes + 2]
     int2* adj = nullptr;        // [M] (.x = neighbour id, .y = edge id)
     double* ts = nullptr;       // [M]
+    int32_t* mirror = nullptr;  // [M] position of the same event's entry in the other endpoint's list
+                                // (graphs built from events with M < 2^31 only, else null)
 };
 
 namespace flid {

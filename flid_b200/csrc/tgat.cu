@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(256) level_sample_kernel(
     const int32_t* __restrict__ ids, const double* __restrict__ times, int64_t n, int64_t n_f64, int k,
     int32_t* __restrict__ nbr, int32_t* __restrict__ eid, float* __restrict__ dt, int32_t* __restrict__ next_ids,
     double* __restrict__ next_times, int32_t* __restrict__ pos, int32_t pad_pos,
-    unsigned long long* __restrict__ valid_slots) {
+    const int32_t* __restrict__ mirror, int32_t* __restrict__ self_pos, unsigned long long* __restrict__ valid_slots) {
     __shared__ int s_cnt;
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
@@ -103,6 +103,18 @@ __global__ void __launch_bounds__(256) level_sample_kernel(
         const int64_t have = cut - start;
         const int cnt = have < (int64_t)k ? (int)have : k;
         if (next_ids && lane == 0) next_ids[q] = v, next_times[q] = t;
+        if (self_pos && lane == 0) {
+            // Is (v, t) itself an event of the graph at a float32-exact time?  Then the lower-layer
+            // embeddings of this root are already in the layer memo: the row of the event's entry in
+            // the other endpoint's list is h_l(v, float32(t)), and with float32(t) == t both the
+            // neighbourhood (ts < t) and every float32 dt of the root (models/TGAT.py:120-125:
+            // float64 subtraction rounded once == float32 subtraction of the same two values) coincide.
+            int32_t sp = -1;
+            const int64_t end = __ldg(indptr + v + 1);
+            if (cut < end && __ldg(ts + cut) == t && (double)(float)t == t) sp = __ldg(mirror + cut);
+            self_pos[q] = sp;
+            if (sp < 0) atomicAdd(valid_slots + 1, 1ull);  // misses
+        }
         const bool f64_rule = q < n_f64;
         const float tf = (float)t;
         for (int j = lane; j < k; j += 32) {
@@ -289,7 +301,7 @@ int tgat_embed_ids(flid_tgat* m, const flid_graph* g, const float* node_feat, co
             level_sample_kernel<<<(unsigned)ceil_div(c[l] * 32, 256), 256, 0, st>>>(
                 g->indptr, g->adj, g->ts, w_ids + o[l], w_times + o[l], c[l], nf, k, w_nbr + o[l] * k,
                 w_eid + o[l] * k, w_dt + o[l] * k, l > 1 ? w_ids + o[l - 1] : nullptr,
-                l > 1 ? w_times + o[l - 1] : nullptr, nullptr, 0, d_valid);
+                l > 1 ? w_times + o[l - 1] : nullptr, nullptr, 0, nullptr, nullptr, d_valid);
             FLID_LAUNCH_CHECK();
             queries += c[l];
         }
@@ -433,7 +445,7 @@ int tgat_memo_build(flid_tgat* m, const flid_graph* g, const float* node_feat, c
             level_sample_kernel<<<(unsigned)ceil_div(n * 32, 256), 256, 0, st>>>(
                 g->indptr, g->adj, g->ts, w_ids, w_times, n, 0, k, m->ws_nbr.as<int32_t>(), m->ws_eid.as<int32_t>(),
                 m->ws_dt.as<float>(), nullptr, nullptr, level > 1 ? m->ws_pos.as<int32_t>() : nullptr, (int32_t)M,
-                d_valid);
+                nullptr, nullptr, d_valid);
             FLID_LAUNCH_CHECK();
         }
         LayerCall c;
@@ -453,20 +465,25 @@ int tgat_memo_build(flid_tgat* m, const flid_graph* g, const float* node_feat, c
     return FLID_OK;
 }
 
-// roots with the lower layers memoised: one sampling pass, L attention evaluations per root
+// roots with the lower layers memoised: one sampling pass and, per root, L attention evaluations --
+// or a single one (level L) when the root is itself an event of the graph at a float32-exact time,
+// because its own lower-layer embeddings are then rows of the memo as well (see level_sample_kernel).
 int tgat_embed_memo(flid_tgat* m, const flid_graph* g, const float* node_feat, const float* edge_feat,
                     const float* const* memo, const int32_t* ids, const double* times, int64_t n_f64, int64_t n, int k,
                     float* out, cudaStream_t st) {
     const int L = m->L;
     const int64_t M = g->num_entries;
     const bool use_table = (m->table_src == node_feat && m->table_rows > 0);
+    const bool try_self = L > 1 && g->mirror != nullptr && m->self_from_memo;
     const int64_t chunk = std::max<int64_t>(1, m->max_l1_targets);
     const int64_t nmax = std::min(chunk, n);
     FLID_TRY(reserve_layer_ws(m, nmax, k, L > 1 || !use_table));
     if (L > 1) FLID_TRY(m->ws_h.reserve(sizeof(float) * 2 * nmax * m->dn));
-    unsigned long long* d_valid = m->ws_misc.as<unsigned long long>();
-    FLID_CUDA(cudaMemsetAsync(d_valid, 0, sizeof(unsigned long long), st));
-    int64_t evals = 0;
+    if (try_self) FLID_TRY(m->ws_self.reserve(sizeof(int32_t) * nmax));
+    unsigned long long* d_cnt = m->ws_misc.as<unsigned long long>();  // [0] valid slots, [1] roots without a memo row
+    FLID_CUDA(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(unsigned long long), st));
+    int64_t evals = 0, valid_weighted = 0;
+    unsigned long long h_prev[2] = {0, 0};
     for (int64_t r0 = 0; r0 < n; r0 += chunk) {
         const int64_t nc = std::min(chunk, n - r0);
         const int64_t nf = std::max<int64_t>(0, std::min(nc, n_f64 - r0));
@@ -475,11 +492,19 @@ int tgat_embed_memo(flid_tgat* m, const flid_graph* g, const float* node_feat, c
             level_sample_kernel<<<(unsigned)ceil_div(nc * 32, 256), 256, 0, st>>>(
                 g->indptr, g->adj, g->ts, ids + r0, times + r0, nc, nf, k, m->ws_nbr.as<int32_t>(),
                 m->ws_eid.as<int32_t>(), m->ws_dt.as<float>(), nullptr, nullptr,
-                L > 1 ? m->ws_pos.as<int32_t>() : nullptr, (int32_t)M, d_valid);
+                L > 1 ? m->ws_pos.as<int32_t>() : nullptr, (int32_t)M, try_self ? g->mirror : nullptr,
+                try_self ? m->ws_self.as<int32_t>() : nullptr, d_cnt);
             FLID_LAUNCH_CHECK();
         }
+        // counters of this chunk (one small synchronous read per chunk of up to 65 536 roots)
+        unsigned long long h_cnt[2];
+        FLID_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
+        FLID_CUDA(cudaStreamSynchronize(st));
+        const int64_t chunk_valid = (int64_t)(h_cnt[0] - h_prev[0]);
+        const bool all_in_memo = try_self && h_cnt[1] == h_prev[1];
+        h_prev[0] = h_cnt[0], h_prev[1] = h_cnt[1];
         float* hbuf[2] = {m->ws_h.as<float>(), L > 1 ? m->ws_h.as<float>() + nmax * m->dn : nullptr};
-        for (int l = 1; l <= L; ++l) {
+        for (int l = all_in_memo ? L : 1; l <= L; ++l) {
             LayerCall c;
             c.n = nc, c.ids = ids + r0;
             c.nbr = m->ws_nbr.as<int32_t>(), c.eid = m->ws_eid.as<int32_t>(), c.dt = m->ws_dt.as<float>();
@@ -487,14 +512,19 @@ int tgat_embed_memo(flid_tgat* m, const flid_graph* g, const float* node_feat, c
                 c.hrow_base = node_feat, c.self_base = node_feat, c.self_idx = ids + r0, c.u_from_table = use_table;
             } else {
                 c.pos = m->ws_pos.as<int32_t>();
-                c.hrow_base = memo[l - 2], c.self_base = hbuf[l & 1];
+                c.hrow_base = memo[l - 2];
+                if (all_in_memo)
+                    c.self_base = memo[l - 2], c.self_idx = m->ws_self.as<int32_t>();
+                else
+                    c.self_base = hbuf[l & 1];
             }
             c.out = (l == L) ? out + r0 * m->dn : hbuf[(l + 1) & 1];
             FLID_TRY(layer_eval(m, l, c, node_feat, edge_feat, k, st));
             evals += nc;
+            valid_weighted += chunk_valid;
         }
     }
-    m->stats[0] = evals, m->stats[2] = n, m->stats[1] = -1, m->valid_mult = L;
+    m->stats[0] = evals, m->stats[2] = n, m->stats[1] = valid_weighted, m->valid_mult = 1;
     return FLID_OK;
 }
 
@@ -523,6 +553,8 @@ int flid_tgat_create(int node_dim, int edge_dim, int time_dim, int num_layers, i
     m->layers.resize(num_layers);
     const char* mode = getenv("FLID_GEMM");
     m->use_tc = !(mode && strcmp(mode, "simt") == 0);
+    const char* sm = getenv("FLID_SELF_MEMO");
+    m->self_from_memo = !(sm && sm[0] == '0');
     *out = m;
     return FLID_OK;
 }
@@ -539,7 +571,7 @@ void flid_tgat_free(flid_tgat* m) {
     for (auto e : m->prof_ev) cudaEventDestroy(e);
     flid::DevBuf* bufs[] = {&m->raw_q, &m->raw_k, &m->raw_v, &m->raw_r, &m->table, &m->ws_ids, &m->ws_times,
                             &m->ws_nbr, &m->ws_eid, &m->ws_dt, &m->ws_h, &m->ws_u, &m->ws_z, &m->ws_o,
-                            &m->ws_a, &m->ws_hd, &m->ws_misc, &m->ws_rid, &m->ws_rt, &m->ws_bad, &m->ws_pos};
+                            &m->ws_a, &m->ws_hd, &m->ws_misc, &m->ws_rid, &m->ws_rt, &m->ws_bad, &m->ws_pos, &m->ws_self};
     for (auto* b : bufs) b->release();
     delete m;
 }
@@ -706,6 +738,13 @@ int flid_tgat_embed_memo(flid_tgat* m, const flid_graph* g, const float* node_fe
     return FLID_OK;
 }
 
+int flid_tgat_set_self_from_memo(flid_tgat* m, int enable) {
+    using namespace flid;
+    FLID_REQUIRE(m != nullptr, "flid_tgat_set_self_from_memo: null handle");
+    m->self_from_memo = enable != 0;
+    return FLID_OK;
+}
+
 int flid_tgat_set_chunk_targets(flid_tgat* m, int64_t max_layer1_targets) {
     using namespace flid;
     FLID_REQUIRE(m && max_layer1_targets > 0, "flid_tgat_set_chunk_targets: bad argument");
@@ -740,11 +779,12 @@ int flid_tgat_last_stats(const flid_tgat* m, int64_t stats[4]) {
     using namespace flid;
     FLID_REQUIRE(m && stats, "flid_tgat_last_stats: null argument");
     unsigned long long hv = 0;
-    if (m->ws_misc.p) {
+    if (m->stats[1] < 0 && m->ws_misc.p) {
         FLID_CUDA(cudaDeviceSynchronize());
         FLID_CUDA(cudaMemcpy(&hv, m->ws_misc.p, sizeof(hv), cudaMemcpyDeviceToHost));
     }
-    stats[0] = m->stats[0], stats[1] = (int64_t)hv * m->valid_mult, stats[2] = m->stats[2];
+    stats[0] = m->stats[0], stats[2] = m->stats[2];
+    stats[1] = m->stats[1] < 0 ? (int64_t)hv * m->valid_mult : m->stats[1];
     const flid::DevBuf* bufs[] = {&m->table, &m->ws_ids, &m->ws_times, &m->ws_nbr, &m->ws_eid, &m->ws_dt, &m->ws_h,
                                   &m->ws_u,  &m->ws_z,   &m->ws_o,     &m->ws_a,   &m->ws_hd, &m->ws_pos};
     int64_t b = 0;

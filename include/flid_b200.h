@@ -148,6 +148,12 @@ int flid_tgat_memo_build(flid_tgat* m, const flid_graph* g, const float* node_fe
 int flid_tgat_embed_memo(flid_tgat* m, const flid_graph* g, const float* node_feat, const float* edge_feat,
                          const float* const* memo_tables_host, const int64_t* nodes, const double* times,
                          int times_are_f32, int64_t n, int k, float* out, flid_stream stream);
+/* A root query (v, t) that is itself an event of the graph (built with flid_graph_build_events)
+ * at a float32-exact time finds its own lower-layer embeddings in the memo too (the table row
+ * of the event's entry in the other endpoint's list), so flid_tgat_embed_memo evaluates only
+ * the top layer for it; other roots take the full chain.  Same bits either way; on by default,
+ * this switch exists for tests and A/B timing.                                            */
+int flid_tgat_set_self_from_memo(flid_tgat* m, int enable);
 /* upper bound on layer-1 targets processed per internal chunk (workspace ~7 KB per target;
  * default 65536).  Results do not depend on it.                                        */
 int flid_tgat_set_chunk_targets(flid_tgat* m, int64_t max_layer1_targets);

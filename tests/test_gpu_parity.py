@@ -255,12 +255,31 @@ def test_tgat_layer_memo_is_bit_identical(shape, L, k):
         memo32 = m.compute_node_temporal_embeddings(nodes, times.astype(np.float32), L, k)
     assert L in m._engine.memo
     assert torch.equal(plain64, memo64) and torch.equal(plain32, memo32)
+    # roots that are events of the graph at float32-exact times take their own lower layers from the
+    # memo (one evaluation per root); switched off, every root runs all L levels.  Same bits.
+    h, lib = m._engine.handles[L], _lib.lib()
+    exact = bool(np.all(times.astype(np.float32).astype(np.float64) == times))
     st = m.last_stats()
-    assert st[0] == len(nodes) * L and st[2] == len(nodes)
+    assert st[2] == len(nodes) and st[0] == len(nodes) * (1 if exact else L)
+    _lib.check(lib.flid_tgat_set_self_from_memo(h, 0))
+    with torch.no_grad():
+        full64 = m.compute_node_temporal_embeddings(nodes, times, L, k)
+    st = m.last_stats()
+    assert st[0] == len(nodes) * L and torch.equal(full64, memo64)
+    _lib.check(lib.flid_tgat_set_self_from_memo(h, 1))
+    # roots that are not events (shifted times, other nodes) must fall back to the full chain
+    t_off = times + 0.5
+    n_off = np.roll(nodes, 7)
+    with torch.no_grad():
+        a_memo = m.compute_node_temporal_embeddings(n_off, t_off, L, k)
+        m.set_layer_memo(False)
+        a_plain = m.compute_node_temporal_embeddings(n_off, t_off, L, k)
+        m.set_layer_memo(True)
+        m.compute_node_temporal_embeddings(nodes[:4], times[:4], L, k)      # rebuilds the memo for the split-build check
+    assert torch.equal(a_memo, a_plain)
     # split build == whole build
     tables = m._engine.memo[L][1]
     rows = s.num_entries + 1
-    h, lib = m._engine.handles[L], _lib.lib()
     prev = None
     for level, whole in enumerate(tables, start=1):
         part = torch.full_like(whole, float("nan"))
