@@ -6,6 +6,7 @@ nvcc cross-compiles without a GPU; the CUDA runtime is linked statically so the
 library loads (and exports its symbols) on a CPU-only box too.
 """
 import concurrent.futures as cf
+import fcntl
 import hashlib
 import os
 import subprocess
@@ -18,8 +19,8 @@ INCLUDE = os.path.join(ROOT, "include")
 LIB = os.path.join(HERE, "libflid_b200.so")
 OBJ = os.path.join(HERE, "csrc", "_obj")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-         "-Xcompiler", "-fPIC", "-I", INCLUDE, "-I", CSRC]
+BASE_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC"]
+FLAGS = BASE_FLAGS + ["-I", INCLUDE, "-I", CSRC]
 
 
 def _sources():
@@ -34,7 +35,7 @@ def _digest():
             if os.path.isfile(p) and f.endswith((".cu", ".cuh", ".h")):
                 h.update(f.encode())
                 h.update(open(p, "rb").read())
-    h.update(" ".join(FLAGS).encode())
+    h.update(" ".join(BASE_FLAGS).encode())      # no absolute paths: the tree is copied to other boxes
     return h.hexdigest()
 
 
@@ -47,11 +48,28 @@ def _compile(src):
     return obj
 
 
+def _up_to_date(stamp, digest):
+    return os.path.isfile(LIB) and os.path.isfile(stamp) and open(stamp).read() == digest
+
+
 def build(force=False, verbose=True):
     stamp = os.path.join(OBJ, "digest.txt")
     digest = _digest()
-    if not force and os.path.isfile(LIB) and os.path.isfile(stamp) and open(stamp).read() == digest:
+    if not force and _up_to_date(stamp, digest):
         return LIB
+    # several ranks of one job may get here at once: build under an exclusive lock, re-check inside
+    os.makedirs(OBJ, exist_ok=True)
+    with open(os.path.join(OBJ, "build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and _up_to_date(stamp, digest):
+                return LIB
+            return _build_locked(stamp, digest, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(stamp, digest, verbose):
     if not os.path.isfile(NVCC):
         if os.path.isfile(LIB):
             return LIB  # GPU box without a toolkit: use the shipped binary
@@ -62,10 +80,12 @@ def build(force=False, verbose=True):
         print(f"[flid_b200.build] nvcc sm_100a: {', '.join(srcs)}", file=sys.stderr)
     with cf.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(_compile, srcs))
-    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    tmp_lib = LIB + ".tmp"
+    cmd = [NVCC, "-shared", "-o", tmp_lib, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp_lib, LIB)                      # atomic: a concurrent loader never sees a half-written file
     with open(stamp, "w") as f:
         f.write(digest)
     return LIB
