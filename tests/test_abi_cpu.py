@@ -59,9 +59,10 @@ def test_no_cpu_fallback():
     with pytest.raises(ValueError):
         flid_b200.NeighborSampler([[]], "bogus")
     m = flid_b200.TGAT(np.zeros((4, 172), np.float32), np.zeros((4, 172), np.float32), None, 100, 2, 2, 0.1, "cpu")
-    m.eval()
-    with pytest.raises(RuntimeError, match="no CPU fallback"):
-        m.compute_src_dst_node_temporal_embeddings(np.array([1]), np.array([2]), np.array([1.0]), 20)
+    for mode in (m.eval, m.train):
+        mode()
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            m.compute_src_dst_node_temporal_embeddings(np.array([1]), np.array([2]), np.array([1.0]), 20)
 
 
 def test_state_dict_keys_match_reference_layout():

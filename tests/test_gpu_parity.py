@@ -351,9 +351,55 @@ def test_tgat_errors():
             m.compute_src_dst_node_temporal_embeddings(np.array([10 ** 6]), np.array([1]), np.array([5.0]), 5)
         with pytest.raises(AssertionError):
             m.compute_src_dst_node_temporal_embeddings(np.array([1]), np.array([1]), np.array([5.0]), 0)
+
+
+@pytest.mark.parametrize("L,k,tdtype", [(2, 5, "f64"), (1, 20, "f64"), (2, 4, "f32")])
+def test_tgat_training_mode_forward_and_gradients(L, k, tdtype):
+    """Training-mode calls (M-step batches) go through the differentiable path: device-sampled
+    neighbourhoods + torch CUDA ops.  With dropout = 0 the values must match the oracle and the
+    eval kernels, and every parameter gradient must match the oracle's autograd."""
+    src, dst, eid, ts, nf, ef = cases.small_stream()
+    p = otgat.default_params(172, 172, 100, L, 2, seed=5, time_bias_scale=0.3)
+    s = make_sampler(src, dst, eid, ts, nf.shape[0] - 1)
+    m = flid_b200.TGAT(nf, ef, s, 100, L, 2, 0.0, DEV).to(DEV)
+    m.load_state_dict({kk: v for kk, v in p.items() if not kk.startswith("_")})
+    o = osamp.OracleSampler.from_events(src, dst, eid, ts, nf.shape[0] - 1)
+    sel = np.arange(440, 470)
+    tt = ts[sel] if tdtype == "f64" else ts[sel].astype(np.float32)
     m.train()
-    with pytest.raises(NotImplementedError):
-        m.compute_src_dst_node_temporal_embeddings(np.array([1]), np.array([1]), np.array([5.0]), 5)
+    a, b = m.compute_src_dst_node_temporal_embeddings(src[sel], dst[sel], tt, k)
+    assert a.requires_grad and a.device.type == "cuda"
+    g = torch.Generator().manual_seed(1)
+    wa, wb = torch.randn(a.shape, generator=g), torch.randn(b.shape, generator=g)
+    ((a * wa.to(DEV)).sum() + (b * wb.to(DEV)).sum()).backward()
+    # oracle: same weights as leaf tensors
+    po = {kk: (v.clone().requires_grad_(True) if torch.is_tensor(v) else v) for kk, v in p.items()}
+    nft, eft = torch.from_numpy(nf), torch.from_numpy(ef)
+    oa = otgat.embed(po, nft, eft, o, src[sel], tt, L, k)
+    ob = otgat.embed(po, nft, eft, o, dst[sel], tt, L, k)
+    ((oa * wa).sum() + (ob * wb).sum()).backward()
+    assert_fp32_close(a.detach().cpu().numpy(), oa.detach().numpy(), "train-mode src")
+    assert_fp32_close(b.detach().cpu().numpy(), ob.detach().numpy(), "train-mode dst")
+    for name, prm in m.named_parameters():
+        want = po[name].grad
+        assert prm.grad is not None, name
+        got = prm.grad.cpu()
+        # Frobenius-relative: a ReLU unit whose pre-activation sits within rounding of 0 may flip between the
+        # two implementations and change one row of a weight gradient, which a max-norm test would trip on
+        rel = float((got - want).norm()) / max(float(want.norm()), 1e-6)
+        assert rel <= 2e-3, (name, rel)
+    # the eval kernels agree with the differentiable path
+    m.eval()
+    with torch.no_grad():
+        ea, eb = m.compute_src_dst_node_temporal_embeddings(src[sel], dst[sel], tt, k)
+    assert_fp32_close(ea.cpu().numpy(), a.detach().cpu().numpy(), "eval kernels vs training path")
+    # dropout is live in training mode
+    m2 = flid_b200.TGAT(nf, ef, s, 100, L, 2, 0.5, DEV).to(DEV)
+    m2.load_state_dict(m.state_dict())
+    m2.train()
+    d1, _ = m2.compute_src_dst_node_temporal_embeddings(src[sel], dst[sel], tt, k)
+    d2, _ = m2.compute_src_dst_node_temporal_embeddings(src[sel], dst[sel], tt, k)
+    assert not torch.equal(d1, d2)
 
 
 # ===================================================================== TGN
