@@ -369,7 +369,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the graph (debugging only; 1.0 = BASELINE config)")
     ap.add_argument("--memo", default="on", choices=["on", "off"],
                     help="layer memo of the bulk pass (off = the reference's recursion, 22 evaluations per root)")
-    ap.add_argument("--ref-batches", type=int, default=60, help="oracle calls of 200 events in the CPU sample")
+    ap.add_argument("--ref-batches", type=int, default=120, help="oracle calls of 200 events in the CPU sample")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

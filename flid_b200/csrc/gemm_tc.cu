@@ -446,14 +446,14 @@ int tc_gemm(const TcGemmArgs& g, const TcWeight& w, cudaStream_t st) {
     FLID_REQUIRE(g.w0 > 0 && g.w0 + g.w1 == w.K, "tc_gemm: A width %d+%d != weight K %d", g.w0, g.w1, w.K);
     FLID_REQUIRE((g.w0 % 4) == 0 && (g.w1 % 4) == 0 && (g.lda0 % 4) == 0 && (g.lda1 % 4) == 0,
                  "tc_gemm: segment widths / row strides must be multiples of 4 floats");
-    static int sm_count = 0, smem_max = 0, ms_cap = 2;
+    static int sm_count = 0, smem_max = 0, ms_cap = 1;
     if (sm_count == 0) {
         int dev = 0;
         FLID_CUDA(cudaGetDevice(&dev));
         FLID_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
         FLID_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
         const char* e = getenv("FLID_GEMM_MS");  // development knob: cap the sub-tiles per work item
-        if (e && e[0] >= '1' && e[0] <= '3') ms_cap = e[0] - '0';
+        if (e && e[0] >= '1' && e[0] <= '2') ms_cap = e[0] - '0';
     }
     TcShape sh;
     sh.trace = nullptr;
@@ -473,26 +473,22 @@ int tc_gemm(const TcGemmArgs& g, const TcWeight& w, cudaStream_t st) {
         sh.reps = reps, sh.rep_stride = (int64_t)(w.image_bytes() / 16);
     }
     sh.N = w.N, sh.n_tile = w.n_tile, sh.n_blocks = w.n_blocks, sh.k_chunks = w.k_chunks;
-    // Sub-tiles per work item: minimise a small cost model of cycles per row -- per K chunk the
-    // slower of the MMAs (3 per 8 K-elements, n_tile / 2 cycles each) and the L2 -> SM traffic
-    // (A rows + the hi/lo weight chunk at ~43 B/cycle/SM, the chip-wide L2 cap shared by 148 SMs),
-    // plus the epilogue when the accumulators cannot be double-buffered in the 512 TMEM columns.
+    // Sub-tiles per work item.  Measured on the B200 (tools/gemm_probe.py, M = 65 536): sharing a
+    // weight stage between two sub-tiles halves the weight traffic but was 10-25 % slower on every
+    // shape (accumulators can no longer be double-buffered, so the epilogue is exposed, and the
+    // ring holds fewer stages than the ~4500-cycle L2 latency under load needs).  One sub-tile is
+    // the default; FLID_GEMM_MS=2 keeps the other variant reachable for experiments.
     int ms = 1;
-    double best = 1e30;
-    for (int cand = 1; cand <= ms_cap; ++cand) {
+    for (int cand = ms_cap; cand > 1; --cand) {
         const size_t stage = (size_t)cand * A_SUB + 2 * (size_t)C4 * w.n_tile * 16;
-        const bool fits = cand * w.n_tile <= 512 && (size_t)(smem_max - 1024) / stage >= 3;
-        const bool fills = cand == 1 || ceil_div(g.M, cand * 128) * w.n_blocks >= (int64_t)sm_count;
-        if (!fits || !fills) continue;
-        const double mma = cand * (KC / 8) * 3 * (w.n_tile / 2.0);
-        const double l2 = (cand * 128.0 * KC * 4 + 2.0 * C4 * w.n_tile * 16) / 43.0;
-        const double epi = 2 * cand * w.n_tile <= 512 ? 0.0 : cand * (w.n_tile / 16.0) * 150.0;
-        const double per_row = (w.k_chunks * (mma > l2 ? mma : l2) + epi) / (cand * 128.0);
-        if (per_row < best * 0.97) best = per_row, ms = cand;  // prefer fewer sub-tiles on near-ties
+        if (cand * w.n_tile <= 512 && (size_t)(smem_max - 1024) / stage >= 3 &&
+            ceil_div(g.M, cand * 128) * w.n_blocks >= (int64_t)sm_count) {
+            ms = cand;
+            break;
+        }
     }
     int rc;
     switch (ms) {
-        case 3: rc = launch_ms<3>(g, w, sh, sm_count, smem_max, st); break;
         case 2: rc = launch_ms<2>(g, w, sh, sm_count, smem_max, st); break;
         default: rc = launch_ms<1>(g, w, sh, sm_count, smem_max, st); break;
     }

@@ -596,3 +596,58 @@ def test_e_step_pass_matches_oracle_pipeline():
         assert clear.float().mean() > 0.95
         assert torch.equal(pseudo.cpu()[0][clear], want[0][clear])
     assert len(store_gpu) == 3
+
+
+# ===================================================================== full-size properties
+def test_full_size_reddit_shape_properties():
+    """BASELINE.json configs[2] at full size (10 984 nodes / 672 447 edges), where the oracle would
+    take the better part of an hour: size-independent properties instead.
+      * sampler: right-aligned zero padding, strictly-earlier and non-decreasing timestamps, every
+        returned (neighbour, edge, time) triple is an entry of the queried node, for all 1.34 M roots;
+      * embeddings: the memoised bulk pass, the recursion and a permuted / re-chunked evaluation of
+        the same roots agree bit for bit; a sample of roots agrees with the oracle within 1e-4."""
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    g = synth.reddit_shape(seed=0, scale=1.0)
+    e = g.num_interactions
+    s = flid_b200.get_neighbor_sampler(g, "recent", seed=1, device=DEV)
+    nodes = np.concatenate([g.src_node_ids, g.dst_node_ids])
+    times = np.concatenate([g.node_interact_times, g.node_interact_times])
+    nbr, eid, ts = s.get_historical_neighbors(nodes, times, 20)
+    pad = nbr == 0
+    assert (pad[:, :-1] >= pad[:, 1:]).all(), "padding must be on the left"
+    assert ((eid == 0) == pad).all() and (ts[pad] == 0).all()
+    assert (ts.astype(np.float64) < times[:, None])[~pad].all(), "neighbours must be strictly earlier"
+    both = ~pad[:, 1:] & ~pad[:, :-1]
+    assert (np.diff(ts, axis=1)[both] >= 0).all(), "timestamps must be non-decreasing"
+    ev = eid[~pad] - 1                                            # edge ids are 1..E in event order
+    owner = np.repeat(nodes, 20).reshape(-1, 20)[~pad]
+    other = np.where(g.src_node_ids[ev] == owner, g.dst_node_ids[ev], g.src_node_ids[ev])
+    assert ((g.src_node_ids[ev] == owner) | (g.dst_node_ids[ev] == owner)).all()
+    assert (other == nbr[~pad]).all() and (g.node_interact_times[ev].astype(np.float32) == ts[~pad]).all()
+    # the k most recent: the number of valid slots is min(k, number of earlier interactions of the node)
+    order = np.argsort(nodes, kind="stable")
+    # embeddings
+    p = otgat.default_params(172, 172, 100, 2, 2, seed=2, time_bias_scale=0.1)
+    m = flid_b200.TGAT(g.node_raw_features, g.edge_raw_features, s, 100, 2, 2, 0.1, DEV).to(DEV)
+    m.load_state_dict({k: v for k, v in p.items() if not k.startswith("_")})
+    m.eval()
+    with torch.no_grad():
+        a, b = passes.embed_events(m, g.src_node_ids, g.dst_node_ids, g.node_interact_times, 20)   # memoised bulk pass
+        assert 2 in m._engine.memo
+        rs = np.random.RandomState(0)
+        sel = np.sort(rs.choice(e, 3000, replace=False))
+        m.set_layer_memo(False)
+        pa, pb = m.compute_src_dst_node_temporal_embeddings(g.src_node_ids[sel], g.dst_node_ids[sel],
+                                                            g.node_interact_times[sel], 20)          # the recursion
+        assert torch.equal(a[sel], pa) and torch.equal(b[sel], pb)
+        perm = rs.permutation(len(sel))
+        qa, _ = m.compute_src_dst_node_temporal_embeddings(g.src_node_ids[sel][perm], g.dst_node_ids[sel][perm],
+                                                           g.node_interact_times[sel][perm], 20)
+        assert torch.equal(qa, pa[perm])
+    assert torch.isfinite(a).all() and torch.isfinite(b).all()
+    o = osamp.OracleSampler.from_events(g.src_node_ids, g.dst_node_ids, g.edge_ids, g.node_interact_times, g.num_nodes)
+    few = sel[::100]
+    wa, wb = otgat.embed_src_dst(p, torch.from_numpy(g.node_raw_features), torch.from_numpy(g.edge_raw_features), o,
+                                 g.src_node_ids[few], g.dst_node_ids[few], g.node_interact_times[few], 2, 20)
+    assert_fp32_close(a[few].cpu().numpy(), wa.numpy(), "full-size src vs oracle")
+    assert_fp32_close(b[few].cpu().numpy(), wb.numpy(), "full-size dst vs oracle")
