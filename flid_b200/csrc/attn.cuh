@@ -1,4 +1,4 @@
-// Attention stream: gather + cos time encoding + masked softmax + weighted sum (see attn.cu).
+// Attention stream: gather + cos time encoding + masked softmax + weighted sum (see attn_packed.cu).
 #pragma once
 #include "common.cuh"
 
@@ -23,7 +23,6 @@ struct AttnArgs {
     int k, dn, de, T;
 };
 
-int launch_attn(const AttnArgs& a, int H, cudaStream_t st);         // packed-pair kernel (attn_packed.cu)
-int launch_attn_scalar(const AttnArgs& a, int H, cudaStream_t st);  // scalar-FFMA predecessor, FLID_ATTN=scalar
+int launch_attn(const AttnArgs& a, int H, cudaStream_t st);  // attn_packed.cu
 
 }  // namespace flid

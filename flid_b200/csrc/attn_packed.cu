@@ -18,9 +18,6 @@
 // Padded slots (neighbour id 0) contribute exp(-1e10 - max) == 0 in the reference, so they are
 // skipped; a target with no neighbour at all gets the reference's uniform 1/k over its padded
 // rows (models/modules.py:217-224).
-#include <stdlib.h>
-#include <string.h>
-
 #include "attn.cuh"
 
 namespace flid {
@@ -346,12 +343,6 @@ int launch_h(const AttnArgs& a, int nv, int tp, cudaStream_t st) {
 
 int launch_attn(const AttnArgs& a, int H, cudaStream_t st) {
     if (a.n <= 0) return FLID_OK;
-    static int scalar = -1;
-    if (scalar < 0) {
-        const char* v = getenv("FLID_ATTN");
-        scalar = (v && strcmp(v, "scalar") == 0) ? 1 : 0;
-    }
-    if (scalar) return launch_attn_scalar(a, H, st);
     const int nv = (int)ceil_div((a.dn + a.de) / 4, 32), tp = (int)ceil_div(a.T, 64);
     switch (H) {
         case 1: return launch_h<1>(a, nv, tp, st);

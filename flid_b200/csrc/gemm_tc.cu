@@ -12,14 +12,24 @@
 //   warp  13    loader    : one thread bulk-copies (cp.async.bulk, SASS UBLKCP) the pre-tiled
 //                           weight chunk of every stage as soon as the stage is free
 //
-// What bounds this kernel is not the tensor pipe but L2 -> SM traffic: with hi/lo images the
+// What bounds this kernel is not the tensor pipe but the L2 -> SM path.  With hi/lo images the
 // weights are 8 B per element and every 128-row tile re-streams all of them (out-projection:
-// 1.9 MB per tile, 2.25x the bytes of the A tile itself; measured: the bare barrier/copy
-// skeleton without loads, stores or MMAs ran at 107 us of a 250 us launch, profiles/).  So one
-// CTA work item is a group of MS 128-row sub-tiles that share every weight stage (MS
-// accumulators side by side in TMEM), which divides the weight traffic by MS.  K is streamed in
-// chunks of 16 floats through a ring of shared-memory stages; when two accumulator sets fit in
-// the 512 TMEM columns the epilogue of one group overlaps the MMAs of the next.
+// 1.9 MB per tile, 2.25x the bytes of the A tile itself), so a launch moves ~1.45 GB through L2
+// for 0.23 GB of A.  Measured on the B200 (per-stage clock64 stamps of one CTA, FLID_GEMM_TRACE):
+// the producers finish a stage ~4400 cycles before the issuer sees it full; what it waits for is
+// the weight bulk copy, ~4700 cycles after issue with 5-6 copies in flight, i.e. ~28 B/cycle/SM
+// of combined ingest -- the chip-wide L2 read rate divided by 148.  Switching off loads, smem
+// stores, MMAs and C stores one at a time confirmed it: without any of them the barrier + copy
+// skeleton alone needs 107 us of a 250 us launch.  Design consequences kept in this file:
+//   * K chunks of 16 floats and as many ring stages as fit (6 at n_tile = 144): bytes in flight
+//     per SM, not stage count, is what buys throughput;
+//   * a dedicated loader thread, so a copy is issued the moment its stage is free;
+//   * two producer groups, so the per-stage drain/fence/arrive tail is off the critical path;
+//   * optionally MS 128-row sub-tiles per work item sharing every weight stage (MS accumulators
+//     side by side in TMEM) -- halves the weight traffic, but the accumulators can then no longer
+//     be double-buffered and the ring gets shallower; measured slower, off by default.
+// The weight image is also kept in TC_REPLICAS copies read round-robin by CTA (no measurable
+// effect: the stall is bandwidth, not slice hot-spotting; kept at 1 replica in use by default).
 #include "gemm_tc.cuh"
 
 #include <stdlib.h>
