@@ -99,6 +99,16 @@ def build_problem(scale):
     return synth.reddit_shape(seed=0, scale=scale)
 
 
+def measured_traffic_per_eval():
+    """DRAM bytes per attention evaluation from the committed ncu --set full capture (profiles/)."""
+    path = os.path.join(ROOT, "profiles", "r1_attention_traffic.json")
+    try:
+        d = json.load(open(path))
+        return float(d["dram_bytes_per_eval"]), d["capture"]
+    except Exception:
+        return None, None
+
+
 def algorithmic_bytes(evals_l1, evals_l2, valid_slots, k):
     """SURVEY.md 8(d) A(k, l), with the measured number of valid (non-padded) neighbour slots
     instead of k for the gathered rows: per slot 4*dn + 4*de gathered, per evaluation 20*k index
@@ -320,6 +330,8 @@ def run_ours(args, rank, world, local_rank):
         attn_ms, attn_n = prof_ms[2], prof_n[2]
         peak, peak_src = measured_peaks()
         achieved = (alg * args.steps / 1e9) / (attn_ms / 1000.0) if attn_ms > 0 else 0.0
+        per_eval, traffic_src = measured_traffic_per_eval()
+        traffic = per_eval * (evals_l1 + evals_l2) * args.steps / max(attn_n, 1) if per_eval else None
         cores = os.cpu_count() or 1
         cpu_base = None
         if world == 1:     # reported on rank 0 at N = 1 only (torchrun pins OMP to one thread per rank)
@@ -345,7 +357,7 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "attn_pk_kernel<2,3,2> (gather + time-encode + masked softmax + "
                          "weighted sum, packed fp32 pairs)", "attention_evals_per_step": int(evals_l1 + evals_l2), "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg * args.steps / max(attn_n, 1),
                          "launches": int(attn_n), "avg_launch_ms": attn_ms / max(attn_n, 1),
                          "kernel_ms_per_step": {"level_sample": prof_ms[0] / args.steps,
