@@ -177,8 +177,9 @@ int flid_tgn_step(flid_tgat* m, const flid_graph* g, const flid_tgn_state* s, co
                   const double* times, const int64_t* eids, int64_t batch, int positive, int k, float* out,
                   int32_t* err_flag, flid_stream stream) {
     using namespace flid;
-    FLID_REQUIRE(m && g && s && gru && node_raw && edge_feat && src && dst && times && out && err_flag,
+    FLID_REQUIRE(m && g && s && gru && node_raw && edge_feat && src && dst && times && err_flag,
                  "flid_tgn_step: null argument");
+    FLID_REQUIRE(out != nullptr || positive, "flid_tgn_step: nothing to do (no output buffer and no state update)");
     FLID_REQUIRE(m->have_weights, "flid_tgn_step: weights not set");
     FLID_REQUIRE(k > 0 && k <= 32, "flid_tgn_step: num_neighbors must be in 1..32");
     FLID_REQUIRE(!positive || eids, "flid_tgn_step: edge_ids are required for positive edges");
@@ -196,7 +197,8 @@ int flid_tgn_step(flid_tgat* m, const flid_graph* g, const flid_tgn_state* s, co
                                                                err_flag);
     FLID_LAUNCH_CHECK();
     // (1)+(2): embeddings on memory' + raw   (models/MemoryModel.py:117-146)
-    FLID_TRY(tgat_embed_ids(m, g, s->layer0, edge_feat, ids, t2, n2, n2, k, out, st));
+    // out == nullptr: state update only (the training-mode host path computes the embeddings itself)
+    if (out != nullptr) FLID_TRY(tgat_embed_ids(m, g, s->layer0, edge_feat, ids, t2, n2, n2, k, out, st));
     if (!positive) return FLID_OK;
     // (3): persist, elect, build messages, refresh the incremental GRU state (:155-180)
     tgn_persist_kernel<<<(unsigned)ceil_div(n2 * 32, 256), 256, 0, st>>>(*s, ids, n2, m->dn, err_flag);

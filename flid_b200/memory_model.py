@@ -19,7 +19,7 @@ import torch.nn as nn
 
 from . import _lib
 from .sampler import NeighborSampler
-from .tgat import MergeLayer, MultiHeadAttention, TimeEncoder, _Engine
+from .tgat import MergeLayer, MultiHeadAttention, TimeEncoder, _Engine, autograd_forward
 
 
 class MessageAggregator(nn.Module):
@@ -264,8 +264,6 @@ class MemoryModel(nn.Module):
         """models/MemoryModel.py:96-189."""
         dev = self.node_raw_features.device
         _lib.require_cuda(dev)
-        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("flid_b200.MemoryModel: forward-only fused path; call under torch.no_grad() / eval()")
         sampler = self.embedding_module.neighbor_sampler
         if not isinstance(sampler, NeighborSampler):
             raise TypeError("flid_b200.MemoryModel needs a flid_b200.NeighborSampler")
@@ -273,6 +271,9 @@ class MemoryModel(nn.Module):
             assert edge_ids is not None
         b = len(src_node_ids)
         emb = self.embedding_module
+        if self.training or (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())):
+            return self._autograd_step(sampler, src_node_ids, dst_node_ids, node_interact_times, edge_ids,
+                                       edges_are_positive, num_neighbors)
         with torch.cuda.device(dev):
             h = self._engine.handle(self.num_layers, self.time_encoder, emb.temporal_conv_layers, emb.merge_layers, dev)
             self._sync(h)
@@ -294,6 +295,55 @@ class MemoryModel(nn.Module):
                 if err == 1:
                     raise AssertionError("Trying to update memory to time in the past!")
                 raise IndexError("flid_b200.MemoryModel: node or edge id out of range")
+        return out[:b], out[b:]
+
+    def _autograd_step(self, sampler, src_node_ids, dst_node_ids, node_interact_times, edge_ids, positive, k):
+        """Training-mode batch (models/MemoryModel.py:96-189 with dropout and a backward pass).
+        Differentiable part in torch CUDA ops: the GRU update of every node with a pending message
+        (get_updated_memories, :190-212 -- the path the memory updater's gradients take) and the
+        embedding on ``memory' + raw`` over device-sampled neighbourhoods.  The stored messages are
+        constants, as they are in the reference after ``detach_memory_bank``.  The state update
+        (persist, last-message election, new raw messages, :155-180) is the same C call as in eval
+        mode, run without an output buffer."""
+        dev = self.node_raw_features.device
+        bank, emb = self.memory_bank, self.embedding_module
+        b = len(src_node_ids)
+        with torch.cuda.device(dev):
+            h = self._engine.handle(self.num_layers, self.time_encoder, emb.temporal_conv_layers, emb.merge_layers, dev)
+            self._sync(h)
+            mem = bank.node_memories.data
+            idx = torch.nonzero(bank._has_pending).reshape(-1)
+            mem_view = mem
+            if idx.numel():
+                tf = bank._pending_ts[idx].to(torch.float32)
+                assert bool((bank.node_last_updated_times.data[idx] <= tf).all()), \
+                    "Trying to update memory to time in the past!"
+                upd = self.memory_updater.memory_updater(bank._pending_msg[idx], mem[idx])
+                mem_view = mem.index_put((idx,), upd)
+            layer0 = mem_view + self.node_raw_features
+            ids = np.concatenate([np.asarray(src_node_ids), np.asarray(dst_node_ids)])
+            tt = np.concatenate([np.asarray(node_interact_times), np.asarray(node_interact_times)])
+            out = autograd_forward(self.time_encoder, emb.temporal_conv_layers, emb.merge_layers, sampler, layer0,
+                                   self.edge_raw_features, ids, tt, self.num_layers, num_neighbors=k,
+                                   training=self.training)
+            if positive:
+                if self._err is None or self._err.device != dev:
+                    self._err = torch.zeros(1, dtype=torch.int32, device=dev)
+                d_src = _lib.to_device(src_node_ids, np.int64, dev, "g_src")
+                d_dst = _lib.to_device(dst_node_ids, np.int64, dev, "g_dst")
+                d_t = _lib.to_device(node_interact_times, np.float64, dev, "g_t")
+                d_e = _lib.to_device(edge_ids, np.int64, dev, "g_e")
+                s, g = bank._c_state(), self._gru()
+                _lib.check(_lib.lib().flid_tgn_step(h, sampler.handle, C.byref(s), C.byref(g),
+                                                    _lib.ptr(self.node_raw_features), _lib.ptr(self.edge_raw_features),
+                                                    _lib.ptr(d_src), _lib.ptr(d_dst), _lib.ptr(d_t), _lib.ptr(d_e), b, 1,
+                                                    int(k), None, _lib.ptr(self._err), _lib.stream()))
+                err = int(self._err.item())
+                if err:
+                    self._err.zero_()
+                    if err == 1:
+                        raise AssertionError("Trying to update memory to time in the past!")
+                    raise IndexError("flid_b200.MemoryModel: node or edge id out of range")
         return out[:b], out[b:]
 
     def set_neighbor_sampler(self, neighbor_sampler: NeighborSampler):

@@ -203,7 +203,9 @@ int flid_tgn_rebuild(flid_tgat* m, const flid_tgn_state* s, const flid_gru_weigh
  * pending updates of the batch nodes, build their new raw messages (dst role stored
  * after src role, so it wins) and refresh next_memories/layer0.  err_flag (device int32)
  * is set to 1 if the reference's "update memory to time in the past" assertion would fire
- * and to 2 if a node / edge id is out of range (the id is then clamped to padding).      */
+ * and to 2 if a node / edge id is out of range (the id is then clamped to padding).
+ * out may be null with positive != 0: only the state update runs (training-mode calls compute
+ * their embeddings through autograd on the host side).                                   */
 int flid_tgn_step(flid_tgat* m, const flid_graph* g, const flid_tgn_state* s, const flid_gru_weights* gru,
                   const float* node_raw, const float* edge_feat, const int64_t* src, const int64_t* dst,
                   const double* times, const int64_t* eids, int64_t batch, int positive, int k,

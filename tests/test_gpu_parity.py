@@ -490,6 +490,72 @@ def test_tgn_time_travel_is_rejected():
                                                            eid[lo:lo + 20], True, 5)
 
 
+def test_tgn_training_mode_matches_eval_kernels_and_finite_differences():
+    """Training-mode TGN batches take the differentiable path (torch GRU + attention on device-sampled
+    neighbourhoods, same C state update).  With dropout = 0 it must track the eval kernels batch by
+    batch, leave the same memory state, and its gradients must agree with central finite differences
+    taken through the *eval kernels* (an independent implementation)."""
+    src, dst, eid, ts, nf, ef = cases.small_stream()
+    L, k, bs = 1, 5, 20
+    p = otgn.default_params(172, 172, 100, L, 2, seed=8, time_bias_scale=0.2)
+    s = make_sampler(src, dst, eid, ts, nf.shape[0] - 1)
+
+    def build(dropout):
+        m = flid_b200.MemoryModel(nf, ef, s, 100, "TGN", L, 2, dropout, device=DEV).to(DEV)
+        missing = m.load_state_dict({kk: v for kk, v in p.items() if not kk.startswith("_")}, strict=False)
+        assert not missing.unexpected_keys
+        m.memory_bank.__init_memory_bank__()
+        return m
+
+    ev, tr = build(0.0), build(0.0)
+    ev.eval(), tr.train()
+    g = torch.Generator().manual_seed(3)
+    for bi in range(6):
+        sl = slice(200 + bi * bs, 200 + (bi + 1) * bs)
+        if bi == 5:
+            backup_ev = ev.memory_bank.backup_memory_bank()
+        with torch.no_grad():
+            ea, eb = ev.compute_src_dst_node_temporal_embeddings(src[sl], dst[sl], ts[sl], eid[sl], True, k)
+        ta, tb = tr.compute_src_dst_node_temporal_embeddings(src[sl], dst[sl], ts[sl], eid[sl], True, k)
+        assert ta.requires_grad
+        assert_fp32_close(ta.detach().cpu().numpy(), ea.cpu().numpy(), f"batch {bi} src")
+        assert_fp32_close(tb.detach().cpu().numpy(), eb.cpu().numpy(), f"batch {bi} dst")
+        tr.memory_bank.detach_memory_bank()
+    assert torch.equal(ev.memory_bank.node_memories.data, tr.memory_bank.node_memories.data)
+    assert torch.equal(ev.memory_bank.node_last_updated_times.data, tr.memory_bank.node_last_updated_times.data)
+    assert torch.equal(ev.memory_bank._pending_msg, tr.memory_bank._pending_msg)
+    # gradients of the last batch
+    wa, wb = torch.randn(ta.shape, generator=g).to(DEV), torch.randn(tb.shape, generator=g).to(DEV)
+    ((ta * wa).sum() + (tb * wb).sum()).backward()
+    cell = tr.memory_updater.memory_updater
+    for prm in (cell.weight_ih, cell.weight_hh, cell.bias_ih, cell.bias_hh, tr.time_encoder.w.bias,
+                tr.embedding_module.merge_layers[0].fc2.bias):
+        assert prm.grad is not None and torch.isfinite(prm.grad).all() and float(prm.grad.abs().max()) > 0
+
+    def eval_loss():
+        ev.memory_bank.reload_memory_bank(backup_ev)
+        with torch.no_grad():
+            a, b = ev.compute_src_dst_node_temporal_embeddings(src[sl], dst[sl], ts[sl], eid[sl], False, k)
+        return float(((a * wa).sum() + (b * wb).sum()).double())
+
+    checks = [("memory_updater.memory_updater.bias_ih", cell.bias_ih, ev.memory_updater.memory_updater.bias_ih),
+              ("memory_updater.memory_updater.bias_hh", cell.bias_hh, ev.memory_updater.memory_updater.bias_hh),
+              ("merge fc2 bias", tr.embedding_module.merge_layers[0].fc2.bias, ev.embedding_module.merge_layers[0].fc2.bias)]
+    for name, ptr_tr, ptr_ev in checks:
+        j = int(ptr_tr.grad.abs().argmax())
+        eps = 2e-2
+        with torch.no_grad():
+            ptr_ev[j] += eps
+        lp = eval_loss()
+        with torch.no_grad():
+            ptr_ev[j] -= 2 * eps
+        lm = eval_loss()
+        with torch.no_grad():
+            ptr_ev[j] += eps
+        fd, an = (lp - lm) / (2 * eps), float(ptr_tr.grad[j])
+        assert abs(fd - an) <= 3e-2 * max(1.0, abs(an)), (name, fd, an)
+
+
 # ===================================================================== pseudo labels
 @pytest.mark.parametrize("C", [2, 5])
 def test_pseudo_label_golden(C):
