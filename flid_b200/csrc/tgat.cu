@@ -139,44 +139,79 @@ __global__ void __launch_bounds__(256) level_sample_kernel(
 
 // ------------------------------------------------------------------ residual + LayerNorm
 // out = LayerNorm(O + [h_self | te0])   (models/modules.py:235-238; O already holds
-// residual_fc's output incl. bias).  One warp per row.
+// residual_fc's output incl. bias).  One warp per row, 16-byte accesses, two rows in flight per
+// warp (a row is only ~1 KB: with one row per warp the kernel sat at a third of HBM bandwidth).
+template <int NV>  // float4 per lane: ceil(qd / 128)
 __global__ void __launch_bounds__(256) ln_kernel(const float* __restrict__ O, const float* __restrict__ self_base,
                                                  const int32_t* __restrict__ self_idx, const float* __restrict__ te0,
                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
                                                  float* __restrict__ A, int64_t n, int dn, int T) {
-    constexpr int MAXR = 16;
+    constexpr int R = 2;
     const int lane = threadIdx.x & 31;
-    const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    if (i >= n) return;
-    const int qd = dn + T;
-    const float* self = self_base + (self_idx ? (int64_t)__ldg(self_idx + i) : i) * (int64_t)dn;
-    float x[MAXR];
-    float s = 0.f;
+    const int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int qd = dn + T, q4 = qd >> 2, d4 = dn >> 2;
+    const float inv_qd = 1.0f / (float)qd;
+    float4 x[R][NV];
 #pragma unroll
-    for (int r = 0; r < MAXR; ++r) {
-        const int c = lane + 32 * r;
-        x[r] = 0.f;
-        if (c < qd) {
-            x[r] = O[i * qd + c] + (c < dn ? __ldg(self + c) : __ldg(te0 + (c - dn)));
-            s += x[r];
+    for (int r = 0; r < R; ++r) {
+        const int64_t i = w * R + r;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const int f = lane + 32 * v;
+            x[r][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < n && f < q4) {
+                const float4 o = __ldg(reinterpret_cast<const float4*>(O + i * qd) + f);
+                const float* self = self_base + (self_idx ? (int64_t)__ldg(self_idx + i) : i) * (int64_t)dn;
+                const float4 s4 = f < d4 ? __ldg(reinterpret_cast<const float4*>(self) + f)
+                                         : __ldg(reinterpret_cast<const float4*>(te0) + (f - d4));
+                x[r][v] = make_float4(o.x + s4.x, o.y + s4.y, o.z + s4.z, o.w + s4.w);
+            }
         }
     }
-    const float mean = warp_sum(s) / (float)qd;
-    float v = 0.f;
 #pragma unroll
-    for (int r = 0; r < MAXR; ++r) {
-        const int c = lane + 32 * r;
-        if (c < qd) {
-            const float d = x[r] - mean;
-            v = fmaf(d, d, v);
+    for (int r = 0; r < R; ++r) {
+        const int64_t i = w * R + r;
+        if (i >= n) break;  // warp-uniform
+        float s = 0.f;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) s += (x[r][v].x + x[r][v].y) + (x[r][v].z + x[r][v].w);
+        const float mean = warp_sum(s) * inv_qd;
+        float q = 0.f;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            if (lane + 32 * v < q4) {
+                const float a = x[r][v].x - mean, b = x[r][v].y - mean, c = x[r][v].z - mean, d = x[r][v].w - mean;
+                q = fmaf(a, a, q), q = fmaf(b, b, q), q = fmaf(c, c, q), q = fmaf(d, d, q);
+            }
+        }
+        const float rstd = 1.0f / sqrtf(warp_sum(q) * inv_qd + 1e-5f);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const int f = lane + 32 * v;
+            if (f < q4) {
+                const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + f);
+                const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + f);
+                float4 y;
+                y.x = fmaf((x[r][v].x - mean) * rstd, gm.x, bt.x);
+                y.y = fmaf((x[r][v].y - mean) * rstd, gm.y, bt.y);
+                y.z = fmaf((x[r][v].z - mean) * rstd, gm.z, bt.z);
+                y.w = fmaf((x[r][v].w - mean) * rstd, gm.w, bt.w);
+                reinterpret_cast<float4*>(A + i * qd)[f] = y;
+            }
         }
     }
-    const float rstd = 1.0f / sqrtf(warp_sum(v) / (float)qd + 1e-5f);
-#pragma unroll
-    for (int r = 0; r < MAXR; ++r) {
-        const int c = lane + 32 * r;
-        if (c < qd) A[i * qd + c] = fmaf((x[r] - mean) * rstd, __ldg(gamma + c), __ldg(beta + c));
-    }
+}
+
+static int launch_ln(const float* O, const float* self_base, const int32_t* self_idx, const float* te0,
+                     const float* gamma, const float* beta, float* A, int64_t n, int dn, int T, cudaStream_t st) {
+    const int q4 = (dn + T) / 4;
+    const unsigned blocks = (unsigned)ceil_div(ceil_div(n, 2) * 32, 256);
+    if (q4 <= 96)
+        ln_kernel<3><<<blocks, 256, 0, st>>>(O, self_base, self_idx, te0, gamma, beta, A, n, dn, T);
+    else
+        ln_kernel<4><<<blocks, 256, 0, st>>>(O, self_base, self_idx, te0, gamma, beta, A, n, dn, T);
+    FLID_LAUNCH_CHECK();
+    return FLID_OK;
 }
 
 // ------------------------------------------------------------------ host pipeline
@@ -210,9 +245,7 @@ static int output_chain(flid_tgat* m, int layer, int64_t n, const float* Z, cons
         TcGemmArgs t1;
         t1.A0 = Z, t1.lda0 = m->zw, t1.w0 = m->zw, t1.C = O, t1.ldc = m->qd, t1.bias = ld.res_b, t1.M = n;
         FLID_TRY(tc_gemm(t1, ld.tc_o, st));
-        ln_kernel<<<(unsigned)ceil_div(n * 32, 256), 256, 0, st>>>(O, self_base, self_idx, m->te0, ld.ln_w, ld.ln_b, A,
-                                                                   n, m->dn, m->T);
-        FLID_LAUNCH_CHECK();
+        FLID_TRY(launch_ln(O, self_base, self_idx, m->te0, ld.ln_w, ld.ln_b, A, n, m->dn, m->T, st));
         TcGemmArgs t2;   // fc1 on [attention output | layer-0 row of the target], ReLU fused
         t2.A0 = A, t2.lda0 = m->qd, t2.w0 = m->qd, t2.A1 = merge_feat, t2.lda1 = m->dn, t2.idx1 = ids, t2.w1 = m->dn;
         t2.C = Hd, t2.ldc = m->dn, t2.bias = ld.fc1_b, t2.M = n, t2.relu = 1;
@@ -223,9 +256,7 @@ static int output_chain(flid_tgat* m, int layer, int64_t n, const float* Z, cons
     }
     GemmArgs g1{Z, m->zw, nullptr, ld.wvoT, m->zw, O, m->qd, ld.res_b, n, m->qd, m->zw, 0, 0};
     FLID_TRY(launch_gemm(g1, st));
-    ln_kernel<<<(unsigned)ceil_div(n * 32, 256), 256, 0, st>>>(O, self_base, self_idx, m->te0, ld.ln_w, ld.ln_b, A, n,
-                                                               m->dn, m->T);
-    FLID_LAUNCH_CHECK();
+    FLID_TRY(launch_ln(O, self_base, self_idx, m->te0, ld.ln_w, ld.ln_b, A, n, m->dn, m->T, st));
     const int64_t ld1 = m->qd + m->dn;
     GemmArgs g2{A, m->qd, nullptr, ld.fc1_w, ld1, Hd, m->dn, nullptr, n, m->dn, m->qd, 0, 0};
     FLID_TRY(launch_gemm(g2, st));
