@@ -49,12 +49,13 @@ __global__ void __launch_bounds__(256) gemm_nt_kernel(GemmArgs g) {
     for (int i = 0; i < 4; ++i) {
         const int64_t m = m0 + ty * 4 + i;
         if (m >= g.M) continue;
+        const int64_t mrow = g.c_idx ? (int64_t)__ldg(g.c_idx + m) : m;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int n = n0 + tx * 4 + j;
             if (n >= g.N) continue;
             float v = acc[i][j];
-            float* c = g.C + m * g.ldc + n;
+            float* c = g.C + mrow * g.ldc + n;
             if (g.accumulate) v += *c;
             if (g.bias) v += __ldg(g.bias + n);
             if (g.relu) v = fmaxf(v, 0.f);

@@ -21,6 +21,7 @@ struct GemmArgs {
     int N, K;
     int accumulate;  // C += ...
     int relu;
+    const int32_t* c_idx = nullptr;  // nullable: output row m is written to C + c_idx[m] * ldc (scatter)
 };
 
 int launch_gemm(const GemmArgs& g, cudaStream_t st);

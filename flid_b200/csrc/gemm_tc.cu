@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(TcGemmArgs g, cons
             for (int ms = 0; ms < MS; ++ms) {
                 const int64_t row = (int64_t)mg * (MS * 128) + ms * 128 + ew * 32 + lane;
                 const uint32_t taddr = tmem + acc * sh.acc_stride + ms * sh.n_tile + ((uint32_t)(ew * 32) << 16);
-                float* crow = (row < g.M) ? g.C + row * g.ldc : nullptr;
+                float* crow = (row < g.M) ? g.C + (g.cidx ? (int64_t)__ldg(g.cidx + row) : row) * g.ldc : nullptr;
                 for (int c0 = 0; c0 < sh.n_tile; c0 += 16) {
                     float v[16];
                     tmem_ld16(taddr + (uint32_t)c0, v);

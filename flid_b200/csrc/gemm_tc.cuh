@@ -35,6 +35,7 @@ struct TcGemmArgs {
     int w1 = 0;  // columns [w0, w0 + w1) from segment 1 (0 = unused)
     float* C = nullptr;
     int64_t ldc = 0;
+    const int32_t* cidx = nullptr;  // nullable: output row m is written to C + cidx[m] * ldc (scatter)
     const float* bias = nullptr;
     int64_t M = 0;
     int relu = 0;

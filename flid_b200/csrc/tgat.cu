@@ -239,7 +239,7 @@ static int query_fold(flid_tgat* m, int layer, const float* feat, const int32_t*
 // +residual -> LayerNorm -> MergeLayer.  self rows: layer-(l-1) features of the targets.
 static int output_chain(flid_tgat* m, int layer, int64_t n, const float* Z, const float* self_base,
                         const int32_t* self_idx, const float* merge_feat, const int32_t* ids, float* O, float* A,
-                        float* Hd, float* out, cudaStream_t st) {
+                        float* Hd, float* out, const int32_t* out_idx, cudaStream_t st) {
     const LayerDev& ld = m->layers[layer];
     if (m->use_tc) {
         TcGemmArgs t1;
@@ -252,6 +252,7 @@ static int output_chain(flid_tgat* m, int layer, int64_t n, const float* Z, cons
         FLID_TRY(tc_gemm(t2, ld.tc_f1, st));
         TcGemmArgs t3;
         t3.A0 = Hd, t3.lda0 = m->dn, t3.w0 = m->dn, t3.C = out, t3.ldc = m->dn, t3.bias = ld.fc2_b, t3.M = n;
+        t3.cidx = out_idx;
         return tc_gemm(t3, ld.tc_f2, st);
     }
     GemmArgs g1{Z, m->zw, nullptr, ld.wvoT, m->zw, O, m->qd, ld.res_b, n, m->qd, m->zw, 0, 0};
@@ -262,7 +263,7 @@ static int output_chain(flid_tgat* m, int layer, int64_t n, const float* Z, cons
     FLID_TRY(launch_gemm(g2, st));
     GemmArgs g3{merge_feat, m->dn, ids, ld.fc1_w + m->qd, ld1, Hd, m->dn, ld.fc1_b, n, m->dn, m->dn, 1, 1};
     FLID_TRY(launch_gemm(g3, st));
-    GemmArgs g4{Hd, m->dn, nullptr, ld.fc2_w, m->dn, out, m->dn, ld.fc2_b, n, m->dn, m->dn, 0, 0};
+    GemmArgs g4{Hd, m->dn, nullptr, ld.fc2_w, m->dn, out, m->dn, ld.fc2_b, n, m->dn, m->dn, 0, 0, out_idx};
     return launch_gemm(g4, st);
 }
 
@@ -374,7 +375,7 @@ int tgat_embed_ids(flid_tgat* m, const flid_graph* g, const float* node_feat, co
             float* dst = (l == L) ? out + r0 * m->dn : w_h + ho[l] * m->dn;
             {
                 ProfScope prof(m, PROF_OUT, st);
-                FLID_TRY(output_chain(m, l - 1, nl, Z, self_base, self_idx, node_feat, lids, O, A, Hd, dst, st));
+                FLID_TRY(output_chain(m, l - 1, nl, Z, self_base, self_idx, node_feat, lids, O, A, Hd, dst, nullptr, st));
             }
             evals += nl;
         }
@@ -394,10 +395,18 @@ int tgat_embed_ids(flid_tgat* m, const flid_graph* g, const float* node_feat, co
 // A target's k neighbour rows are then k consecutive table rows, and the layer-(l-1)
 // feature of target p itself is memo_{l-1}[p] (same key).
 __global__ void memo_targets_kernel(const int2* __restrict__ adj, const double* __restrict__ ts, int64_t M,
-                                    int64_t lo, int64_t n, int32_t* __restrict__ ids, double* __restrict__ times) {
+                                    int64_t lo, int64_t n, int32_t* __restrict__ ids, double* __restrict__ times,
+                                    const int32_t* __restrict__ mirror, int32_t* __restrict__ rows) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int64_t p = lo + i;
+    int64_t p = lo + i;
+    // Owner-major order: work item q evaluates the table row of q's partner entry, i.e. the query
+    // (owner of q, time of q).  Consecutive items then ask for the same node at increasing times and
+    // their neighbour windows overlap in all but one slot, so the gathered rows are cache hits.
+    if (mirror) {
+        if (p < M) p = __ldg(mirror + p);
+        rows[i] = (int32_t)p;
+    }
     ids[i] = p < M ? __ldg(adj + p).x : 0;
     times[i] = p < M ? (double)(float)__ldg(ts + p) : 0.0;  // the float32 neighbour time the recursion passes down
 }
@@ -412,6 +421,7 @@ struct LayerCall {
     const int32_t* self_idx = nullptr; // nullable: self row i = self_base[self_idx[i]]
     bool u_from_table = false;         // layer 1 with the cached per-node query fold
     float* out = nullptr;              // [n, dn]
+    const int32_t* out_idx = nullptr;  // nullable: row i is written to out + out_idx[i] * dn
 };
 
 // one attention layer (1-based `layer`) for n targets: query fold -> stream -> out chain
@@ -437,7 +447,7 @@ static int layer_eval(flid_tgat* m, int layer, const LayerCall& c, const float* 
         FLID_TRY(launch_attn(a, m->H, st));
     }
     ProfScope prof(m, PROF_OUT, st);
-    return output_chain(m, layer - 1, c.n, Z, c.self_base, c.self_idx, node_feat, c.ids, O, A, Hd, c.out, st);
+    return output_chain(m, layer - 1, c.n, Z, c.self_base, c.self_idx, node_feat, c.ids, O, A, Hd, c.out, c.out_idx, st);
 }
 
 static int reserve_layer_ws(flid_tgat* m, int64_t n, int k, bool need_u) {
@@ -466,12 +476,19 @@ int tgat_memo_build(flid_tgat* m, const flid_graph* g, const float* node_feat, c
     FLID_CUDA(cudaMemsetAsync(d_valid, 0, sizeof(unsigned long long), st));
     int32_t* w_ids = m->ws_ids.as<int32_t>();
     double* w_times = m->ws_times.as<double>();
+    // A build of the whole table walks it in owner-major order and scatters the rows (the mirror is a
+    // permutation, so every row is written exactly once); a row-range build (one rank's slice of a
+    // sharded build) keeps table order so that its output stays one contiguous block.
+    const bool owner_major = g->mirror != nullptr && row_lo == 0 && row_hi == M + 1;
+    if (owner_major) FLID_TRY(m->ws_self.reserve(sizeof(int32_t) * std::min(chunk, row_hi - row_lo)));
+    int32_t* w_rows = owner_major ? m->ws_self.as<int32_t>() : nullptr;
     int64_t evals = 0;
     for (int64_t c0 = row_lo; c0 < row_hi; c0 += chunk) {
         const int64_t n = std::min(chunk, row_hi - c0);
         {
             ProfScope prof(m, PROF_SAMPLE, st);
-            memo_targets_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(g->adj, g->ts, M, c0, n, w_ids, w_times);
+            memo_targets_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(g->adj, g->ts, M, c0, n, w_ids, w_times,
+                                                                         owner_major ? g->mirror : nullptr, w_rows);
             FLID_LAUNCH_CHECK();
             level_sample_kernel<<<(unsigned)ceil_div(n * 32, 256), 256, 0, st>>>(
                 g->indptr, g->adj, g->ts, w_ids, w_times, n, 0, k, m->ws_nbr.as<int32_t>(), m->ws_eid.as<int32_t>(),
@@ -486,9 +503,16 @@ int tgat_memo_build(flid_tgat* m, const flid_graph* g, const float* node_feat, c
             c.hrow_base = node_feat, c.self_base = node_feat, c.self_idx = w_ids, c.u_from_table = use_table;
         } else {
             c.pos = m->ws_pos.as<int32_t>();
-            c.hrow_base = memo_prev, c.self_base = memo_prev + c0 * m->dn;
+            c.hrow_base = memo_prev;
+            if (owner_major)
+                c.self_base = memo_prev, c.self_idx = w_rows;
+            else
+                c.self_base = memo_prev + c0 * m->dn;
         }
-        c.out = memo_out + c0 * m->dn;
+        if (owner_major)
+            c.out = memo_out, c.out_idx = w_rows;
+        else
+            c.out = memo_out + c0 * m->dn;
         FLID_TRY(layer_eval(m, level, c, node_feat, edge_feat, k, st));
         evals += n;
     }
