@@ -28,8 +28,8 @@
 //   * optionally MS 128-row sub-tiles per work item sharing every weight stage (MS accumulators
 //     side by side in TMEM) -- halves the weight traffic, but the accumulators can then no longer
 //     be double-buffered and the ring gets shallower; measured slower, off by default.
-// The weight image is also kept in TC_REPLICAS copies read round-robin by CTA (no measurable
-// effect: the stall is bandwidth, not slice hot-spotting; kept at 1 replica in use by default).
+// Also tried without effect: 8 replicas of the weight image read round-robin by CTA (the stall is
+// bandwidth, not L2 slice hot-spotting) and a 3-deep register prefetch in the producers.
 #include "gemm_tc.cuh"
 
 #include <stdlib.h>
@@ -153,8 +153,6 @@ struct TcShape {
     int acc_bufs;          // 2 when two accumulator sets fit in TMEM (epilogue overlaps the next group)
     uint32_t acc_stride;   // TMEM columns per accumulator set (MS * n_tile)
     int64_t m_groups;      // groups of MS * 128 rows
-    int reps;              // weight image replicas in use (<= TC_REPLICAS)
-    int64_t rep_stride;    // float4 per replica
     long long* trace;      // FLID_GEMM_TRACE (development): per-stage clock64 stamps of CTA 0, [6][TRACE_Q]
 };
 constexpr int TRACE_Q = 512;
@@ -377,7 +375,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(TcGemmArgs g, cons
         const int64_t chunk4 = (int64_t)2 * C4 * sh.n_tile;  // float4 per (n block, K chunk)
         for (uint32_t t = blockIdx.x; t < work; t += gridDim.x) {
             const uint32_t nb = t % nblk;
-            const float4* wsrc = wbuf + (int64_t)(blockIdx.x % sh.reps) * sh.rep_stride + (int64_t)nb * sh.k_chunks * chunk4;
+            const float4* wsrc = wbuf + (int64_t)nb * sh.k_chunks * chunk4;
             for (int kc = 0; kc < sh.k_chunks; ++kc) {
                 mbar_wait(&bar_empty[s], ph ^ 1);
                 TRACE(5, tq);
@@ -418,9 +416,6 @@ int tc_prepare_weight(const float* W, int64_t ldw, int N, int K, TcWeight* w, cu
     tc_prep_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(W, ldw, N, K, n_tile, n_blocks, k_chunks,
                                                                   reinterpret_cast<float4*>(w->buf));
     FLID_LAUNCH_CHECK();
-    for (int r = 1; r < TC_REPLICAS; ++r)
-        FLID_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(w->buf) + r * w->image_bytes(), w->buf, w->image_bytes(),
-                                  cudaMemcpyDeviceToDevice, st));
     return FLID_OK;
 }
 
@@ -472,15 +467,6 @@ int tc_gemm(const TcGemmArgs& g, const TcWeight& w, cudaStream_t st) {
         if (!d_trace) cudaMalloc((void**)&d_trace, sizeof(long long) * 6 * TRACE_Q);
         cudaMemsetAsync(d_trace, 0, sizeof(long long) * 6 * TRACE_Q, st);
         sh.trace = d_trace;
-    }
-    {
-        static int reps = 0;
-        if (reps == 0) {
-            const char* e = getenv("FLID_GEMM_REPS");  // development knob
-            reps = e ? atoi(e) : TC_REPLICAS;
-            if (reps < 1 || reps > TC_REPLICAS) reps = TC_REPLICAS;
-        }
-        sh.reps = reps, sh.rep_stride = (int64_t)(w.image_bytes() / 16);
     }
     sh.N = w.N, sh.n_tile = w.n_tile, sh.n_blocks = w.n_blocks, sh.k_chunks = w.k_chunks;
     // Sub-tiles per work item.  Measured on the B200 (tools/gemm_probe.py, M = 65 536): sharing a

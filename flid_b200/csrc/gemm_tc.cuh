@@ -13,15 +13,10 @@ constexpr int TC_KC = 16;  // K floats per pipeline stage (2 UMMA k-steps of 8)
 
 // weight pre-split into (hi, lo) and pre-tiled so that one (n-block, k-chunk) stage is a
 // single contiguous bulk copy:  [n_block][k_chunk][half][c4 = 4][n_tile][4 floats]
-// TC_REPLICAS copies of the image at different addresses, read round-robin by CTA, were tried
-// against L2 slice hot-spotting (all CTAs walk the same chunk sequence at about the same time);
-// no measurable effect, so a single copy is kept.
-constexpr int TC_REPLICAS = 1;
 struct TcWeight {
     float* buf = nullptr;
     int N = 0, K = 0, n_tile = 0, n_blocks = 0, k_chunks = 0;
-    size_t image_bytes() const { return (size_t)n_blocks * k_chunks * 2 * (TC_KC / 4) * n_tile * 16; }
-    size_t bytes() const { return image_bytes() * TC_REPLICAS; }
+    size_t bytes() const { return (size_t)n_blocks * k_chunks * 2 * (TC_KC / 4) * n_tile * 16; }
 };
 
 struct TcGemmArgs {
