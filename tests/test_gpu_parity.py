@@ -187,6 +187,33 @@ def test_tgat_vs_oracle_synthetic_shapes(shape, L, k, heads):
     assert_fp32_close(b.cpu().numpy(), wb.numpy(), f"{shape} L{L} dst")
 
 
+@pytest.mark.parametrize("dn,de,T,heads,L,k", [(64, 128, 36, 2, 2, 7), (32, 16, 32, 4, 1, 32), (256, 172, 128, 1, 2, 3)])
+def test_tgat_other_feature_widths(dn, de, T, heads, L, k):
+    """Nothing in the kernels is specialised to d = 172 / T = 100: other (multiple-of-4) widths, head counts
+    and k up to the 32-slot limit, plain and memoised."""
+    rs = np.random.RandomState(dn + de)
+    src, dst, eid, ts, _, _ = cases.small_stream()
+    n_nodes = int(max(src.max(), dst.max()))
+    nf = rs.standard_normal((n_nodes + 1, dn)).astype(np.float32)
+    ef = rs.standard_normal((len(src) + 1, de)).astype(np.float32)
+    nf[0] = 0
+    ef[0] = 0
+    p = otgat.default_params(dn, de, T, L, heads, seed=13, time_bias_scale=0.2)
+    s = make_sampler(src, dst, eid, ts, n_nodes)
+    o = osamp.OracleSampler.from_events(src, dst, eid, ts, n_nodes)
+    m = flid_b200.TGAT(nf, ef, s, T, L, heads, 0.1, DEV).to(DEV)
+    m.load_state_dict({kk: v for kk, v in p.items() if not kk.startswith("_")})
+    m.eval()
+    sel = np.arange(420, 480)
+    wa, wb = otgat.embed_src_dst(p, torch.from_numpy(nf), torch.from_numpy(ef), o, src[sel], dst[sel], ts[sel], L, k)
+    for memo in (False, True):
+        m.set_layer_memo(memo)
+        with torch.no_grad():
+            a, b = m.compute_src_dst_node_temporal_embeddings(src[sel], dst[sel], ts[sel], k)
+        assert_fp32_close(a.cpu().numpy(), wa.numpy(), f"widths {dn}/{de}/{T} memo={memo} src")
+        assert_fp32_close(b.cpu().numpy(), wb.numpy(), f"widths {dn}/{de}/{T} memo={memo} dst")
+
+
 def test_tgat_float32_root_times_and_lower_layers():
     """compute_node_temporal_embeddings with float32 times (the recursion's call shape) and
     current_layer_num below num_layers."""
