@@ -177,6 +177,24 @@ def to_device(arr, dtype, device, tag):
     return out
 
 
+def to_device_concat(arrays, dtype, device, tag):
+    """concatenate(arrays) on the device without materialising the concatenation on the host: each
+    piece is copied into its slice of one pinned staging buffer, one async H2D copy follows."""
+    parts = [np.asarray(a) for a in arrays]
+    total = sum(p.shape[0] for p in parts)
+    tdtype = torch.from_numpy(np.empty(0, dtype=dtype)).dtype
+    stage = _pool.get(tag, total, tdtype)
+    view = stage.numpy()
+    off = 0
+    for p in parts:
+        n = p.shape[0]
+        np.copyto(view[off:off + n], p, casting="same_kind")
+        off += n
+    out = stage.to(device, non_blocking=True)
+    _pool.mark(tag, tdtype)
+    return out
+
+
 def to_host(t, tag):
     """device tensor -> fresh numpy array via pinned staging (synchronises the current stream)."""
     stage = _pool.get(tag, t.numel(), t.dtype)

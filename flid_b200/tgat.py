@@ -353,10 +353,19 @@ class TGAT(nn.Module):
         """models/TGAT.py:50-66 -> (Tensor[B, dn], Tensor[B, dn]) on the model's device.
         src and dst roots are independent, so both halves go through one launch chain."""
         b = len(src_node_ids)
-        both = self.compute_node_temporal_embeddings(
-            np.concatenate([np.asarray(src_node_ids), np.asarray(dst_node_ids)]),
-            np.concatenate([np.asarray(node_interact_times), np.asarray(node_interact_times)]),
-            self.num_layers, num_neighbors)
+        dev = self.node_raw_features.device
+        t = np.asarray(node_interact_times)
+        if self._needs_autograd() or dev.type != "cuda" or t.dtype == np.float32:
+            both = self.compute_node_temporal_embeddings(
+                np.concatenate([np.asarray(src_node_ids), np.asarray(dst_node_ids)]), np.concatenate([t, t]),
+                self.num_layers, num_neighbors)
+        else:
+            # stage [src ; dst] straight into pinned memory (no host-side concatenation), send the times once
+            with torch.cuda.device(dev):
+                d_nodes = _lib.to_device_concat([src_node_ids, dst_node_ids], np.int64, dev, "e_nodes")
+                d_t = _lib.to_device(t, np.float64, dev, "e_times")
+                d_times = torch.cat([d_t, d_t])
+            both = self.compute_node_temporal_embeddings(d_nodes, d_times, self.num_layers, num_neighbors)
         return both[:b], both[b:]
 
     def compute_node_temporal_embeddings(self, node_ids: np.ndarray, node_interact_times: np.ndarray,
