@@ -18,7 +18,7 @@
 // for 0.23 GB of A.  Measured on the B200 (per-stage clock64 stamps of one CTA, FLID_GEMM_TRACE):
 // the producers finish a stage ~4400 cycles before the issuer sees it full; what it waits for is
 // the weight bulk copy, ~4700 cycles after issue with 5-6 copies in flight, i.e. ~28 B/cycle/SM
-// of combined ingest -- the chip-wide L2 read rate divided by 148.  Switching off loads, smem
+// of combined ingest -- about what one SM's path from L2 delivers when all 148 pull at once.  Switching off loads, smem
 // stores, MMAs and C stores one at a time confirmed it: without any of them the barrier + copy
 // skeleton alone needs 107 us of a 250 us launch.  Design consequences kept in this file:
 //   * K chunks of 16 floats and as many ring stages as fit (6 at n_tile = 144): bytes in flight
@@ -43,6 +43,9 @@ constexpr uint32_t A_CSTRIDE = 130 * 16;  // byte stride between the K chunks of
 constexpr uint32_t A_HALF = C4 * A_CSTRIDE;
 constexpr uint32_t A_SUB = 2 * A_HALF;    // hi + lo image of one 128-row sub-tile
 constexpr int NPROD = 128, NEPI = 128, NTHREADS = 448, MAX_STAGES = 8;  // NPROD: threads of ONE producer group
+constexpr int EPI_LD = 20;                // floats per staged epilogue row (16 + pad: conflict-free row writes)
+constexpr int STATIC_SMEM = 1024;         // barriers etc.
+constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;  // epilogue staging of the four epilogue warps
 
 // ---------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -153,6 +156,7 @@ struct TcShape {
     int acc_bufs;          // 2 when two accumulator sets fit in TMEM (epilogue overlaps the next group)
     uint32_t acc_stride;   // TMEM columns per accumulator set (MS * n_tile)
     int64_t m_groups;      // groups of MS * 128 rows
+    int staged_epilogue;   // stage C through shared memory (pays off for long K loops and scattered rows)
     long long* trace;      // FLID_GEMM_TRACE (development): per-stage clock64 stamps of CTA 0, [6][TRACE_Q]
 };
 constexpr int TRACE_Q = 512;
@@ -281,7 +285,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(TcGemmArgs g, cons
         }
     } else if (warp < 12) {
         // ===================================================== epilogue
+        // A TMEM lane is a row, so after tcgen05.ld every thread holds 16 columns of its own row and
+        // a direct store would touch 32 rows (32 half-used sectors) per instruction.  Each warp stages
+        // its 32 x 16 block through shared memory and stores it 8 rows x 64 B per instruction instead.
         const int ew = warp - 8;  // TMEM lane quarter == warp id % 4
+        // staging area: the last EPI_BYTES of the dynamic allocation (only reserved by staged launches)
+        float* stg = reinterpret_cast<float*>(smem + (size_t)sh.stages * stage_bytes) + ew * (32 * EPI_LD);
+        const bool vec_ok = (g.ldc & 3) == 0 && (sh.N & 3) == 0;
+        const bool staged = vec_ok && sh.staged_epilogue;
+        const int sr = lane >> 2, sc = (lane & 3) * 4;  // this lane's (row within 8, column) in the store phase
         uint32_t it = 0;
         for (uint32_t t = blockIdx.x; t < work; t += gridDim.x, ++it) {
             const uint32_t mg = t / nblk, nb = t - mg * nblk;
@@ -291,35 +303,76 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(TcGemmArgs g, cons
             tc_fence_after();
 #pragma unroll
             for (int ms = 0; ms < MS; ++ms) {
-                const int64_t row = (int64_t)mg * (MS * 128) + ms * 128 + ew * 32 + lane;
+                const int64_t row0 = (int64_t)mg * (MS * 128) + ms * 128 + ew * 32;
                 const uint32_t taddr = tmem + acc * sh.acc_stride + ms * sh.n_tile + ((uint32_t)(ew * 32) << 16);
+                float* crow4[4];  // destination rows of the store phase
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int64_t r = row0 + j * 8 + sr;
+                    crow4[j] = (r < g.M) ? g.C + (g.cidx ? (int64_t)__ldg(g.cidx + r) : r) * g.ldc : nullptr;
+                }
+                const int64_t row = row0 + lane;
                 float* crow = (row < g.M) ? g.C + (g.cidx ? (int64_t)__ldg(g.cidx + row) : row) * g.ldc : nullptr;
                 for (int c0 = 0; c0 < sh.n_tile; c0 += 16) {
                     float v[16];
                     tmem_ld16(taddr + (uint32_t)c0, v);
                     const int n0 = nb * sh.n_tile + c0;
-                    if (crow != nullptr) {
-                        if (n0 + 16 <= sh.N && (g.ldc & 3) == 0) {
+                    if (n0 >= sh.N) continue;  // warp-uniform: padding columns of the last n block
+                    if (vec_ok && !staged) {
+                        if (crow != nullptr) {
+                            if (n0 + 16 <= sh.N) {
 #pragma unroll
-                            for (int i = 0; i < 16; i += 4) {
-                                float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                                if (g.bias) {
-                                    const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + i));
-                                    o.x += b.x, o.y += b.y, o.z += b.z, o.w += b.w;
+                                for (int i = 0; i < 16; i += 4) {
+                                    float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                                    if (g.bias) {
+                                        const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + i));
+                                        o.x += b.x, o.y += b.y, o.z += b.z, o.w += b.w;
+                                    }
+                                    if (g.relu) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
+                                    *reinterpret_cast<float4*>(crow + n0 + i) = o;
                                 }
-                                if (g.relu) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
-                                *reinterpret_cast<float4*>(crow + n0 + i) = o;
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) {
+                                    const int n = n0 + i;
+                                    if (n < sh.N) {
+                                        float x = v[i];
+                                        if (g.bias) x += __ldg(g.bias + n);
+                                        if (g.relu) x = fmaxf(x, 0.f);
+                                        crow[n] = x;
+                                    }
+                                }
                             }
-                        } else {
+                        }
+                    } else if (staged) {
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                const int n = n0 + i;
-                                if (n < sh.N) {
-                                    float x = v[i];
-                                    if (g.bias) x += __ldg(g.bias + n);
-                                    if (g.relu) x = fmaxf(x, 0.f);
-                                    crow[n] = x;
-                                }
+                        for (int i = 0; i < 16; i += 4) {
+                            float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                            if (g.bias && n0 + i < sh.N) {
+                                const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + i));
+                                o.x += b.x, o.y += b.y, o.z += b.z, o.w += b.w;
+                            }
+                            if (g.relu) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
+                            *reinterpret_cast<float4*>(stg + lane * EPI_LD + i) = o;
+                        }
+                        __syncwarp();
+                        if (n0 + sc < sh.N) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float4 o = *reinterpret_cast<const float4*>(stg + (j * 8 + sr) * EPI_LD + sc);
+                                if (crow4[j] != nullptr) *reinterpret_cast<float4*>(crow4[j] + n0 + sc) = o;
+                            }
+                        }
+                        __syncwarp();
+                    } else if (crow != nullptr) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int n = n0 + i;
+                            if (n < sh.N) {
+                                float x = v[i];
+                                if (g.bias) x += __ldg(g.bias + n);
+                                if (g.relu) x = fmaxf(x, 0.f);
+                                crow[n] = x;
                             }
                         }
                     }
@@ -428,11 +481,16 @@ template <int MS>
 static int launch_ms(const TcGemmArgs& g, const TcWeight& w, TcShape sh, int sm_count, int smem_max, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        FLID_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max - 1024));
+        FLID_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max - STATIC_SMEM));
         attr_set = true;
     }
     const size_t stage = (size_t)MS * A_SUB + 2 * (size_t)C4 * w.n_tile * 16;
-    int stages = (int)((size_t)(smem_max - 1024) / stage);
+    // measured (tools/gemm_probe.py): staging C through shared memory is +3 % on the K = 888 out-projection, a
+    // clear win for scattered rows and for the wide query-fold output; the narrow short-K shapes store directly
+    sh.staged_epilogue = (g.cidx != nullptr || w.k_chunks >= 48 || w.N >= 512) ? 1 : 0;
+    if (const char* e = getenv("FLID_GEMM_EPI")) sh.staged_epilogue = e[0] == '1';  // development knob
+    const size_t ring_bytes = (size_t)(smem_max - STATIC_SMEM) - (sh.staged_epilogue ? EPI_BYTES : 0);
+    int stages = (int)(ring_bytes / stage);
     sh.stages = stages > MAX_STAGES ? MAX_STAGES : stages;
     sh.m_groups = ceil_div(g.M, MS * 128);
     sh.acc_stride = (uint32_t)(MS * w.n_tile);
@@ -440,7 +498,8 @@ static int launch_ms(const TcGemmArgs& g, const TcWeight& w, TcShape sh, int sm_
     const int64_t work = sh.m_groups * sh.n_blocks;
     FLID_REQUIRE(work < (1LL << 31) - 65536, "tc_gemm: too many tiles for one launch (M = %lld)", (long long)g.M);
     const unsigned grid = (unsigned)(work < sm_count ? work : sm_count);
-    gemm_tc_kernel<MS><<<grid, NTHREADS, sh.stages * stage, st>>>(g, reinterpret_cast<const float4*>(w.buf), sh);
+    gemm_tc_kernel<MS><<<grid, NTHREADS, sh.stages * stage + (sh.staged_epilogue ? EPI_BYTES : 0), st>>>(
+        g, reinterpret_cast<const float4*>(w.buf), sh);
     FLID_LAUNCH_CHECK();
     return FLID_OK;
 }
@@ -477,7 +536,7 @@ int tc_gemm(const TcGemmArgs& g, const TcWeight& w, cudaStream_t st) {
     int ms = 1;
     for (int cand = ms_cap; cand > 1; --cand) {
         const size_t stage = (size_t)cand * A_SUB + 2 * (size_t)C4 * w.n_tile * 16;
-        if (cand * w.n_tile <= 512 && (size_t)(smem_max - 1024) / stage >= 3 &&
+        if (cand * w.n_tile <= 512 && (size_t)(smem_max - STATIC_SMEM) / stage >= 3 &&
             ceil_div(g.M, cand * 128) * w.n_blocks >= (int64_t)sm_count) {
             ms = cand;
             break;
