@@ -384,7 +384,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(TcGemmArgs g, cons
     } else if (warp == 12 && lane == 0) {
         // ===================================================== MMA issuer (one thread)
         // instruction descriptor: D=f32, A=B=tf32, K-major both, N = n_tile, M = 128
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(sh.n_tile >> 3) << 17) | (8u << 24);
+        // An MMA covers at most 256 columns: a wider tile (one pass over A for 256 < N <= 512) is issued as
+        // two column groups that read different rows of the same weight stage.
+        const uint32_t n_a = sh.n_tile > 256 ? (uint32_t)((sh.n_tile / 2 + 15) / 16 * 16) : (uint32_t)sh.n_tile;
+        const uint32_t n_b = (uint32_t)sh.n_tile - n_a;
+        auto make_idesc = [](uint32_t n) { return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | (8u << 24); };
+        const uint32_t idesc = make_idesc(n_a), idesc_b = make_idesc(n_b);
         const uint32_t smem_base = smem_u32(smem);
         const uint32_t b_lbo = (uint32_t)sh.n_tile * 16;
         uint32_t it = 0, s = 0, ph = 0, tq = 0;
@@ -413,6 +418,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(TcGemmArgs g, cons
                         umma_tf32(d, d_alo, d_bhi, idesc, (kc | j) ? 1u : 0u);  // small terms first
                         umma_tf32(d, d_ahi, d_blo, idesc, 1u);
                         umma_tf32(d, d_ahi, d_bhi, idesc, 1u);
+                        if (n_b) {  // second column group: weight rows n_a.. of the same chunk (16 B per row)
+                            const uint64_t row_off = (uint64_t)((n_a * 16u) >> 4);  // start-address field is in 16 B units
+                            umma_tf32(d + n_a, d_alo, d_bhi + row_off, idesc_b, (kc | j) ? 1u : 0u);
+                            umma_tf32(d + n_a, d_ahi, d_blo + row_off, idesc_b, 1u);
+                            umma_tf32(d + n_a, d_ahi, d_bhi + row_off, idesc_b, 1u);
+                        }
                     }
                 }
                 tc_commit(&bar_empty[s]);  // frees the smem stage when these MMAs have read it
@@ -447,6 +458,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(TcGemmArgs g, cons
 
 // ---------------------------------------------------------------- host side
 static int pick_n_tile(int N) {
+    // 256 < N <= 512: one tile of the full (padded) width -- A is then read once instead of once per
+    // n block; the accumulator (<= 512 TMEM columns) is single-buffered and fed by two MMA column groups
+    // (out-projection, N = 272: 221 -> 198 us at M = 65 536; FLID_GEMM_WIDE=0 restores the two-block form)
+    const char* wide = getenv("FLID_GEMM_WIDE");
+    if (N > 256 && (N + 15) / 16 * 16 <= 512 && !(wide && wide[0] == '0')) return (N + 15) / 16 * 16;
     const int blocks = (N + 255) / 256;
     int t = (N + blocks - 1) / blocks;
     t = (t + 15) / 16 * 16;
