@@ -166,18 +166,21 @@ class _PinnedPool:
 _pool = _PinnedPool()
 
 
-def to_device(arr, dtype, device, tag):
-    """numpy -> device tensor through a pinned staging buffer (async on the current stream)."""
+def to_device(arr, dtype, device, tag, sync_follows=False):
+    """numpy -> device tensor through a pinned staging buffer (async on the current stream).
+    ``sync_follows``: the caller synchronises the stream before anyone can stage under this tag
+    again (every compute entry point that reports errors does), so no guard event is recorded."""
     a = np.ascontiguousarray(arr, dtype=dtype)
     t = torch.from_numpy(a)
     stage = _pool.get(tag, t.numel(), t.dtype)
     stage.copy_(t.reshape(-1))
     out = stage.to(device, non_blocking=True).reshape(a.shape)
-    _pool.mark(tag, t.dtype)
+    if not sync_follows:
+        _pool.mark(tag, t.dtype)
     return out
 
 
-def to_device_concat(arrays, dtype, device, tag):
+def to_device_concat(arrays, dtype, device, tag, sync_follows=False):
     """concatenate(arrays) on the device without materialising the concatenation on the host: each
     piece is copied into its slice of one pinned staging buffer, one async H2D copy follows."""
     parts = [np.asarray(a) for a in arrays]
@@ -191,7 +194,8 @@ def to_device_concat(arrays, dtype, device, tag):
         np.copyto(view[off:off + n], p, casting="same_kind")
         off += n
     out = stage.to(device, non_blocking=True)
-    _pool.mark(tag, tdtype)
+    if not sync_follows:
+        _pool.mark(tag, tdtype)
     return out
 
 

@@ -525,7 +525,7 @@ int tgat_memo_build(flid_tgat* m, const flid_graph* g, const float* node_feat, c
 // because its own lower-layer embeddings are then rows of the memo as well (see level_sample_kernel).
 int tgat_embed_memo(flid_tgat* m, const flid_graph* g, const float* node_feat, const float* edge_feat,
                     const float* const* memo, const int32_t* ids, const double* times, int64_t n_f64, int64_t n, int k,
-                    float* out, cudaStream_t st) {
+                    float* out, int* bad_ids, cudaStream_t st) {
     const int L = m->L;
     const int64_t M = g->num_entries;
     const bool use_table = (m->table_src == node_feat && m->table_rows > 0);
@@ -535,7 +535,9 @@ int tgat_embed_memo(flid_tgat* m, const flid_graph* g, const float* node_feat, c
     FLID_TRY(reserve_layer_ws(m, nmax, k, L > 1 || !use_table));
     if (L > 1) FLID_TRY(m->ws_h.reserve(sizeof(float) * 2 * nmax * m->dn));
     if (try_self) FLID_TRY(m->ws_self.reserve(sizeof(int32_t) * nmax));
-    unsigned long long* d_cnt = m->ws_misc.as<unsigned long long>();  // [0] valid slots, [1] roots without a memo row
+    // [0] valid slots, [1] roots without a memo row, [2] "node id outside the graph" flag of the caller's
+    // root conversion (already zeroed / set before this function runs; read with the first chunk's counters)
+    unsigned long long* d_cnt = m->ws_misc.as<unsigned long long>();
     FLID_CUDA(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(unsigned long long), st));
     int64_t evals = 0, valid_weighted = 0;
     unsigned long long h_prev[2] = {0, 0};
@@ -552,9 +554,10 @@ int tgat_embed_memo(flid_tgat* m, const flid_graph* g, const float* node_feat, c
             FLID_LAUNCH_CHECK();
         }
         // counters of this chunk (one small synchronous read per chunk of up to 65 536 roots)
-        unsigned long long h_cnt[2];
+        unsigned long long h_cnt[3];
         FLID_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
         FLID_CUDA(cudaStreamSynchronize(st));
+        if (bad_ids) *bad_ids = h_cnt[2] != 0;
         const int64_t chunk_valid = (int64_t)(h_cnt[0] - h_prev[0]);
         const bool all_in_memo = try_self && h_cnt[1] == h_prev[1];
         h_prev[0] = h_cnt[0], h_prev[1] = h_cnt[1];
@@ -776,17 +779,19 @@ int flid_tgat_embed_memo(flid_tgat* m, const flid_graph* g, const float* node_fe
     cudaStream_t st = (cudaStream_t)stream;
     FLID_TRY(m->ws_rid.reserve(sizeof(int32_t) * n));
     FLID_TRY(m->ws_rt.reserve(sizeof(double) * n));
-    FLID_TRY(m->ws_bad.reserve(sizeof(int)));
-    FLID_CUDA(cudaMemsetAsync(m->ws_bad.p, 0, sizeof(int), st));
+    FLID_TRY(m->ws_misc.reserve(64));
+    // the range flag lives next to the sampling counters so that one small read per chunk (which also
+    // orders the host after the kernels that consume the caller's staging buffers) returns all three
+    int* d_bad = reinterpret_cast<int*>(m->ws_misc.as<unsigned long long>() + 2);
+    FLID_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(unsigned long long), st));
     roots_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(nodes, times, n, g->num_nodes, m->ws_rid.as<int32_t>(),
-                                                            m->ws_rt.as<double>(), m->ws_bad.as<int>());
+                                                            m->ws_rt.as<double>(), d_bad);
     FLID_LAUNCH_CHECK();
-    FLID_TRY(tgat_embed_memo(m, g, node_feat, edge_feat, memo_tables_host, m->ws_rid.as<int32_t>(),
-                             m->ws_rt.as<double>(), times_are_f32 ? 0 : n, n, k, out, st));
     int hbad = 0;
-    FLID_CUDA(cudaMemcpyAsync(&hbad, m->ws_bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-    FLID_CUDA(cudaStreamSynchronize(st));
+    FLID_TRY(tgat_embed_memo(m, g, node_feat, edge_feat, memo_tables_host, m->ws_rid.as<int32_t>(),
+                             m->ws_rt.as<double>(), times_are_f32 ? 0 : n, n, k, out, &hbad, st));
     if (hbad) {
+        FLID_CUDA(cudaStreamSynchronize(st));
         set_error("flid_tgat_embed_memo: node id outside the graph");
         return FLID_ERR_RANGE;
     }
