@@ -100,6 +100,70 @@ __global__ void max_kernel(const unsigned long long* __restrict__ counts, int64_
     atomicMax(out, m);
 }
 
+// ---------------------------------------------------------------- query ordering
+// Sort root queries by (node, time): consecutive queries of a bulk pass then ask for the same node at
+// increasing times, their neighbour windows overlap in all but one slot and the rows they gather are
+// cache hits.  LSD: stable sort on the time image, then stable sort on the node id.
+__global__ void query_keys_kernel(const double* __restrict__ times, int64_t n, unsigned long long* __restrict__ tkey,
+                                  uint32_t* __restrict__ iota) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    tkey[i] = sortable_f64(times[i] + 0.0);
+    iota[i] = (uint32_t)i;
+}
+__global__ void gather_ids_kernel(const int32_t* __restrict__ ids, const uint32_t* __restrict__ perm, int64_t n,
+                                  int32_t* __restrict__ out) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = ids[perm[i]];
+}
+__global__ void gather_queries_kernel(const int32_t* __restrict__ ids, const double* __restrict__ times,
+                                      const uint32_t* __restrict__ perm, int64_t n, int32_t* __restrict__ ids_out,
+                                      double* __restrict__ times_out) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t p = perm[i];
+    ids_out[i] = ids[p], times_out[i] = times[p];
+}
+
+int sort_queries(const int32_t* ids, const double* times, int64_t n, int64_t num_nodes, DevBuf& scratch,
+                 int32_t** perm_out, int32_t** ids_sorted, double** times_sorted, cudaStream_t st) {
+    const int T = 256;
+    const unsigned B = (unsigned)ceil_div(n, T);
+    size_t need_a = 0, need_b = 0;
+    FLID_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need_a, (unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                              (uint32_t*)nullptr, (uint32_t*)nullptr, n, 0, 64, st));
+    FLID_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need_b, (int32_t*)nullptr, (int32_t*)nullptr, (uint32_t*)nullptr,
+                                              (uint32_t*)nullptr, n, 0, 32, st));
+    const size_t tmp_bytes = std::max(need_a, need_b);
+    auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+    // layout: tkey_a | tkey_b | perm_a | perm_b | id_a | id_b | times_sorted | cub temp
+    const size_t o_ka = 0, o_kb = o_ka + al(8 * n), o_pa = o_kb + al(8 * n), o_pb = o_pa + al(4 * n), o_ia = o_pb + al(4 * n),
+                 o_ib = o_ia + al(4 * n), o_ts = o_ib + al(4 * n), o_tmp = o_ts + al(8 * n);
+    FLID_TRY(scratch.reserve(o_tmp + tmp_bytes));
+    char* base = scratch.as<char>();
+    unsigned long long *ka = (unsigned long long*)(base + o_ka), *kb = (unsigned long long*)(base + o_kb);
+    uint32_t *pa = (uint32_t*)(base + o_pa), *pb = (uint32_t*)(base + o_pb);
+    int32_t *ia = (int32_t*)(base + o_ia), *ib = (int32_t*)(base + o_ib);
+    double* ts = (double*)(base + o_ts);
+    void* tmp = base + o_tmp;
+    size_t tb = tmp_bytes;
+    query_keys_kernel<<<B, T, 0, st>>>(times, n, ka, pa);
+    FLID_LAUNCH_CHECK();
+    FLID_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, ka, kb, pa, pb, n, 0, 64, st));
+    gather_ids_kernel<<<B, T, 0, st>>>(ids, pb, n, ia);
+    FLID_LAUNCH_CHECK();
+    int bits = 1;
+    while (bits < 32 && (num_nodes >> bits) != 0) ++bits;
+    tb = tmp_bytes;
+    FLID_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, ia, ib, pb, pa, n, 0, bits, st));
+    count_launch(8);
+    // pa = final permutation, ib = sorted ids; sorted times into ts (ia is free again: reuse for nothing else)
+    gather_queries_kernel<<<B, T, 0, st>>>(ids, times, pa, n, ia, ts);
+    FLID_LAUNCH_CHECK();
+    *perm_out = reinterpret_cast<int32_t*>(pa), *ids_sorted = ia, *times_sorted = ts;
+    return FLID_OK;
+}
+
 static int build_sorted(flid_graph* g, int32_t* owner, int2* adj_in, unsigned long long* tkey, int64_t M,
                         bool paired, cudaStream_t st) {
     const int64_t N1 = g->num_nodes + 1;

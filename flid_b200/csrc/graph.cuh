@@ -15,6 +15,11 @@ struct flid_graph {
 
 namespace flid {
 
+// (node, time) ordering of n root queries: perm[i] = original index of the i-th query in sorted order, plus the
+// sorted ids / times; all three live in `scratch` (valid until its next use).  n < 2^31.
+int sort_queries(const int32_t* ids, const double* times, int64_t n, int64_t num_nodes, DevBuf& scratch,
+                 int32_t** perm_out, int32_t** ids_sorted, double** times_sorted, cudaStream_t st);
+
 #ifdef __CUDACC__
 // Warp-cooperative searchsorted(ts[lo:hi), t, side='left'): first position whose
 // timestamp is >= t.  32 probes per round, so ceil(log32(deg)) + 1 dependent loads.

@@ -525,7 +525,7 @@ int tgat_memo_build(flid_tgat* m, const flid_graph* g, const float* node_feat, c
 // because its own lower-layer embeddings are then rows of the memo as well (see level_sample_kernel).
 int tgat_embed_memo(flid_tgat* m, const flid_graph* g, const float* node_feat, const float* edge_feat,
                     const float* const* memo, const int32_t* ids, const double* times, int64_t n_f64, int64_t n, int k,
-                    float* out, int* bad_ids, cudaStream_t st) {
+                    float* out, const int32_t* out_perm, int* bad_ids, cudaStream_t st) {
     const int L = m->L;
     const int64_t M = g->num_entries;
     const bool use_table = (m->table_src == node_feat && m->table_rows > 0);
@@ -577,6 +577,7 @@ int tgat_embed_memo(flid_tgat* m, const flid_graph* g, const float* node_feat, c
                     c.self_base = hbuf[l & 1];
             }
             c.out = (l == L) ? out + r0 * m->dn : hbuf[(l + 1) & 1];
+            if (l == L && out_perm != nullptr) c.out = out, c.out_idx = out_perm + r0;  // queries were reordered
             FLID_TRY(layer_eval(m, l, c, node_feat, edge_feat, k, st));
             evals += nc;
             valid_weighted += chunk_valid;
@@ -613,6 +614,8 @@ int flid_tgat_create(int node_dim, int edge_dim, int time_dim, int num_layers, i
     m->use_tc = !(mode && strcmp(mode, "simt") == 0);
     const char* sm = getenv("FLID_SELF_MEMO");
     m->self_from_memo = !(sm && sm[0] == '0');
+    const char* so = getenv("FLID_SORT_QUERIES");
+    m->sort_bulk_queries = !(so && so[0] == '0');
     *out = m;
     return FLID_OK;
 }
@@ -629,7 +632,7 @@ void flid_tgat_free(flid_tgat* m) {
     for (auto e : m->prof_ev) cudaEventDestroy(e);
     flid::DevBuf* bufs[] = {&m->raw_q, &m->raw_k, &m->raw_v, &m->raw_r, &m->table, &m->ws_ids, &m->ws_times,
                             &m->ws_nbr, &m->ws_eid, &m->ws_dt, &m->ws_h, &m->ws_u, &m->ws_z, &m->ws_o,
-                            &m->ws_a, &m->ws_hd, &m->ws_misc, &m->ws_rid, &m->ws_rt, &m->ws_bad, &m->ws_pos, &m->ws_self};
+                            &m->ws_a, &m->ws_hd, &m->ws_misc, &m->ws_rid, &m->ws_rt, &m->ws_bad, &m->ws_pos, &m->ws_self, &m->ws_sort};
     for (auto* b : bufs) b->release();
     delete m;
 }
@@ -788,8 +791,18 @@ int flid_tgat_embed_memo(flid_tgat* m, const flid_graph* g, const float* node_fe
                                                             m->ws_rt.as<double>(), d_bad);
     FLID_LAUNCH_CHECK();
     int hbad = 0;
-    FLID_TRY(tgat_embed_memo(m, g, node_feat, edge_feat, memo_tables_host, m->ws_rid.as<int32_t>(),
-                             m->ws_rt.as<double>(), times_are_f32 ? 0 : n, n, k, out, &hbad, st));
+    const int32_t* q_ids = m->ws_rid.as<int32_t>();
+    const double* q_times = m->ws_rt.as<double>();
+    const int32_t* perm = nullptr;
+    if (n >= 8192 && n < 0x7fffffffLL && m->sort_bulk_queries) {
+        // bulk pass: evaluate the roots in (node, time) order, scatter the rows back through the last GEMM
+        int32_t *p = nullptr, *si = nullptr;
+        double* stm = nullptr;
+        FLID_TRY(sort_queries(q_ids, q_times, n, g->num_nodes, m->ws_sort, &p, &si, &stm, st));
+        perm = p, q_ids = si, q_times = stm;
+    }
+    FLID_TRY(tgat_embed_memo(m, g, node_feat, edge_feat, memo_tables_host, q_ids, q_times, times_are_f32 ? 0 : n, n, k,
+                             out, perm, &hbad, st));
     if (hbad) {
         FLID_CUDA(cudaStreamSynchronize(st));
         set_error("flid_tgat_embed_memo: node id outside the graph");

@@ -31,8 +31,9 @@ struct flid_tgat {
     flid::DevBuf table;
     // workspace
     int64_t max_l1_targets = 65536;
+    bool sort_bulk_queries = true;  // bulk memoised calls evaluate their roots in (node, time) order (FLID_SORT_QUERIES=0 disables)
     bool self_from_memo = true;  // roots that are graph events read their own lower layers from the memo (FLID_SELF_MEMO=0 disables)
-    flid::DevBuf ws_ids, ws_times, ws_nbr, ws_eid, ws_dt, ws_h, ws_u, ws_z, ws_o, ws_a, ws_hd, ws_misc, ws_pos, ws_self;
+    flid::DevBuf ws_ids, ws_times, ws_nbr, ws_eid, ws_dt, ws_h, ws_u, ws_z, ws_o, ws_a, ws_hd, ws_misc, ws_pos, ws_self, ws_sort;
     flid::DevBuf ws_rid, ws_rt, ws_bad;  // root conversion staging
     int64_t stats[4] = {0, 0, 0, 0};
     int64_t valid_mult = 1;  // attention evaluations that consume each sampled neighbour list

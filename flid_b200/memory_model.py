@@ -279,10 +279,10 @@ class MemoryModel(nn.Module):
             self._sync(h)
             if self._err is None or self._err.device != dev:
                 self._err = torch.zeros(1, dtype=torch.int32, device=dev)
-            d_src = _lib.to_device(src_node_ids, np.int64, dev, "g_src")
-            d_dst = _lib.to_device(dst_node_ids, np.int64, dev, "g_dst")
-            d_t = _lib.to_device(node_interact_times, np.float64, dev, "g_t")
-            d_e = _lib.to_device(edge_ids, np.int64, dev, "g_e") if edge_ids is not None else None
+            d_src = _lib.to_device(src_node_ids, np.int64, dev, "g_src", sync_follows=True)
+            d_dst = _lib.to_device(dst_node_ids, np.int64, dev, "g_dst", sync_follows=True)
+            d_t = _lib.to_device(node_interact_times, np.float64, dev, "g_t", sync_follows=True)
+            d_e = _lib.to_device(edge_ids, np.int64, dev, "g_e", sync_follows=True) if edge_ids is not None else None
             out = torch.empty((2 * b, self.node_feat_dim), dtype=torch.float32, device=dev)
             s, g = self.memory_bank._c_state(), self._gru()
             _lib.check(_lib.lib().flid_tgn_step(h, sampler.handle, C.byref(s), C.byref(g), _lib.ptr(self.node_raw_features),
@@ -329,10 +329,10 @@ class MemoryModel(nn.Module):
             if positive:
                 if self._err is None or self._err.device != dev:
                     self._err = torch.zeros(1, dtype=torch.int32, device=dev)
-                d_src = _lib.to_device(src_node_ids, np.int64, dev, "g_src")
-                d_dst = _lib.to_device(dst_node_ids, np.int64, dev, "g_dst")
-                d_t = _lib.to_device(node_interact_times, np.float64, dev, "g_t")
-                d_e = _lib.to_device(edge_ids, np.int64, dev, "g_e")
+                d_src = _lib.to_device(src_node_ids, np.int64, dev, "g_src", sync_follows=True)
+                d_dst = _lib.to_device(dst_node_ids, np.int64, dev, "g_dst", sync_follows=True)
+                d_t = _lib.to_device(node_interact_times, np.float64, dev, "g_t", sync_follows=True)
+                d_e = _lib.to_device(edge_ids, np.int64, dev, "g_e", sync_follows=True)
                 s, g = bank._c_state(), self._gru()
                 _lib.check(_lib.lib().flid_tgn_step(h, sampler.handle, C.byref(s), C.byref(g),
                                                     _lib.ptr(self.node_raw_features), _lib.ptr(self.edge_raw_features),
