@@ -30,98 +30,11 @@
 //     be double-buffered and the ring gets shallower; measured slower, off by default.
 // Also tried without effect: 8 replicas of the weight image read round-robin by CTA (the stall is
 // bandwidth, not L2 slice hot-spotting) and a 3-deep register prefetch in the producers.
-#include "gemm_tc.cuh"
-
 #include <stdlib.h>
 
+#include "tc_ptx.cuh"
+
 namespace flid {
-
-constexpr int KC = TC_KC;                 // 16 floats per stage
-constexpr int C4 = KC / 4;                // 16-byte chunks per row per stage
-constexpr uint32_t A_CSTRIDE = 130 * 16;  // byte stride between the K chunks of a sub-tile (== 2 mod 8 in 16 B units:
-                                          // the 8 rows x 4 chunks of a warp store hit 32 distinct bank groups)
-constexpr uint32_t A_HALF = C4 * A_CSTRIDE;
-constexpr uint32_t A_SUB = 2 * A_HALF;    // hi + lo image of one 128-row sub-tile
-constexpr int NPROD = 128, NEPI = 128, NTHREADS = 448, MAX_STAGES = 8;  // NPROD: threads of ONE producer group
-constexpr int EPI_LD = 20;                // floats per staged epilogue row (16 + pad: conflict-free row writes)
-constexpr int STATIC_SMEM = 1024;         // barriers etc.
-constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;  // epilogue staging of the four epilogue warps
-
-// ---------------------------------------------------------------- PTX helpers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// bounded wait: a protocol bug traps instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t b = smem_u32(bar);
-    for (uint32_t spin = 0; !mbar_try(b, parity); ++spin)
-        if (spin > (1u << 28)) __trap();
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-// arrive + expect_tx in one operation: the phase cannot complete before the byte count is registered
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-// K-major, no swizzle: 8 rows x 16 B core matrices; LBO = byte distance between the two 16-byte
-// K chunks of one MMA, SBO = byte distance between 8-row groups (cute::UMMA::SmemDescriptor).
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(da), "l"(db), "r"(idesc), "r"(accum)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
-        "[%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
 // ---------------------------------------------------------------- weight tiling
 // image layout: [n_block][k_chunk][half][c4][n_tile] float4
@@ -478,6 +391,8 @@ int tc_prepare_weight(const float* W, int64_t ldw, int N, int K, TcWeight* w, cu
         FLID_CUDA(cudaDeviceSynchronize());
         FLID_CUDA(cudaFree(w->buf));
         w->buf = nullptr;
+        if (w->buf_pair) FLID_CUDA(cudaFree(w->buf_pair));
+        w->buf_pair = nullptr, w->pair_ok = 0;
     }
     w->N = N, w->K = K, w->n_tile = n_tile, w->n_blocks = n_blocks, w->k_chunks = k_chunks;
     if (!w->buf) FLID_CUDA(cudaMalloc((void**)&w->buf, w->bytes()));
@@ -485,12 +400,13 @@ int tc_prepare_weight(const float* W, int64_t ldw, int N, int K, TcWeight* w, cu
     tc_prep_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(W, ldw, N, K, n_tile, n_blocks, k_chunks,
                                                                   reinterpret_cast<float4*>(w->buf));
     FLID_LAUNCH_CHECK();
-    return FLID_OK;
+    return tc_prepare_weight_pair(W, ldw, w, st);
 }
 
 void tc_free_weight(TcWeight* w) {
     if (w && w->buf) cudaFree(w->buf);
-    if (w) w->buf = nullptr;
+    if (w && w->buf_pair) cudaFree(w->buf_pair);
+    if (w) w->buf = nullptr, w->buf_pair = nullptr, w->pair_ok = 0;
 }
 
 template <int MS>
@@ -534,6 +450,24 @@ int tc_gemm(const TcGemmArgs& g, const TcWeight& w, cudaStream_t st) {
         FLID_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
         const char* e = getenv("FLID_GEMM_MS");  // development knob: cap the sub-tiles per work item
         if (e && e[0] >= '1' && e[0] <= '2') ms_cap = e[0] - '0';
+    }
+    {   // CTA-pair kernel for bulk calls (FLID_GEMM_PAIR=1 while it is being validated)
+        static int pair = -1;
+        if (pair < 0) {
+            const char* e = getenv("FLID_GEMM_PAIR");
+            pair = (e && e[0] == '1') ? 1 : 0;
+        }
+        if (pair && w.pair_ok && ceil_div(g.M, 256) * w.n_blocks >= sm_count / 2)
+            return tc_gemm_pair(g, w, sm_count, smem_max, st);
+        // A-from-TMEM kernel (gemm_tc_ts.cu) for single-n-block shapes: measured 5-12 % faster there; the wide
+        // query-fold output (4 n blocks, epilogue-heavy) keeps the kernel below, whose accumulators double-buffer
+        static int ts = -1;
+        if (ts < 0) {
+            const char* e = getenv("FLID_GEMM_TS");
+            ts = (e && e[0] == '0') ? 0 : 1;
+        }
+        if (ts && w.n_blocks == 1 && (512 - w.n_tile) / 32 >= 4)  // >= 4 stages of A columns next to the accumulator
+            return tc_gemm_ts(g, w, sm_count, smem_max, st);
     }
     TcShape sh;
     sh.trace = nullptr;

@@ -1,0 +1,358 @@
+// A-from-TMEM ("TS") variant of the tcgen05 3xTF32 GEMM.
+//
+// In gemm_tc.cu both operands of every tcgen05.mma come from shared memory, and with the 3xTF32
+// split each 8-float K step issues three MMAs that re-read A (4 KB) and B (N x 32 B) -- about
+// 120 B/cycle of operand fetch at N = 144, i.e. the whole shared-memory bandwidth, before the
+// producers' stores and the weight copies land in the same memory.  That, not the tensor pipe
+// and not L2, is what paces that kernel (measured ~1700 cycles per 16-float K chunk against
+// 864 cycles of MMA; halving the weight bytes per SM with a CTA pair changed nothing).
+//
+// Here the A operand lives in tensor memory: producer threads own one row each (TMEM lane =
+// row), split their 16 K-floats into hi | lo and write them with tcgen05.st into a ring of
+// 32-column stages next to the accumulators; the MMAs read A from TMEM and only the weight
+// chunk from shared memory.  Shared memory then carries the weight copies and the B fetches
+// only, and it holds more stages.  Everything else (roles, barriers, epilogue, weight image) is
+// gemm_tc.cu's.
+#include <stdlib.h>
+
+#include "tc_ptx.cuh"
+
+namespace flid {
+
+namespace {
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(
+            taddr),
+        "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        : "memory");
+}
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accum) {
+    const uint32_t z = 0;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(db), "r"(idesc), "r"(accum), "r"(z)
+        : "memory");
+}
+
+}  // namespace
+
+struct TsShape {
+    int N, n_tile, n_blocks, k_chunks, stages;
+    int acc_bufs;          // accumulator sets in TMEM (the A ring takes the remaining columns)
+    uint32_t acc_stride;   // TMEM columns per accumulator set (= n_tile)
+    int staged_epilogue;
+    int64_t m_groups;      // 128-row tiles
+    long long* trace;      // unused (kept so that the shared code compiles unchanged)
+};
+#define TRACE(role, q) do { } while (0)
+
+__global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_ts_kernel(TcGemmArgs g, const float4* __restrict__ wbuf, TsShape sh) {
+    constexpr int MS = 1;
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar_full[MAX_STAGES], bar_empty[MAX_STAGES], bar_acc_full[2], bar_acc_empty[2];
+    __shared__ uint32_t tmem_slot;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t b_half = (uint32_t)C4 * sh.n_tile * 16;
+    const uint32_t stage_bytes = 2 * b_half;               // shared memory holds the weight chunks only
+    const uint32_t a_cols = sh.acc_bufs * (uint32_t)sh.n_tile; // first TMEM column of the A ring (32 columns per stage)
+    const uint32_t nblk = (uint32_t)sh.n_blocks;
+    const uint32_t work = (uint32_t)(sh.m_groups * sh.n_blocks);  // host guarantees < 2^31
+
+    if (tid == 0) {
+        for (int s = 0; s < sh.stages; ++s) mbar_init(&bar_full[s], NPROD + 1), mbar_init(&bar_empty[s], 1);
+        for (int a = 0; a < 2; ++a) mbar_init(&bar_acc_full[a], 1), mbar_init(&bar_acc_empty[a], NEPI);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 12) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                     "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const int ktot = g.w0 + g.w1;
+
+    if (warp < 8) {
+        // ===================================================== producers (two alternating groups)
+        // One thread per row (TMEM lane = row): the thread loads its row's 16 K-floats of the chunk,
+        // splits them and writes hi | lo into 32 TMEM columns of the stage with tcgen05.st.  The loads
+        // of the group's next chunk are in flight (registers) meanwhile.
+        const int pg = warp >> 2, pw = warp & 3;
+        const uint32_t dq = gridDim.x / nblk, dr = gridDim.x % nblk;
+        struct Cursor {
+            uint32_t t, mg, nb;
+            int kc;
+        };
+        auto next_item = [&](Cursor& cu) {
+            cu.t += gridDim.x, cu.mg += dq, cu.nb += dr;
+            if (cu.nb >= nblk) cu.nb -= nblk, cu.mg += 1;
+        };
+        Cursor lc{blockIdx.x, blockIdx.x / nblk, blockIdx.x % nblk, pg};
+        const float* p0 = g.A0;
+        const float* p1 = g.A1;
+        bool row_ok = false;
+        auto bind_row = [&]() {
+            const int64_t row = (int64_t)lc.mg * 128 + pw * 32 + lane;
+            row_ok = lc.t < work && row < g.M;
+            p0 = g.A0, p1 = g.A1;
+            if (row_ok) {
+                p0 = g.A0 + (g.idx0 ? (int64_t)__ldg(g.idx0 + row) : row) * g.lda0;
+                if (g.w1 > 0) p1 = g.A1 + (g.idx1 ? (int64_t)__ldg(g.idx1 + row) : row) * g.lda1;
+            }
+        };
+        if (lc.kc >= sh.k_chunks) lc.kc -= sh.k_chunks, next_item(lc);
+        bind_row();
+        auto load_next = [&](float4 (&v)[4]) {
+            const int k0 = lc.kc * KC;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int k = k0 + 4 * i;
+                const float* src = k < g.w0 ? p0 + k : p1 + (k - g.w0);
+                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row_ok && k < ktot) v[i] = __ldg(reinterpret_cast<const float4*>(src));
+            }
+            lc.kc += 2;
+            if (lc.kc >= sh.k_chunks) {  // next work item (rare path)
+                lc.kc -= sh.k_chunks;
+                next_item(lc);
+                if (lc.kc >= sh.k_chunks) lc.kc -= sh.k_chunks, next_item(lc);  // k_chunks == 1
+                bind_row();
+            }
+        };
+        const uint32_t my_items = work > blockIdx.x ? (work - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        const uint32_t total_q = my_items * (uint32_t)sh.k_chunks;
+        uint32_t sq = (uint32_t)pg;
+        uint32_t stage = (uint32_t)pg % (uint32_t)sh.stages, phase = 0;
+        auto store_next = [&](const float4 (&v)[4]) {
+            mbar_wait(&bar_empty[stage], phase ^ 1);
+            tc_fence_after();
+            float hi[16], lo[16];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) hi[4 * i + e] = tf32_hi(x[e]), lo[4 * i + e] = x[e] - hi[4 * i + e];
+            }
+            const uint32_t taddr = tmem + a_cols + stage * 32u + ((uint32_t)(pw * 32) << 16);
+            tmem_st16(taddr, hi);
+            tmem_st16(taddr + 16u, lo);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            mbar_arrive(&bar_full[stage]);
+            sq += 2;
+            stage += 2;
+            if (stage >= (uint32_t)sh.stages) stage -= (uint32_t)sh.stages, phase ^= 1;
+        };
+        float4 ra[4], rb[4];
+        load_next(ra);
+        while (sq < total_q) {
+            load_next(rb);
+            store_next(ra);
+            if (sq >= total_q) break;
+            load_next(ra);
+            store_next(rb);
+        }
+    } else if (warp < 12) {
+        // ===================================================== epilogue
+        // A TMEM lane is a row, so after tcgen05.ld every thread holds 16 columns of its own row and
+        // a direct store would touch 32 rows (32 half-used sectors) per instruction.  Each warp stages
+        // its 32 x 16 block through shared memory and stores it 8 rows x 64 B per instruction instead.
+        const int ew = warp - 8;  // TMEM lane quarter == warp id % 4
+        // staging area: the last EPI_BYTES of the dynamic allocation (only reserved by staged launches)
+        float* stg = reinterpret_cast<float*>(smem + (size_t)sh.stages * stage_bytes) + ew * (32 * EPI_LD);
+        const bool vec_ok = (g.ldc & 3) == 0 && (sh.N & 3) == 0;
+        const bool staged = vec_ok && sh.staged_epilogue;
+        const int sr = lane >> 2, sc = (lane & 3) * 4;  // this lane's (row within 8, column) in the store phase
+        uint32_t it = 0;
+        for (uint32_t t = blockIdx.x; t < work; t += gridDim.x, ++it) {
+            const uint32_t mg = t / nblk, nb = t - mg * nblk;
+            const uint32_t acc = sh.acc_bufs == 2 ? (it & 1) : 0;
+            const uint32_t par = sh.acc_bufs == 2 ? ((it >> 1) & 1) : (it & 1);
+            mbar_wait(&bar_acc_full[acc], par);
+            tc_fence_after();
+#pragma unroll
+            for (int ms = 0; ms < MS; ++ms) {
+                const int64_t row0 = (int64_t)mg * (MS * 128) + ms * 128 + ew * 32;
+                const uint32_t taddr = tmem + acc * sh.acc_stride + ms * sh.n_tile + ((uint32_t)(ew * 32) << 16);
+                float* crow4[4];  // destination rows of the store phase
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int64_t r = row0 + j * 8 + sr;
+                    crow4[j] = (r < g.M) ? g.C + (g.cidx ? (int64_t)__ldg(g.cidx + r) : r) * g.ldc : nullptr;
+                }
+                const int64_t row = row0 + lane;
+                float* crow = (row < g.M) ? g.C + (g.cidx ? (int64_t)__ldg(g.cidx + row) : row) * g.ldc : nullptr;
+                for (int c0 = 0; c0 < sh.n_tile; c0 += 16) {
+                    float v[16];
+                    tmem_ld16(taddr + (uint32_t)c0, v);
+                    const int n0 = nb * sh.n_tile + c0;
+                    if (n0 >= sh.N) continue;  // warp-uniform: padding columns of the last n block
+                    if (vec_ok && !staged) {
+                        if (crow != nullptr) {
+                            if (n0 + 16 <= sh.N) {
+#pragma unroll
+                                for (int i = 0; i < 16; i += 4) {
+                                    float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                                    if (g.bias) {
+                                        const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + i));
+                                        o.x += b.x, o.y += b.y, o.z += b.z, o.w += b.w;
+                                    }
+                                    if (g.relu) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
+                                    *reinterpret_cast<float4*>(crow + n0 + i) = o;
+                                }
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) {
+                                    const int n = n0 + i;
+                                    if (n < sh.N) {
+                                        float x = v[i];
+                                        if (g.bias) x += __ldg(g.bias + n);
+                                        if (g.relu) x = fmaxf(x, 0.f);
+                                        crow[n] = x;
+                                    }
+                                }
+                            }
+                        }
+                    } else if (staged) {
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4) {
+                            float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                            if (g.bias && n0 + i < sh.N) {
+                                const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + i));
+                                o.x += b.x, o.y += b.y, o.z += b.z, o.w += b.w;
+                            }
+                            if (g.relu) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
+                            *reinterpret_cast<float4*>(stg + lane * EPI_LD + i) = o;
+                        }
+                        __syncwarp();
+                        if (n0 + sc < sh.N) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float4 o = *reinterpret_cast<const float4*>(stg + (j * 8 + sr) * EPI_LD + sc);
+                                if (crow4[j] != nullptr) *reinterpret_cast<float4*>(crow4[j] + n0 + sc) = o;
+                            }
+                        }
+                        __syncwarp();
+                    } else if (crow != nullptr) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int n = n0 + i;
+                            if (n < sh.N) {
+                                float x = v[i];
+                                if (g.bias) x += __ldg(g.bias + n);
+                                if (g.relu) x = fmaxf(x, 0.f);
+                                crow[n] = x;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&bar_acc_empty[acc]);
+        }
+    } else if (warp == 12 && lane == 0) {
+        // ===================================================== MMA issuer (one thread)
+        // instruction descriptor: D=f32, A=B=tf32, K-major both, N = n_tile, M = 128
+        // An MMA covers at most 256 columns: a wider tile (one pass over A for 256 < N <= 512) is issued as
+        // two column groups that read different rows of the same weight stage.
+        const uint32_t n_a = sh.n_tile > 256 ? (uint32_t)((sh.n_tile / 2 + 15) / 16 * 16) : (uint32_t)sh.n_tile;
+        const uint32_t n_b = (uint32_t)sh.n_tile - n_a;
+        auto make_idesc = [](uint32_t n) { return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | (8u << 24); };
+        const uint32_t idesc = make_idesc(n_a), idesc_b = make_idesc(n_b);
+        const uint32_t smem_base = smem_u32(smem);
+        const uint32_t b_lbo = (uint32_t)sh.n_tile * 16;
+        uint32_t it = 0, s = 0, ph = 0;
+        for (uint32_t t = blockIdx.x; t < work; t += gridDim.x, ++it) {
+            const uint32_t acc = sh.acc_bufs == 2 ? (it & 1) : 0;
+            const uint32_t par = sh.acc_bufs == 2 ? ((it >> 1) & 1) : (it & 1);
+            mbar_wait(&bar_acc_empty[acc], par ^ 1);
+            tc_fence_after();
+            const uint32_t d0 = tmem + acc * sh.acc_stride;
+            for (int kc = 0; kc < sh.k_chunks; ++kc) {
+                mbar_wait(&bar_full[s], ph);
+                tc_fence_after();
+                const uint32_t sb = smem_base + s * stage_bytes;
+                const uint32_t ta = tmem + a_cols + s * 32u;  // this stage's A columns: hi at +0..15, lo at +16..31
+#pragma unroll
+                for (int j = 0; j < KC / 8; ++j) {
+                    const uint64_t d_bhi = umma_desc(sb + (2 * j) * b_lbo, b_lbo, 128);
+                    const uint64_t d_blo = umma_desc(sb + b_half + (2 * j) * b_lbo, b_lbo, 128);
+                    const uint32_t a_hi = ta + 8u * j, a_lo = a_hi + 16u;
+                    umma_tf32_ts(d0, a_lo, d_bhi, idesc, (kc | j) ? 1u : 0u);  // small terms first
+                    umma_tf32_ts(d0, a_hi, d_blo, idesc, 1u);
+                    umma_tf32_ts(d0, a_hi, d_bhi, idesc, 1u);
+                    if (n_b) {  // second column group: weight rows n_a.. of the same chunk (16 B per row)
+                        const uint64_t row_off = (uint64_t)((n_a * 16u) >> 4);
+                        umma_tf32_ts(d0 + n_a, a_lo, d_bhi + row_off, idesc_b, (kc | j) ? 1u : 0u);
+                        umma_tf32_ts(d0 + n_a, a_hi, d_blo + row_off, idesc_b, 1u);
+                        umma_tf32_ts(d0 + n_a, a_hi, d_bhi + row_off, idesc_b, 1u);
+                    }
+                }
+                tc_commit(&bar_empty[s]);  // frees the smem stage when these MMAs have read it
+                if (++s == (uint32_t)sh.stages) s = 0, ph ^= 1;
+            }
+            tc_commit(&bar_acc_full[acc]);  // accumulators complete -> epilogue
+        }
+    } else if (warp == 13 && lane == 0) {
+        // ===================================================== weight loader (one thread)
+        uint32_t s = 0, ph = 0;
+        const int64_t chunk4 = (int64_t)2 * C4 * sh.n_tile;  // float4 per (n block, K chunk)
+        for (uint32_t t = blockIdx.x; t < work; t += gridDim.x) {
+            const uint32_t nb = t % nblk;
+            const float4* wsrc = wbuf + (int64_t)nb * sh.k_chunks * chunk4;
+            for (int kc = 0; kc < sh.k_chunks; ++kc) {
+                mbar_wait(&bar_empty[s], ph ^ 1);
+                uint8_t* st = smem + (size_t)s * stage_bytes;
+                mbar_arrive_expect_tx(&bar_full[s], 2 * b_half);
+                bulk_g2s(st, wsrc + kc * chunk4, 2 * b_half, &bar_full[s]);
+                if (++s == (uint32_t)sh.stages) s = 0, ph ^= 1;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 12) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
+}
+
+
+int tc_gemm_ts(const TcGemmArgs& g, const TcWeight& w, int sm_count, int smem_max, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        FLID_CUDA(cudaFuncSetAttribute(gemm_tc_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max - STATIC_SMEM));
+        attr_set = true;
+    }
+    TsShape sh;
+    sh.trace = nullptr;
+    sh.N = w.N, sh.n_tile = w.n_tile, sh.n_blocks = w.n_blocks, sh.k_chunks = w.k_chunks;
+    sh.m_groups = ceil_div(g.M, 128);
+    sh.acc_stride = (uint32_t)w.n_tile;
+    // two accumulator sets when that still leaves >= 4 stages of A columns, else one
+    sh.acc_bufs = (2 * w.n_tile <= 512 && (512 - 2 * w.n_tile) / 32 >= 4) ? 2 : 1;
+    const int a_stages = (512 - sh.acc_bufs * w.n_tile) / 32;
+    sh.staged_epilogue = (g.cidx != nullptr || w.k_chunks >= 48 || w.N >= 512) ? 1 : 0;
+    const size_t stage = 2 * (size_t)C4 * w.n_tile * 16;
+    const size_t ring_bytes = (size_t)(smem_max - STATIC_SMEM) - (sh.staged_epilogue ? EPI_BYTES : 0);
+    int stages = (int)(ring_bytes / stage);
+    stages = stages > MAX_STAGES ? MAX_STAGES : stages;
+    sh.stages = stages < a_stages ? stages : a_stages;
+    FLID_REQUIRE(sh.stages >= 3, "tc_gemm_ts: tile does not fit (n_tile = %d)", w.n_tile);
+    const int64_t work = sh.m_groups * sh.n_blocks;
+    FLID_REQUIRE(work < (1LL << 31) - 65536, "tc_gemm_ts: too many tiles for one launch");
+    const unsigned grid = (unsigned)(work < sm_count ? work : sm_count);
+    gemm_tc_ts_kernel<<<grid, NTHREADS, sh.stages * stage + (sh.staged_epilogue ? EPI_BYTES : 0), st>>>(
+        g, reinterpret_cast<const float4*>(w.buf), sh);
+    FLID_LAUNCH_CHECK();
+    return FLID_OK;
+}
+
+}  // namespace flid

@@ -30,7 +30,7 @@ struct flid_tgat {
     int64_t table_rows = 0;
     flid::DevBuf table;
     // workspace
-    int64_t max_l1_targets = 65536;
+    int64_t max_l1_targets = 75776;  // 148 SMs x 512: every 128-row GEMM tile round and every 4-target attention block round is full
     bool sort_bulk_queries = true;  // bulk memoised calls evaluate their roots in (node, time) order (FLID_SORT_QUERIES=0 disables)
     bool self_from_memo = true;  // roots that are graph events read their own lower layers from the memo (FLID_SELF_MEMO=0 disables)
     flid::DevBuf ws_ids, ws_times, ws_nbr, ws_eid, ws_dt, ws_h, ws_u, ws_z, ws_o, ws_a, ws_hd, ws_misc, ws_pos, ws_self, ws_sort;

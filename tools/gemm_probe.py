@@ -52,13 +52,21 @@ def main():
                                                 a1g.stride(0) if w1 else 0, w1, _lib.ptr(w), w.stride(0),
                                                 _lib.ptr(bias), _lib.ptr(c), c.stride(0), m, n, int(relu), args.reps,
                                                 C.byref(ms), _lib.stream()))
+        # correctness on a sample of rows (the timing hook leaves the last launch's output in c)
+        torch.cuda.synchronize()
+        rows = torch.randint(0, m, (2048,), device=dev)
+        a_full = a0[rows] if not w1 else torch.cat([a0[rows], a1g[rows]], dim=1)
+        want = a_full.double() @ w.double().t() + bias.double()
+        if relu:
+            want = want.clamp_min(0)
+        err = float((c[rows].double() - want).abs().max()) / float(want.abs().max())
         k = w0 + w1
         n_pad = -(-n // 16) * 16
         floor_cycles = (-(-m // 128)) * (-(-k // 8)) * 3 * (n_pad / 2) / 148
         floor_ms = floor_cycles / sm_clock * 1e3
         gbs = m * k * 4 / (ms.value * 1e-3) / 1e9
         print(f"{name}  M={m}: {ms.value * 1e3:8.1f} us   mma-floor {floor_ms * 1e3:6.1f} us ({100 * floor_ms / ms.value:4.1f}% of tensor peak)"
-              f"   A-read {gbs:7.0f} GB/s", flush=True)
+              f"   A-read {gbs:7.0f} GB/s   rel.err {err:.1e}", flush=True)
 
 
 if __name__ == "__main__":
