@@ -12,24 +12,24 @@
 //   warp  13    loader    : one thread bulk-copies (cp.async.bulk, SASS UBLKCP) the pre-tiled
 //                           weight chunk of every stage as soon as the stage is free
 //
-// What bounds this kernel is not the tensor pipe but the L2 -> SM path.  With hi/lo images the
-// weights are 8 B per element and every 128-row tile re-streams all of them (out-projection:
-// 1.9 MB per tile, 2.25x the bytes of the A tile itself), so a launch moves ~1.45 GB through L2
-// for 0.23 GB of A.  Measured on the B200 (per-stage clock64 stamps of one CTA, FLID_GEMM_TRACE):
-// the producers finish a stage ~4400 cycles before the issuer sees it full; what it waits for is
-// the weight bulk copy, ~4700 cycles after issue with 5-6 copies in flight, i.e. ~28 B/cycle/SM
-// of combined ingest -- about what one SM's path from L2 delivers when all 148 pull at once.  Switching off loads, smem
-// stores, MMAs and C stores one at a time confirmed it: without any of them the barrier + copy
-// skeleton alone needs 107 us of a 250 us launch.  Design consequences kept in this file:
-//   * K chunks of 16 floats and as many ring stages as fit (6 at n_tile = 144): bytes in flight
-//     per SM, not stage count, is what buys throughput;
-//   * a dedicated loader thread, so a copy is issued the moment its stage is free;
-//   * two producer groups, so the per-stage drain/fence/arrive tail is off the critical path;
-//   * optionally MS 128-row sub-tiles per work item sharing every weight stage (MS accumulators
-//     side by side in TMEM) -- halves the weight traffic, but the accumulators can then no longer
-//     be double-buffered and the ring gets shallower; measured slower, off by default.
-// Also tried without effect: 8 replicas of the weight image read round-robin by CTA (the stall is
-// bandwidth, not L2 slice hot-spotting) and a 3-deep register prefetch in the producers.
+// What paces this kernel (measurements on the B200; DESIGN.md section 4 has the full list):
+// the tensor pipe is only 40-55 % busy.  Per-stage clock64 stamps of one CTA (FLID_GEMM_TRACE)
+// showed the producers finishing a stage thousands of cycles before the issuer sees it full -- the
+// wait is on the weight copy -- and switching off loads, smem stores, MMAs and C stores one at a
+// time left a 107 us barrier-and-copy skeleton of a 250 us launch.  With the 3xTF32 split every
+// 8-float K step issues three MMAs that re-read A (4 KB) and B (n_tile x 32 B) from shared
+// memory, ~120 B/cycle at n_tile = 144: the operand fetch alone takes the whole shared-memory
+// bandwidth, and the producers' stores and the weight copies land in the same memory.
+// Consequences kept in this file:
+//   * K chunks of 16 floats and as many ring stages as fit; a dedicated loader thread, so a copy
+//     is issued the moment its stage is free; two producer groups, so the per-stage
+//     drain/fence/arrive tail is off the critical path; no 64-bit divisions per chunk;
+//   * 256 < N <= 512 as one pass over A (two MMA column groups, single-buffered accumulator);
+//   * C staged through shared memory in the epilogue (row-coalesced stores) where it pays off;
+//   * optionally MS sub-tiles per work item sharing every weight stage -- measured slower, off;
+//   * gemm_tc_ts.cu moves the A operand into tensor memory and is what single-n-block shapes use.
+// Tried without effect: weight-image replicas against L2 slice hot-spotting, a 3-deep register
+// prefetch, a CTA pair with cta_group::2 (gemm_tc_pair.cu: half the weight bytes per SM).
 #include <stdlib.h>
 
 #include "tc_ptx.cuh"
