@@ -118,7 +118,10 @@ __device__ __forceinline__ Row4 ldg_row4(const void* p) {
 
 // NV: float4 chunks per lane per row; TP: packed time-channel pairs per lane
 template <int H, int NV, int TP>
-__global__ void __launch_bounds__(128, (H * NV <= 6 && NV <= 3) ? 3 : 2) attn_pk_kernel(AttnArgs a) {
+__global__ void __launch_bounds__(128, (H * NV <= 6 && NV <= 3) ? 4 : 2) attn_pk_kernel(AttnArgs a) {
+    // the query fold u of the warp's target lives in shared memory (16-byte, lane-contiguous reads): 24-32
+    // registers less than holding it, which is what lets a fourth block (16 warps) fit on the SM
+    extern __shared__ __align__(16) unsigned char u_smem[];
     constexpr int G = 2, V = G * H;
     const int lane = threadIdx.x & 31;
     const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -146,22 +149,27 @@ __global__ void __launch_bounds__(128, (H * NV <= 6 && NV <= 3) ? 3 : 2) attn_pk
 
     const float wmax = __ldg(a.time_bound), bmax = __ldg(a.time_bound + 1);
     const float* u = a.u_base + (a.u_index ? (int64_t)__ldg(a.u_index + i) : i) * (int64_t)(H * kd);
-    Row4 uh[H][NV];
-    u64 ut[H][TP], tw[TP], tb[TP];
+    // this warp's slice of shared memory: [H][NV][32] Row4 (row part of u) then [H][TP][32] packed pairs (time part)
+    Row4* uh_s = reinterpret_cast<Row4*>(u_smem) + (threadIdx.x >> 5) * (H * NV * 32) + lane;
+    u64* ut_s = reinterpret_cast<u64*>(u_smem + (size_t)4 * H * NV * 32 * sizeof(Row4)) + (threadIdx.x >> 5) * (H * TP * 32) + lane;
+    u64 tw[TP], tb[TP];
 #pragma unroll
     for (int h = 0; h < H; ++h) {
 #pragma unroll
         for (int r = 0; r < NV; ++r) {
             const int f = lane + 32 * r;
-            uh[h][r] = Row4{0ull, 0ull};
-            if (f < tot4) uh[h][r] = ldg_row4(u + h * kd + 4 * f);
+            Row4 v{0ull, 0ull};
+            if (f < tot4) v = ldg_row4(u + h * kd + 4 * f);
+            uh_s[(h * NV + r) * 32] = v;
         }
 #pragma unroll
         for (int r = 0; r < TP; ++r) {
             const int c0 = lane + 64 * r, c1 = c0 + 32;
-            ut[h][r] = pk(c0 < T ? __ldg(u + h * kd + dn + de + c0) : 0.f, c1 < T ? __ldg(u + h * kd + dn + de + c1) : 0.f);
+            ut_s[(h * TP + r) * 32] =
+                pk(c0 < T ? __ldg(u + h * kd + dn + de + c0) : 0.f, c1 < T ? __ldg(u + h * kd + dn + de + c1) : 0.f);
         }
     }
+    // every lane only reads back what it wrote itself: no barrier needed
 #pragma unroll
     for (int r = 0; r < TP; ++r) {
         const int c0 = lane + 64 * r, c1 = c0 + 32;
@@ -237,15 +245,17 @@ __global__ void __launch_bounds__(128, (H * NV <= 6 && NV <= 3) ? 3 : 2) attn_pk
                     u64 p0 = 0ull, p1 = 0ull;  // two chains of packed partial sums
 #pragma unroll
                     for (int r = 0; r < NV; ++r) {
-                        p0 = fma2(x[s][r].a, uh[h][r].a, p0);
-                        p1 = fma2(x[s][r].b, uh[h][r].b, p1);
+                        const Row4 uu = uh_s[(h * NV + r) * 32];
+                        p0 = fma2(x[s][r].a, uu.a, p0);
+                        p1 = fma2(x[s][r].b, uu.b, p1);
                     }
 #pragma unroll
                     for (int r = 0; r < TP; ++r) {
+                        const u64 uu = ut_s[(h * TP + r) * 32];
                         if (r & 1)
-                            p1 = fma2(xt[s][r], ut[h][r], p1);
+                            p1 = fma2(xt[s][r], uu, p1);
                         else
-                            p0 = fma2(xt[s][r], ut[h][r], p0);
+                            p0 = fma2(xt[s][r], uu, p0);
                     }
                     part[s * H + h] = hsum(add2(p0, p1));
                 }
@@ -326,7 +336,7 @@ int launch_h(const AttnArgs& a, int nv, int tp, cudaStream_t st) {
     const unsigned blocks = (unsigned)ceil_div(a.n * 32, 128);
 #define FLID_ATTN_CASE(NV_, TP_)                                 \
     if (nv <= NV_ && tp <= TP_) {                                \
-        attn_pk_kernel<H, NV_, TP_><<<blocks, 128, 0, st>>>(a);  \
+        attn_pk_kernel<H, NV_, TP_><<<blocks, 128, 4 * H * 32 * (NV_ * 16 + TP_ * 8), st>>>(a);  \
         FLID_LAUNCH_CHECK();                                     \
         return FLID_OK;                                          \
     }
