@@ -31,6 +31,10 @@ CASES = [  # m, n, w0, w1, gather, bias, relu
     (77, 516, 616, 0, True, True, False),        # GRU input projection
     (5, 16, 4, 0, False, False, False),          # tiny / ragged
     (4096, 272, 888, 0, False, True, False),
+    (300, 172, 172, 172, True, True, True),      # two segments whose boundary falls inside a 16-float K chunk
+    (2500, 80, 172, 0, False, True, True),       # decoder fc1 (double-buffered accumulators, deep A ring)
+    (700, 444, 172, 0, True, True, False),       # single-head query fold: one 448-column tile (two MMA column groups)
+    (40000, 272, 444, 0, False, True, False),    # more work items than SMs, ragged last tile
 ]
 
 
