@@ -235,8 +235,12 @@ def run_ours(args, rank, world, local_rank):
     pass_stats = {}
 
     def memo_build(collect=False):
-        """An E-step pass follows an M-step (new weights), so the layer memo is rebuilt inside
-        every timed pass: rows sharded over the ranks, all-gathered in place over NCCL."""
+        """An E-step pass follows an M-step (new weights), so the weights are re-uploaded and the layer
+        memo is rebuilt inside every timed pass: rows sharded over the ranks, all-gathered in place
+        over NCCL."""
+        # new weights every pass: the weight upload (float64 folds, hi/lo tiling, per-node query-fold table) is
+        # redone inside the timed region as well
+        model._engine.versions.clear()
         if not use_memo:
             return
         model._engine.memo.clear()
