@@ -80,6 +80,7 @@ class _Engine:
         self.param_cache = {}   # depth -> [Parameter, ...] in the order flid_tgat_set_weights expects
         self.memo = {}       # depth -> (key, [level tables])   layer memo of bulk passes
         self.memo_mode = "auto"   # False | True | "auto"
+        self.memo_builds = 0      # how many times a memo was (re)built (diagnostics)
         self.served = {}     # depth -> (key, root queries answered without a memo)
 
     def close(self):
@@ -92,18 +93,19 @@ class _Engine:
 
     def handle(self, depth, time_encoder, conv_layers, merge_layers, device):
         lib = _lib.lib()
-        # the Parameter objects are looked up once per depth (nn.Module attribute access is slow on a
-        # 300-us call path); replaced parameters (rare) are caught by the identity check below
+        # nn.Module attribute access is slow on a ~170-us call path, so the (owning dict, name, Parameter) triples
+        # are collected once per depth; a replaced Parameter object (rare) is caught by the identity check
         cached = self.param_cache.get(depth)
-        if cached is None or cached[0] is not time_encoder.w.weight or cached[-1] is not merge_layers[depth - 1].fc2.bias:
-            cached = [time_encoder.w.weight, time_encoder.w.bias]
+        if cached is None or any(d[k] is not p for d, k, p in cached):
+            mods = [(time_encoder.w, ("weight", "bias"))]
             for l in range(depth):
                 a, m = conv_layers[l], merge_layers[l]
-                cached += [a.query_projection.weight, a.key_projection.weight, a.value_projection.weight,
-                           a.layer_norm.weight, a.layer_norm.bias, a.residual_fc.weight, a.residual_fc.bias,
-                           m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias]
+                mods += [(a.query_projection, ("weight",)), (a.key_projection, ("weight",)), (a.value_projection, ("weight",)),
+                         (a.layer_norm, ("weight", "bias")), (a.residual_fc, ("weight", "bias")),
+                         (m.fc1, ("weight", "bias")), (m.fc2, ("weight", "bias"))]
+            cached = [(mod._parameters, k, mod._parameters[k]) for mod, keys in mods for k in keys]
             self.param_cache[depth] = cached
-        params = cached
+        params = [p for _, _, p in cached]
         fp = tuple([(p.data_ptr(), p._version) for p in params])
         if self.versions.get(depth) != fp:
             for p in params:
@@ -184,6 +186,7 @@ def build_layer_memo(engine, depth, time_encoder, conv_layers, merge_layers, sam
             tables.append(t)
             prev = t
         engine.memo[depth] = (key, tables)
+        engine.memo_builds += 1
         return tables
 
 
