@@ -29,7 +29,8 @@
 //   * optionally MS sub-tiles per work item sharing every weight stage -- measured slower, off;
 //   * gemm_tc_ts.cu moves the A operand into tensor memory and is what single-n-block shapes use.
 // Tried without effect: weight-image replicas against L2 slice hot-spotting, a 3-deep register
-// prefetch, a CTA pair with cta_group::2 (gemm_tc_pair.cu: half the weight bytes per SM).
+// prefetch, a CTA pair with tcgen05.mma.cta_group::2 (half the weight bytes per SM; correct, not faster --
+// in the history, not in the tree).
 #include <stdlib.h>
 
 #include "tc_ptx.cuh"
@@ -391,8 +392,6 @@ int tc_prepare_weight(const float* W, int64_t ldw, int N, int K, TcWeight* w, cu
         FLID_CUDA(cudaDeviceSynchronize());
         FLID_CUDA(cudaFree(w->buf));
         w->buf = nullptr;
-        if (w->buf_pair) FLID_CUDA(cudaFree(w->buf_pair));
-        w->buf_pair = nullptr, w->pair_ok = 0;
     }
     w->N = N, w->K = K, w->n_tile = n_tile, w->n_blocks = n_blocks, w->k_chunks = k_chunks;
     if (!w->buf) FLID_CUDA(cudaMalloc((void**)&w->buf, w->bytes()));
@@ -400,13 +399,12 @@ int tc_prepare_weight(const float* W, int64_t ldw, int N, int K, TcWeight* w, cu
     tc_prep_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(W, ldw, N, K, n_tile, n_blocks, k_chunks,
                                                                   reinterpret_cast<float4*>(w->buf));
     FLID_LAUNCH_CHECK();
-    return tc_prepare_weight_pair(W, ldw, w, st);
+    return FLID_OK;
 }
 
 void tc_free_weight(TcWeight* w) {
     if (w && w->buf) cudaFree(w->buf);
-    if (w && w->buf_pair) cudaFree(w->buf_pair);
-    if (w) w->buf = nullptr, w->buf_pair = nullptr, w->pair_ok = 0;
+    if (w) w->buf = nullptr;
 }
 
 template <int MS>
@@ -451,14 +449,7 @@ int tc_gemm(const TcGemmArgs& g, const TcWeight& w, cudaStream_t st) {
         const char* e = getenv("FLID_GEMM_MS");  // development knob: cap the sub-tiles per work item
         if (e && e[0] >= '1' && e[0] <= '2') ms_cap = e[0] - '0';
     }
-    {   // CTA-pair kernel for bulk calls (FLID_GEMM_PAIR=1 while it is being validated)
-        static int pair = -1;
-        if (pair < 0) {
-            const char* e = getenv("FLID_GEMM_PAIR");
-            pair = (e && e[0] == '1') ? 1 : 0;
-        }
-        if (pair && w.pair_ok && ceil_div(g.M, 256) * w.n_blocks >= sm_count / 2)
-            return tc_gemm_pair(g, w, sm_count, smem_max, st);
+    {
         // A-from-TMEM kernel (gemm_tc_ts.cu) for single-n-block shapes: measured 5-12 % faster there; the wide
         // query-fold output (4 n blocks, epilogue-heavy) keeps the kernel below, whose accumulators double-buffer
         static int ts = -1;

@@ -15,8 +15,6 @@ constexpr int TC_KC = 16;  // K floats per pipeline stage (2 UMMA k-steps of 8)
 // single contiguous bulk copy:  [n_block][k_chunk][half][c4 = 4][n_tile][4 floats]
 struct TcWeight {
     float* buf = nullptr;
-    float* buf_pair = nullptr;  // image for the CTA-pair kernel (each CTA's half of every chunk contiguous)
-    int pair_ok = 0;
     int N = 0, K = 0, n_tile = 0, n_blocks = 0, k_chunks = 0;
     size_t bytes() const { return (size_t)n_blocks * k_chunks * 2 * (TC_KC / 4) * n_tile * 16; }
 };
@@ -42,9 +40,6 @@ struct TcGemmArgs {
 int tc_prepare_weight(const float* W, int64_t ldw, int N, int K, TcWeight* w, cudaStream_t st);
 void tc_free_weight(TcWeight* w);
 int tc_gemm(const TcGemmArgs& g, const TcWeight& w, cudaStream_t st);
-// CTA-pair (tcgen05 cta_group::2) variant, gemm_tc_pair.cu; chosen by tc_gemm for large M
-int tc_prepare_weight_pair(const float* W, int64_t ldw, TcWeight* w, cudaStream_t st);
-int tc_gemm_pair(const TcGemmArgs& g, const TcWeight& w, int sm_count, int smem_max, cudaStream_t st);
 // A-operand-in-TMEM variant, gemm_tc_ts.cu
 int tc_gemm_ts(const TcGemmArgs& g, const TcWeight& w, int sm_count, int smem_max, cudaStream_t st);
 
