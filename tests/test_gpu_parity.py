@@ -744,3 +744,42 @@ def test_full_size_reddit_shape_properties():
                                  g.src_node_ids[few], g.dst_node_ids[few], g.node_interact_times[few], 2, 20)
     assert_fp32_close(a[few].cpu().numpy(), wa.numpy(), "full-size src vs oracle")
     assert_fp32_close(b[few].cpu().numpy(), wb.numpy(), "full-size dst vs oracle")
+
+
+def test_full_size_dsub_shape_properties():
+    """BASELINE.json configs[3] at full size (150 000 nodes / 168 154 edges, k = 30, one year of seconds):
+    most neighbourhoods are padded or empty (the all-masked softmax path) and about half of the event times
+    are not float32-exact, so roots mix "own lower layers from the memo" and the full chain.  The memoised
+    double-way bulk pass must equal the recursion bit for bit and agree with the oracle on a sample."""
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    g = synth.dsub_shape(seed=0, scale=1.0)
+    e = g.num_interactions
+    s = flid_b200.get_neighbor_sampler(g, "recent", seed=1, device=DEV)
+    nodes = np.concatenate([g.src_node_ids, g.dst_node_ids])
+    times = np.concatenate([g.node_interact_times, g.node_interact_times])
+    nbr, eid, ts = s.get_historical_neighbors(nodes, times, 30)
+    pad = nbr == 0
+    assert (pad[:, :-1] >= pad[:, 1:]).all() and (ts.astype(np.float64) < times[:, None])[~pad].all()
+    assert pad.all(axis=1).mean() > 0.2, "the shape is meant to exercise empty neighbourhoods"
+    exact = times.astype(np.float32).astype(np.float64) == times
+    assert 0.2 < exact.mean() < 0.9, "the shape is meant to mix float32-exact and inexact times"
+    p = otgat.default_params(172, 172, 100, 2, 2, seed=4, time_bias_scale=0.1)
+    m = flid_b200.TGAT(g.node_raw_features, g.edge_raw_features, s, 100, 2, 2, 0.1, DEV).to(DEV)
+    m.load_state_dict({k: v for k, v in p.items() if not k.startswith("_")})
+    m.eval()
+    with torch.no_grad():
+        a, b = passes.embed_events(m, g.src_node_ids, g.dst_node_ids, g.node_interact_times, 30)
+        assert 2 in m._engine.memo
+        rs = np.random.RandomState(1)
+        sel = np.sort(rs.choice(e, 2000, replace=False))
+        m.set_layer_memo(False)
+        pa, pb = m.compute_src_dst_node_temporal_embeddings(g.src_node_ids[sel], g.dst_node_ids[sel],
+                                                            g.node_interact_times[sel], 30)
+    assert torch.equal(a[sel], pa) and torch.equal(b[sel], pb)
+    assert torch.isfinite(a).all() and torch.isfinite(b).all()
+    o = osamp.OracleSampler.from_events(g.src_node_ids, g.dst_node_ids, g.edge_ids, g.node_interact_times, g.num_nodes)
+    few = sel[::50]
+    wa, wb = otgat.embed_src_dst(p, torch.from_numpy(g.node_raw_features), torch.from_numpy(g.edge_raw_features), o,
+                                 g.src_node_ids[few], g.dst_node_ids[few], g.node_interact_times[few], 2, 30)
+    assert_fp32_close(a[few].cpu().numpy(), wa.numpy(), "Dsub full-size src vs oracle")
+    assert_fp32_close(b[few].cpu().numpy(), wb.numpy(), "Dsub full-size dst vs oracle")
