@@ -67,12 +67,10 @@ __device__ __forceinline__ u64 cos2_fast(u64 x) {
     u64 r = fma2(kf, pk1(-3.1415927410125732f), x);
     r = fma2(kf, pk1(8.742277657347586e-08f), r);
     const u64 r2 = mul2(r, r);
-    u64 p = fma2(r2, pk1(2.08767569878680990e-9f), pk1(-2.75573192239858907e-7f));
-    p = fma2(p, r2, pk1(2.48015873015873016e-5f));
-    p = fma2(p, r2, pk1(-1.38888888888888889e-3f));
-    p = fma2(p, r2, pk1(4.16666666666666667e-2f));
-    p = fma2(p, r2, pk1(-0.5f));
-    p = fma2(p, r2, pk1(1.0f));
+    u64 p = fma2(r2, pk1(FLID_COS_C4), pk1(FLID_COS_C3));
+    p = fma2(p, r2, pk1(FLID_COS_C2));
+    p = fma2(p, r2, pk1(FLID_COS_C1));
+    p = fma2(p, r2, pk1(FLID_COS_C0));
     float tl, th, pl, ph;
     upk(t, tl, th);
     upk(p, pl, ph);
