@@ -7,9 +7,9 @@ Inference (``torch.no_grad()`` calls in ``.eval()`` mode: every E-step pass, the
 embedding passes, evaluation) runs the sm_100a kernels through the C ABI
 (``flid_tgat_embed``).  The parameter-holder modules below keep the reference's parameter
 names and default initialisation; they have no forward of their own on that path.
-Training-mode calls (dropout + backward) use ``autograd_forward``: device-sampled
-neighbourhoods (the same bit-exact kernel) + torch CUDA ops in the reference's order, so
-autograd supplies the gradients.  A fused forward/backward kernel is SURVEY.md 8(f) rank 1.
+Training-mode calls (dropout + backward) use ``train.autograd_forward``: device-sampled
+neighbourhoods (the same bit-exact kernel), the attention stream as a CUDA kernel with a
+hand-written backward kernel, and torch matmuls for the dense projections.
 """
 import ctypes as C
 
@@ -19,6 +19,7 @@ import torch.nn as nn
 
 from . import _lib
 from .sampler import NeighborSampler
+from .train import autograd_forward
 
 
 class TimeEncoder(nn.Module):
@@ -258,70 +259,6 @@ def embed_roots(engine, depth, time_encoder, conv_layers, merge_layers, sampler,
             _lib.check(_lib.lib().flid_tgat_embed(h, sampler.handle, _lib.ptr(node_feat), _lib.ptr(edge_feat),
                                                   _lib.ptr(d_nodes), _lib.ptr(d_times), is32, n, int(num_neighbors),
                                                   _lib.ptr(out), _lib.stream()))
-    return out
-
-
-def autograd_forward(time_encoder, conv_layers, merge_layers, sampler, node_feat, edge_feat, node_ids,
-                     node_interact_times, depth, num_neighbors, training):
-    """Differentiable forward for training-mode calls (M-step batches, PTCL/M_step.py:196-325).
-
-    The neighbourhoods come from the device sampler kernel (bit-exact with the reference); the
-    differentiable arithmetic is composed from torch CUDA ops in the reference's literal order
-    (models/modules.py:167-245, models/TGAT.py:68-144) so that autograd provides the backward
-    pass and ``nn.Dropout`` behaves as in the reference.  Level-batched instead of recursive:
-    level l holds [targets of level l+1 ; their k neighbours], exactly the multiset of
-    (node, time) pairs the recursion visits.  A fused forward+backward kernel is the next row
-    of SURVEY.md 8(f); this path keeps training-mode calls functional and on the GPU."""
-    device = node_feat.device
-    k = int(num_neighbors)
-    assert k > 0, 'Number of sampled neighbors for each node should be greater than 0!'
-    ids = torch.as_tensor(np.asarray(node_ids), dtype=torch.int64, device=device)
-    t_np = np.asarray(node_interact_times)
-    root_f64 = t_np.dtype != np.float32
-    times = torch.as_tensor(t_np, device=device).to(torch.float64 if root_f64 else torch.float32)
-    # ---- top-down sampling: levels[l] = (ids, nbr, eid, dt) for the targets evaluated at layer l
-    levels = {}
-    cur_ids, cur_t64, n_f64 = ids, times.to(torch.float64), (ids.shape[0] if root_f64 else 0)
-    for l in range(depth, 0, -1):
-        n = cur_ids.shape[0]
-        # query times as float64: root-chain targets keep their float64 times, neighbour targets carry the
-        # sampler's float32 values, which widen exactly (the comparison the reference's searchsorted makes)
-        nbr, eid, ts = sampler.get_historical_neighbors_device(cur_ids, cur_t64, k)
-        dt32 = cur_t64.to(torch.float32)[:, None] - ts
-        if n_f64:
-            dt32[:n_f64] = (cur_t64[:n_f64, None] - ts[:n_f64].to(torch.float64)).to(torch.float32)
-        levels[l] = (cur_ids, nbr, eid, dt32)
-        if l > 1:
-            cur_ids = torch.cat([cur_ids, nbr.reshape(-1)])
-            cur_t64 = torch.cat([cur_t64, ts.reshape(-1).to(torch.float64)])
-    w_t, b_t = time_encoder.w.weight.reshape(-1), time_encoder.w.bias
-
-    def encode(dt):          # cos of the single-rounded fma(dt, w, b), as nn.Linear(1, T) computes it
-        return torch.cos(torch.addcmul(b_t, dt.unsqueeze(-1), w_t))
-
-    # ---- bottom-up layers
-    h_prev = node_feat[levels[1][0]]
-    out = h_prev
-    for l in range(1, depth + 1):
-        t_ids, nbr, eid, dt = levels[l]
-        n = t_ids.shape[0]
-        attn, merge = conv_layers[l - 1], merge_layers[l - 1]
-        h_self = h_prev[:n]
-        h_nbr = node_feat[nbr] if l == 1 else h_prev[n:].reshape(n, k, -1)
-        te0 = encode(torch.zeros((n, 1), dtype=torch.float32, device=device))
-        query = residual = torch.cat([h_self.unsqueeze(1), te0], dim=2)
-        kv = torch.cat([h_nbr, edge_feat[eid], encode(dt)], dim=2)
-        H, hd = attn.num_heads, attn.head_dim
-        q = attn.query_projection(query).reshape(n, 1, H, hd).permute(0, 2, 1, 3)
-        kk = attn.key_projection(kv).reshape(n, k, H, hd).permute(0, 2, 1, 3)
-        vv = attn.value_projection(kv).reshape(n, k, H, hd).permute(0, 2, 1, 3)
-        scores = torch.einsum('bhld,bhnd->bhln', q, kk) * attn.scaling_factor
-        scores = scores.masked_fill((nbr == 0)[:, None, None, :], -1e10)
-        scores = attn.dropout(torch.softmax(scores, dim=-1))
-        ctx = torch.einsum('bhln,bhnd->bhld', scores, vv).permute(0, 2, 1, 3).flatten(start_dim=2)
-        o = attn.layer_norm(attn.dropout(attn.residual_fc(ctx)) + residual).squeeze(1)
-        out = merge.fc2(merge.act(merge.fc1(torch.cat([o, node_feat[t_ids]], dim=1))))
-        h_prev = out
     return out
 
 

@@ -231,6 +231,33 @@ int flid_entropy_filter(const float* const* probs_store_host, int num_iters, int
 int flid_prob_filter(const float* probs_last, int64_t n, int num_classes, float threshold, float* labels,
                      flid_stream stream);
 
+/* ------------------------------------------------------------------ training mode ---
+ * Forward and backward of the attention stream for the M-step batches that run with autograd and
+ * dropout (PTCL/M_step.py:196-325, NPL/NPL.py:185-314, PTCL/EM_warmup.py:113-238): the part of
+ * MultiHeadAttention.forward (models/modules.py:183-231) that is not a dense projection,
+ *     x_j = [table[hrow_j] | edge_feat[eid_j] | cos(fma(dt_j, time_w, time_b))]
+ *     z_h = sum_j dropout(softmax_j(masked_fill(u_h . x_j, nbr_j == 0, -1e10)))_hj x_j ,
+ * with u the query folded through the key projection (scaling included, natural-log domain).
+ * u, z, dz, du: float32 [n, num_heads, node_dim + edge_dim + time_dim]; hrow/nbr/eid int64 [n, k];
+ * dt float32 [n, k]; probs float32 [n, num_heads, k] (softmax before dropout, written by fwd, read
+ * by bwd).  Dropout bits are Philox4x32-10(seed; target, slot), word h = head h, identical in fwd
+ * and bwd; flid_attn_train_keep_mask exports them (uint8 [n, num_heads, k]) for tests.
+ * bwd: dtable (nullable) [rows, node_dim] is ACCUMULATED into (atomic adds, zero it first);
+ * dtime_partial (nullable) float32 [flid_attn_train_partials(n), 2, time_dim] receives per-block
+ * sums of (dL/dtime_w, dL/dtime_b), to be summed over the first axis by the caller.         */
+int64_t flid_attn_train_partials(int64_t n);
+int flid_attn_train_fwd(const float* u, const float* table, const int64_t* hrow, const int64_t* nbr,
+                        const int64_t* eid, const float* dt, const float* edge_feat, const float* time_w,
+                        const float* time_b, int64_t n, int k, int num_heads, int node_dim, int edge_dim,
+                        int time_dim, float p_drop, uint64_t seed, float* z, float* probs, flid_stream stream);
+int flid_attn_train_bwd(const float* u, const float* table, const int64_t* hrow, const int64_t* nbr,
+                        const int64_t* eid, const float* dt, const float* edge_feat, const float* time_w,
+                        const float* time_b, int64_t n, int k, int num_heads, int node_dim, int edge_dim,
+                        int time_dim, float p_drop, uint64_t seed, const float* probs, const float* dz, float* du,
+                        float* dtable, float* dtime_partial, flid_stream stream);
+int flid_attn_train_keep_mask(uint64_t seed, int64_t n, int num_heads, int k, float p_drop, uint8_t* keep,
+                              flid_stream stream);
+
 #ifdef __cplusplus
 }
 #endif
