@@ -36,6 +36,15 @@ class MlpWeights(C.Structure):
                [(n, C.c_int) for n in ("input_dim", "hidden1", "hidden2", "num_classes")]
 
 
+class TrainWeights(C.Structure):   # flid_train_weights and flid_train_grads (same members)
+    _fields_ = [(n, c_void) for n in ("fold_q", "fold_o", "res_b", "ln_w", "ln_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b",
+                                      "time_w", "time_b")]
+
+
+class TrainSaved(C.Structure):
+    _fields_ = [(n, c_void) for n in ("u", "probs", "z", "y", "ln", "hid")]
+
+
 _SIGNATURES = {
     "flid_last_error": (C.c_char_p, []),
     "flid_abi_version": (C.c_int, []),
@@ -83,6 +92,17 @@ _SIGNATURES = {
                                                                                   c_void, c_void]),
     "flid_attn_train_bwd": (C.c_int, [c_void] * 9 + [C.c_int64] + [C.c_int] * 5 + [C.c_float, C.c_uint64] +
                             [c_void] * 6),
+    "flid_train_layer_out_keep_mask": (C.c_int, [C.c_uint64, C.c_int64, C.c_int, C.c_float, c_void, c_void]),
+    "flid_train_layer_scratch_floats": (C.c_int64, [C.c_int64] + [C.c_int] * 5),
+    "flid_train_sample_levels": (C.c_int, [c_void, c_void, c_void, C.c_int, C.c_int64, C.c_int, C.c_int] +
+                                 [C.POINTER(c_void)] * 5 + [c_void]),
+    "flid_train_layer_fwd": (C.c_int, [C.POINTER(TrainWeights)] + [c_void] * 4 + [C.c_int64] + [c_void] * 4 +
+                             [C.c_int64] + [C.c_int] * 5 +
+                             [C.c_float, C.c_uint64, C.POINTER(TrainSaved), c_void, c_void, c_void]),
+    "flid_train_layer_bwd": (C.c_int, [C.POINTER(TrainWeights)] + [c_void] * 4 + [C.c_int64] + [c_void] * 4 +
+                             [C.c_int64] + [C.c_int] * 5 +
+                             [C.c_float, C.c_uint64, C.POINTER(TrainSaved), c_void, c_void, c_void, c_void,
+                              C.POINTER(TrainWeights), c_void, c_void]),
     "flid_attn_train_keep_mask": (C.c_int, [C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_float, c_void, c_void]),
 }
 

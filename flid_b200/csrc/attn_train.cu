@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(128) attn_train_fwd_kernel(AttnTrainArgs a) {
     float dt_l = 0.f;
     bool masked_l = true;
     if (lane < k) {
-        hrow_l = __ldg(a.hrow + i * k + lane);
+        hrow_l = a.hrow ? __ldg(a.hrow + i * k + lane) : a.hrow_offset + i * k + lane;
         e_l = (int)__ldg(a.eid + i * k + lane);
         dt_l = __ldg(a.dt + i * k + lane);
         masked_l = __ldg(a.nbr + i * k + lane) == 0;
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(128) attn_train_bwd_kernel(AttnTrainArgs a, At
         float dt_l = 0.f;
         bool masked_l = true;
         if (lane < k) {
-            hrow_l = __ldg(a.hrow + i * k + lane);
+            hrow_l = a.hrow ? __ldg(a.hrow + i * k + lane) : a.hrow_offset + i * k + lane;
             e_l = (int)__ldg(a.eid + i * k + lane);
             dt_l = __ldg(a.dt + i * k + lane);
             masked_l = __ldg(a.nbr + i * k + lane) == 0;

@@ -7,7 +7,7 @@ namespace flid {
 struct AttnTrainArgs {
     const float* u;          // [n, H, kd] folded queries (natural-log score domain, scaling included)
     const float* table;      // [R, dn] rows the neighbour slots read
-    const int64_t* hrow;     // [n, k] row of `table` per slot
+    const int64_t* hrow;     // [n, k] row of `table` per slot; null: row = hrow_offset + i * k + j
     const int64_t* nbr;      // [n, k] neighbour ids, 0 = padded slot (models/modules.py:206-215)
     const int64_t* eid;      // [n, k]
     const float* dt;         // [n, k]
@@ -20,6 +20,7 @@ struct AttnTrainArgs {
     uint64_t seed;
     float* z;                // [n, H, kd]            (forward only)
     float* probs;            // [n, H, k] softmax probabilities before dropout (forward only; saved for backward)
+    int64_t hrow_offset = 0;
 };
 
 struct AttnTrainGrads {

@@ -39,8 +39,9 @@ namespace flid {
 
 // ---------------------------------------------------------------- weight tiling
 // image layout: [n_block][k_chunk][half][c4][n_tile] float4
-__global__ void tc_prep_kernel(const float* __restrict__ W, int64_t ldw, int N, int K, int n_tile, int n_blocks,
-                               int k_chunks, float4* __restrict__ out) {
+// element (n, k) of the logical weight is W[n * sn + k * sk]: (ldw, 1) for W[N, K], (1, ldw) for a stored W^T[K, N]
+__global__ void tc_prep_kernel(const float* __restrict__ W, int64_t sn, int64_t sk, int N, int K, int n_tile,
+                               int n_blocks, int k_chunks, float4* __restrict__ out) {
     const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t total = (int64_t)n_blocks * k_chunks * 2 * C4 * n_tile;
     if (idx >= total) return;
@@ -57,7 +58,7 @@ __global__ void tc_prep_kernel(const float* __restrict__ W, int64_t ldw, int N, 
     float v[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-        const float x = (n < N && k + e < K) ? W[(int64_t)n * ldw + k + e] : 0.f;
+        const float x = (n < N && k + e < K) ? W[(int64_t)n * sn + (int64_t)(k + e) * sk] : 0.f;
         const float hi = tf32_hi(x);
         v[e] = half ? (x - hi) : hi;
     }
@@ -383,7 +384,7 @@ static int pick_n_tile(int N) {
     return t < 16 ? 16 : t;
 }
 
-int tc_prepare_weight(const float* W, int64_t ldw, int N, int K, TcWeight* w, cudaStream_t st) {
+static int prepare_weight(const float* W, int64_t sn, int64_t sk, int N, int K, TcWeight* w, cudaStream_t st) {
     FLID_REQUIRE(W && w && N > 0 && K > 0, "tc_prepare_weight: bad argument");
     const int n_tile = pick_n_tile(N);
     const int n_blocks = (N + n_tile - 1) / n_tile;
@@ -396,10 +397,18 @@ int tc_prepare_weight(const float* W, int64_t ldw, int N, int K, TcWeight* w, cu
     w->N = N, w->K = K, w->n_tile = n_tile, w->n_blocks = n_blocks, w->k_chunks = k_chunks;
     if (!w->buf) FLID_CUDA(cudaMalloc((void**)&w->buf, w->bytes()));
     const int64_t total = (int64_t)n_blocks * k_chunks * 2 * C4 * n_tile;
-    tc_prep_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(W, ldw, N, K, n_tile, n_blocks, k_chunks,
+    tc_prep_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(W, sn, sk, N, K, n_tile, n_blocks, k_chunks,
                                                                   reinterpret_cast<float4*>(w->buf));
     FLID_LAUNCH_CHECK();
     return FLID_OK;
+}
+
+int tc_prepare_weight(const float* W, int64_t ldw, int N, int K, TcWeight* w, cudaStream_t st) {
+    return prepare_weight(W, ldw, 1, N, K, w, st);
+}
+
+int tc_prepare_weight_t(const float* Wt, int64_t ldw, int N, int K, TcWeight* w, cudaStream_t st) {
+    return prepare_weight(Wt, 1, ldw, N, K, w, st);
 }
 
 void tc_free_weight(TcWeight* w) {

@@ -38,6 +38,8 @@ struct TcGemmArgs {
 
 // (re)build the tiled hi/lo image of W[N, K] (row stride ldw); allocates w->buf on first use
 int tc_prepare_weight(const float* W, int64_t ldw, int N, int K, TcWeight* w, cudaStream_t st);
+// same for a weight stored transposed, Wt[K, N] (row stride ldw): the data-gradient GEMMs of train_layer.cu
+int tc_prepare_weight_t(const float* Wt, int64_t ldw, int N, int K, TcWeight* w, cudaStream_t st);
 void tc_free_weight(TcWeight* w);
 int tc_gemm(const TcGemmArgs& g, const TcWeight& w, cudaStream_t st);
 // A-operand-in-TMEM variant, gemm_tc_ts.cu

@@ -258,6 +258,52 @@ int flid_attn_train_bwd(const float* u, const float* table, const int64_t* hrow,
 int flid_attn_train_keep_mask(uint64_t seed, int64_t n, int num_heads, int k, float p_drop, uint8_t* keep,
                               flid_stream stream);
 
+/* One MultiHeadAttention + MergeLayer evaluation in training mode (models/modules.py:167-245, :58-69 under
+ * autograd), forward and backward.  The caller folds the projections (differentiably) and passes
+ *   fold_q [H*kd, qd] = scaling * Wk_h^T Wq_h stacked over heads,   fold_o [qd, H*kd] = residual_fc.weight . blockdiag(Wv_h)
+ * (kd = node+edge+time, qd = node+time); the backward returns the gradients of those folded matrices.
+ * q [n, qd] = [layer input | cos(time_b)] is the query and the residual; merge_self [n, node_dim] is
+ * MergeLayer's second input.  flid_train_saved: caller-allocated tensors written by fwd and read by bwd:
+ *   u, z [n, H*kd]; probs [n, H, k]; y, ln [n, qd]; hid [n, node_dim].   pre_scratch: [n, qd].
+ * bwd: every member of flid_train_grads (same shapes as the weights) and d_table are ACCUMULATED into;
+ * d_q [n, qd] and d_cat [n, qd + node_dim] (= [grad of ln | grad of merge_self]) are overwritten;
+ * scratch: flid_train_layer_scratch_floats(...) floats.  Dropout (scores and residual_fc output) is
+ * Philox4x32-10 keyed by `seed`, regenerated in bwd.  hrow may be NULL: slot (i, j) then reads table row
+ * hrow_offset + i*k + j (the level-batched layout of flid_train_sample_levels).
+ *
+ * flid_train_sample_levels: the top-down sampling of models/TGAT.py:68-144 for n roots, level-batched.
+ * Level l (1..num_levels, index l-1 in the host arrays of device pointers) holds n*(1+k)^(num_levels-l)
+ * targets = [targets of level l+1 ; their neighbours]: ids int64, t64 float64 query times, nbr / eid int64
+ * [n_l, k], dt float32 [n_l, k] with the reference's dtype rules (TGAT.py:120-125).  Root ids must be
+ * valid (the caller checks them on the host); times_are_f32 = roots carry float32 times (widened).   */
+int flid_train_sample_levels(const flid_graph* g, const int64_t* roots, const double* times, int times_are_f32,
+                             int64_t n, int k, int num_levels, int64_t* const* ids_host, double* const* t64_host,
+                             int64_t* const* nbr_host, int64_t* const* eid_host, float* const* dt_host,
+                             flid_stream stream);
+typedef struct {
+    const float *fold_q, *fold_o, *res_b, *ln_w, *ln_b, *fc1_w, *fc1_b, *fc2_w, *fc2_b, *time_w, *time_b;
+} flid_train_weights;
+typedef struct {
+    float *fold_q, *fold_o, *res_b, *ln_w, *ln_b, *fc1_w, *fc1_b, *fc2_w, *fc2_b, *time_w, *time_b;
+} flid_train_grads;
+typedef struct {
+    float *u, *probs, *z, *y, *ln, *hid;
+} flid_train_saved;
+/* test hook: the residual_fc-output dropout bits of a layer call with this seed (uint8 [n, qd], 1 = kept) */
+int flid_train_layer_out_keep_mask(uint64_t seed, int64_t n, int qd, float p_drop, uint8_t* keep, flid_stream stream);
+int64_t flid_train_layer_scratch_floats(int64_t n, int k, int num_heads, int node_dim, int edge_dim, int time_dim);
+int flid_train_layer_fwd(const flid_train_weights* w, const float* q, const float* merge_self, const float* table,
+                         const int64_t* hrow, int64_t hrow_offset, const int64_t* nbr, const int64_t* eid,
+                         const float* dt, const float* edge_feat, int64_t n, int k, int num_heads, int node_dim,
+                         int edge_dim, int time_dim, float p_drop, uint64_t seed, const flid_train_saved* saved, float* pre_scratch,
+                         float* out, flid_stream stream);
+int flid_train_layer_bwd(const flid_train_weights* w, const float* q, const float* merge_self, const float* table,
+                         const int64_t* hrow, int64_t hrow_offset, const int64_t* nbr, const int64_t* eid,
+                         const float* dt, const float* edge_feat, int64_t n, int k, int num_heads, int node_dim,
+                         int edge_dim, int time_dim, float p_drop, uint64_t seed, const flid_train_saved* saved, const float* d_out,
+                         float* d_q, float* d_cat, float* d_table, const flid_train_grads* grads, float* scratch,
+                         flid_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -90,12 +90,13 @@ def test_attn_stream_forward_backward_vs_torch_float64(H, k, dn, de, T, p):
         rel = float((got.double() - want.double()).norm() / want.double().norm())
         assert rel <= 2e-4, (what, rel)
     # rows of all-masked targets take the uniform 1/k over their padded slots (modules.py:217-224)
-    assert torch.isfinite(z).all() and float(z[:10].abs().max()) > 0
+    assert torch.isfinite(z).all() and float(z.detach()[:10].abs().max()) > 0
 
 
-def reference_layers(time_encoder, conv_layers, merge_layers, node_feat, edge_feat, levels, depth, k, keeps, p):
+def reference_layers(time_encoder, conv_layers, merge_layers, node_feat, edge_feat, levels, depth, k, keeps, p,
+                     out_keeps=None):
     """The reference's literal op order (models/modules.py:167-245, models/TGAT.py:68-144) in torch, level-batched,
-    with explicit score-dropout bits."""
+    with explicit dropout bits (scores; residual_fc output when out_keeps is given, else the layer's nn.Dropout)."""
     w_t, b_t = time_encoder.w.weight.reshape(-1), time_encoder.w.bias
     encode = lambda dt: torch.cos(torch.addcmul(b_t, dt.unsqueeze(-1), w_t))
     h_prev = node_feat[levels[1][0]]
@@ -115,7 +116,9 @@ def reference_layers(time_encoder, conv_layers, merge_layers, node_feat, edge_fe
         scores = scores.masked_fill((nbr == 0)[:, None, None, :], -1e10)
         scores = torch.softmax(scores, dim=-1) * keeps[l - 1][:, :, None, :].float() / (1.0 - p)
         ctx = torch.einsum('bhln,bhnd->bhld', scores, vv).permute(0, 2, 1, 3).flatten(start_dim=2).squeeze(1)
-        o = attn.layer_norm(attn.dropout(attn.residual_fc(ctx)) + residual.squeeze(1))
+        res = attn.residual_fc(ctx)
+        res = attn.dropout(res) if out_keeps is None else res * out_keeps[l - 1].float() / (1.0 - p)
+        o = attn.layer_norm(res + residual.squeeze(1))
         h_prev = merge.fc2(merge.act(merge.fc1(torch.cat([o, node_feat[t_ids]], dim=1))))
     return h_prev
 
@@ -136,14 +139,15 @@ def test_training_forward_backward_with_dropout_vs_reference_op_order(L, k, p):
     sel = np.arange(400, 460)
     nodes, times = np.concatenate([src[sel], dst[sel]]), np.concatenate([ts[sel], ts[sel]])
     seeds = [77, 78]
-    torch.manual_seed(5)
     a = train.autograd_forward(ma.time_encoder, ma.temporal_conv_layers, ma.merge_layers, s, ma.node_raw_features,
                                ma.edge_raw_features, nodes, times, L, k, True, seeds=seeds)
     levels = train.sample_levels(s, nodes, times, L, k, torch.device(DEV))
     keeps = [train.score_keep_mask(seeds[l - 1], levels[l][0].shape[0], 2, k, p, DEV) for l in range(1, L + 1)]
-    torch.manual_seed(5)
+    out_keeps = [train.output_keep_mask(seeds[l - 1], levels[l][0].shape[0], 272, p, DEV) for l in range(1, L + 1)]
+    if p > 0:
+        assert abs(float(out_keeps[0].float().mean()) - (1 - p)) < 0.02
     b = reference_layers(mb.time_encoder, mb.temporal_conv_layers, mb.merge_layers, mb.node_raw_features,
-                         mb.edge_raw_features, levels, L, k, keeps, p)
+                         mb.edge_raw_features, levels, L, k, keeps, p, out_keeps)
     w = torch.randn(a.shape, generator=torch.Generator().manual_seed(2)).to(DEV)
     (a * w).sum().backward()
     (b * w).sum().backward()

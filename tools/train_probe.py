@@ -24,7 +24,7 @@ def main():
     ap.add_argument("--layers", type=int, default=2)
     ap.add_argument("--reps", type=int, default=10)
     a = ap.parse_args()
-    from test_gpu_train import reference_layers
+    from test_gpu_train import reference_layers  # torch ops, nn.Dropout for the output dropout
     dev = "cuda:0"
     d = synth.reddit_shape(scale=a.scale)
     src, dst, eid, ts = d.src_node_ids, d.dst_node_ids, d.edge_ids, d.node_interact_times
