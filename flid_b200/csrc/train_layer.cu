@@ -260,67 +260,91 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X
     }
 }
 
-// dW[i, j] += sum_m Y[m, i] X[m, j]: 64 x 64 outputs per block, the rows split into slabs over blockIdx.z
-constexpr int WG_T = 64, WG_R = 32;
+// dW[i, j] += sum_m Y[m, i] X[m, j].  A block owns a (16 RI) x (16 RJ) tile of dW and one slab of rows
+// (blockIdx.z); each of its 256 threads accumulates RI x RJ outputs in registers from two shared-memory
+// row tiles, then adds them to dW atomically.  RI x RJ = 8 x 4 / 4 x 8 keeps the FFMA pipe, not the
+// shared-memory port, the limiter (32 FMAs per three 16-byte loads).
+constexpr int WG_R = 32;
+template <int RI, int RJ>
 __global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ Y, int64_t ldy, int NI,
                                                     const float* __restrict__ X, int64_t ldx, int NJ,
                                                     float* __restrict__ dW, int64_t ldw, int64_t n, int64_t rows_per_slab) {
-    __shared__ __align__(16) float Ys[WG_R][WG_T + 4];
-    __shared__ __align__(16) float Xs[WG_R][WG_T + 4];
+    constexpr int TI = 16 * RI, TJ = 16 * RJ;
+    __shared__ __align__(16) float Ys[WG_R][TI + 4];
+    __shared__ __align__(16) float Xs[WG_R][TJ + 4];
     const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
-    const int i0 = blockIdx.x * WG_T, j0 = blockIdx.y * WG_T;
+    const int i0 = blockIdx.x * TI, j0 = blockIdx.y * TJ;
     const int64_t lo = blockIdx.z * rows_per_slab, hi = min(n, lo + rows_per_slab);
-    float acc[4][4];
+    float acc[RI][RJ];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < RI; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < RJ; ++j) acc[i][j] = 0.f;
     for (int64_t m0 = lo; m0 < hi; m0 += WG_R) {
 #pragma unroll
-        for (int v = t; v < WG_R * WG_T / 4; v += 256) {
-            const int r = v >> 4, c4 = (v & 15) * 4;
-            const int64_t m = m0 + r;
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-            if (m < hi) {
-                if (i0 + c4 < NI) a = __ldg(reinterpret_cast<const float4*>(Y + m * ldy + i0 + c4));
-                if (j0 + c4 < NJ) b = __ldg(reinterpret_cast<const float4*>(X + m * ldx + j0 + c4));
-            }
+        for (int v = t; v < WG_R * TI / 4; v += 256) {
+            const int r = v / (TI / 4), c4 = (v % (TI / 4)) * 4;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m0 + r < hi && i0 + c4 < NI) a = __ldg(reinterpret_cast<const float4*>(Y + (m0 + r) * ldy + i0 + c4));
             *reinterpret_cast<float4*>(&Ys[r][c4]) = a;
+        }
+#pragma unroll
+        for (int v = t; v < WG_R * TJ / 4; v += 256) {
+            const int r = v / (TJ / 4), c4 = (v % (TJ / 4)) * 4;
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m0 + r < hi && j0 + c4 < NJ) b = __ldg(reinterpret_cast<const float4*>(X + (m0 + r) * ldx + j0 + c4));
             *reinterpret_cast<float4*>(&Xs[r][c4]) = b;
         }
         __syncthreads();
-#pragma unroll 8
+#pragma unroll 4
         for (int r = 0; r < WG_R; ++r) {
-            const float4 a = *reinterpret_cast<const float4*>(&Ys[r][ty * 4]);
-            const float4 b = *reinterpret_cast<const float4*>(&Xs[r][tx * 4]);
-            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+            float av[RI], bv[RJ];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < RI; i += 4) {
+                const float4 a = *reinterpret_cast<const float4*>(&Ys[r][ty * RI + i]);
+                av[i] = a.x, av[i + 1] = a.y, av[i + 2] = a.z, av[i + 3] = a.w;
+            }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+            for (int j = 0; j < RJ; j += 4) {
+                const float4 b = *reinterpret_cast<const float4*>(&Xs[r][(j / 4) * 64 + tx * 4]);  // 16-byte lane stride
+                bv[j] = b.x, bv[j + 1] = b.y, bv[j + 2] = b.z, bv[j + 3] = b.w;
+            }
+#pragma unroll
+            for (int i = 0; i < RI; ++i)
+#pragma unroll
+                for (int j = 0; j < RJ; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
         }
         __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < RI; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int gi = i0 + ty * 4 + i, gj = j0 + tx * 4 + j;
+        for (int j = 0; j < RJ; ++j) {
+            const int gi = i0 + ty * RI + i, gj = j0 + (j / 4) * 64 + tx * 4 + (j % 4);
             if (gi < NI && gj < NJ) atomicAdd(dW + (int64_t)gi * ldw + gj, acc[i][j]);
         }
 }
 
-int wgrad(const float* Y, int64_t ldy, int NI, const float* X, int64_t ldx, int NJ, float* dW, int64_t ldw, int64_t n,
-          cudaStream_t st) {
-    const int ti = (int)ceil_div(NI, WG_T), tj = (int)ceil_div(NJ, WG_T);
+template <int RI, int RJ>
+int wgrad_launch(const float* Y, int64_t ldy, int NI, const float* X, int64_t ldx, int NJ, float* dW, int64_t ldw, int64_t n,
+                 cudaStream_t st) {
+    const int ti = (int)ceil_div(NI, 16 * RI), tj = (int)ceil_div(NJ, 16 * RJ);
     int64_t slabs = ceil_div(4 * 148, (int64_t)ti * tj);
     const int64_t max_slabs = ceil_div(n, 2 * WG_R);
     if (slabs > max_slabs) slabs = max_slabs;
     if (slabs < 1) slabs = 1;
     const int64_t rows = ceil_div(ceil_div(n, slabs), WG_R) * WG_R;
-    wgrad_kernel<<<dim3(ti, tj, (unsigned)ceil_div(n, rows)), 256, 0, st>>>(Y, ldy, NI, X, ldx, NJ, dW, ldw, n, rows);
+    wgrad_kernel<RI, RJ><<<dim3(ti, tj, (unsigned)ceil_div(n, rows)), 256, 0, st>>>(Y, ldy, NI, X, ldx, NJ, dW, ldw, n, rows);
     FLID_LAUNCH_CHECK();
     return FLID_OK;
+}
+
+int wgrad(const float* Y, int64_t ldy, int NI, const float* X, int64_t ldx, int NJ, float* dW, int64_t ldw, int64_t n,
+          cudaStream_t st) {
+    // the long side of the tile goes to the larger dimension; small square outputs keep 64 x 64
+    if (NI >= 256 && NI >= NJ) return wgrad_launch<8, 4>(Y, ldy, NI, X, ldx, NJ, dW, ldw, n, st);
+    if (NJ >= 256) return wgrad_launch<4, 8>(Y, ldy, NI, X, ldx, NJ, dW, ldw, n, st);
+    return wgrad_launch<4, 4>(Y, ldy, NI, X, ldx, NJ, dW, ldw, n, st);
 }
 
 int colsum(const float* X, int64_t ld, int64_t n, int cols, float* out, cudaStream_t st) {

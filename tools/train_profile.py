@@ -1,6 +1,7 @@
+"""torch.profiler breakdown (CPU and CUDA time by op / kernel) of one training-mode TGAT step at B = 200."""
 import os, sys
 import numpy as np, torch
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import flid_b200
 from flid_b200 import synth, train
 from torch.profiler import profile, ProfilerActivity
