@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--k", type=int, default=20)
     ap.add_argument("--layers", type=int, default=2)
     ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--skip-torch", action="store_true", help="time the kernel path only (ncu captures)")
     a = ap.parse_args()
     from test_gpu_train import reference_layers  # torch ops, nn.Dropout for the output dropout
     dev = "cuda:0"
@@ -70,6 +71,9 @@ def main():
         base = torch.cuda.memory_allocated()
         tk = timed(kernel_step)
         mk = torch.cuda.max_memory_allocated() - base
+        if a.skip_torch:
+            print(f"B={B:6d} roots={2 * B:6d} L={a.layers} k={a.k}: kernel path {tk:8.3f} ms ({mk / 2**20:8.1f} MiB peak)")
+            continue
         torch.cuda.reset_peak_memory_stats()
         tt = timed(torch_step)
         mt = torch.cuda.max_memory_allocated() - base
