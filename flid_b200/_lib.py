@@ -42,7 +42,11 @@ class TrainWeights(C.Structure):   # flid_train_weights and flid_train_grads (sa
 
 
 class TrainSaved(C.Structure):
-    _fields_ = [(n, c_void) for n in ("u", "probs", "z", "y", "ln", "hid")]
+    _fields_ = [(n, c_void) for n in ("q", "merge_self", "u", "probs", "z", "y", "ln", "hid", "out")]
+
+
+class TrainLevel(C.Structure):
+    _fields_ = [(n, c_void) for n in ("ids", "nbr", "eid", "dt")] + [("n", C.c_int64)]
 
 
 _SIGNATURES = {
@@ -93,16 +97,16 @@ _SIGNATURES = {
     "flid_attn_train_bwd": (C.c_int, [c_void] * 9 + [C.c_int64] + [C.c_int] * 5 + [C.c_float, C.c_uint64] +
                             [c_void] * 6),
     "flid_train_layer_out_keep_mask": (C.c_int, [C.c_uint64, C.c_int64, C.c_int, C.c_float, c_void, c_void]),
-    "flid_train_layer_scratch_floats": (C.c_int64, [C.c_int64] + [C.c_int] * 5),
     "flid_train_sample_levels": (C.c_int, [c_void, c_void, c_void, C.c_int, C.c_int64, C.c_int, C.c_int] +
                                  [C.POINTER(c_void)] * 5 + [c_void]),
-    "flid_train_layer_fwd": (C.c_int, [C.POINTER(TrainWeights)] + [c_void] * 4 + [C.c_int64] + [c_void] * 4 +
-                             [C.c_int64] + [C.c_int] * 5 +
-                             [C.c_float, C.c_uint64, C.POINTER(TrainSaved), c_void, c_void, c_void]),
-    "flid_train_layer_bwd": (C.c_int, [C.POINTER(TrainWeights)] + [c_void] * 4 + [C.c_int64] + [c_void] * 4 +
-                             [C.c_int64] + [C.c_int] * 5 +
-                             [C.c_float, C.c_uint64, C.POINTER(TrainSaved), c_void, c_void, c_void, c_void,
-                              C.POINTER(TrainWeights), c_void, c_void]),
+    "flid_train_model_scratch_floats": (C.c_int64, [C.c_int64] + [C.c_int] * 6),
+    "flid_train_model_fwd": (C.c_int, [C.POINTER(TrainWeights), C.POINTER(TrainLevel), C.POINTER(TrainSaved), c_void,
+                                       c_void, c_void] + [C.c_int] * 6 + [C.c_float, C.POINTER(C.c_uint64), c_void,
+                                                                          c_void]),
+    "flid_train_model_bwd": (C.c_int, [C.POINTER(TrainWeights), C.POINTER(TrainLevel), C.POINTER(TrainSaved), c_void,
+                                       c_void] + [C.c_int] * 6 + [C.c_float, C.POINTER(C.c_uint64), c_void,
+                                                                  C.POINTER(TrainWeights), c_void, c_void, c_void,
+                                                                  c_void]),
     "flid_attn_train_keep_mask": (C.c_int, [C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_float, c_void, c_void]),
 }
 

@@ -222,6 +222,48 @@ __global__ void __launch_bounds__(256) train_level_kernel(const int64_t* __restr
     }
 }
 
+// q[i] = [h row | te0] and merge_self[i] = node_feat[ids[i]]: the query / residual and MergeLayer's second input
+// (models/TGAT.py:88-92, :137-141).  h row = h_src[h_by_id ? ids[i] : i].  One warp per target.
+__global__ void __launch_bounds__(256) build_inputs_kernel(const float* __restrict__ h_src, int h_by_id,
+                                                           const float* __restrict__ node_feat, const int64_t* __restrict__ ids,
+                                                           const float* __restrict__ te0, float* __restrict__ q,
+                                                           float* __restrict__ merge_self, int64_t n, int dn, int T) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (i >= n) return;
+    const int64_t id = __ldg(ids + i);
+    const float4* h = reinterpret_cast<const float4*>(h_src + (h_by_id ? id : i) * dn);
+    const float4* raw = reinterpret_cast<const float4*>(node_feat + id * dn);
+    const int qd = dn + T;
+    for (int f = lane; f < dn / 4; f += 32) {
+        reinterpret_cast<float4*>(q + i * qd)[f] = __ldg(h + f);
+        reinterpret_cast<float4*>(merge_self + i * dn)[f] = __ldg(raw + f);
+    }
+    for (int f = lane; f < T / 4; f += 32)
+        reinterpret_cast<float4*>(q + i * qd + dn)[f] = __ldg(reinterpret_cast<const float4*>(te0) + f);
+}
+
+// dst[ids ? ids[i] : i, :dn] += src[i, :dn]  (atomic when rows may repeat)
+__global__ void __launch_bounds__(256) add_rows_kernel(const float* __restrict__ src, int64_t ld_src,
+                                                       const int64_t* __restrict__ ids, float* __restrict__ dst, int64_t n,
+                                                       int dn) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (i >= n) return;
+    const float4* s = reinterpret_cast<const float4*>(src + i * ld_src);
+    float4* d = reinterpret_cast<float4*>(dst + (ids ? __ldg(ids + i) : i) * dn);
+    for (int f = lane; f < dn / 4; f += 32) {
+        const float4 v = __ldg(s + f);
+        if (ids) {
+            atomicAdd(d + f, v);
+        } else {
+            float4 o = d[f];
+            o.x += v.x, o.y += v.y, o.z += v.z, o.w += v.w;
+            d[f] = o;
+        }
+    }
+}
+
 // d_hid *= (hid > 0), in place (ReLU backward)
 __global__ void relu_mask_kernel(float4* __restrict__ d, const float4* __restrict__ h, int64_t n4) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -390,14 +432,6 @@ int make_dims(int64_t n, int k, int H, int dn, int de, int T, Dims* d) {
 
 using namespace flid;
 
-extern "C" int64_t flid_train_layer_scratch_floats(int64_t n, int k, int num_heads, int node_dim, int edge_dim,
-                                                   int time_dim) {
-    const int64_t qd = node_dim + time_dim, zw = (int64_t)num_heads * (node_dim + edge_dim + time_dim);
-    (void)k;
-    // d_hid [n, dn] | d_pre [n, qd] | dz [n, zw] | du [n, zw] | time partial [blocks, 2T]
-    return n * (node_dim + qd + 2 * zw) + attn_train_blocks(n) * 2 * time_dim + 64;
-}
-
 extern "C" int flid_train_sample_levels(const flid_graph* g, const int64_t* roots, const double* times,
                                         int times_are_f32, int64_t n, int k, int num_levels, int64_t* const* ids_host,
                                         double* const* t64_host, int64_t* const* nbr_host, int64_t* const* eid_host,
@@ -431,18 +465,12 @@ extern "C" int flid_train_layer_out_keep_mask(uint64_t seed, int64_t n, int qd, 
     return FLID_OK;
 }
 
-extern "C" int flid_train_layer_fwd(const flid_train_weights* w, const float* q, const float* merge_self,
-                                    const float* table, const int64_t* hrow, int64_t hrow_offset, const int64_t* nbr,
-                                    const int64_t* eid, const float* dt, const float* edge_feat, int64_t n, int k,
-                                    int num_heads, int node_dim,
-                                    int edge_dim, int time_dim, float p_drop, uint64_t seed, const flid_train_saved* s,
-                                    float* pre_scratch, float* out, flid_stream stream) {
-    cudaStream_t st = (cudaStream_t)stream;
-    Dims d;
-    FLID_TRY(make_dims(n, k, num_heads, node_dim, edge_dim, time_dim, &d));
-    FLID_REQUIRE(w && s && q && out && pre_scratch, "flid_train_layer_fwd: null argument");
-    FLID_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "train layer: dropout probability must be in [0, 1)");
-    if (n == 0) return FLID_OK;
+static int layer_fwd(const flid_train_weights* w, const float* q, const float* merge_self, const float* table,
+                     const int64_t* hrow, int64_t hrow_offset, const int64_t* nbr, const int64_t* eid, const float* dt,
+                     const float* edge_feat, const Dims& d, float p_drop, uint64_t seed, const flid_train_saved* s,
+                     float* pre_scratch, float* out, cudaStream_t st) {
+    const int64_t n = d.n;
+    const int k = d.k, num_heads = d.H;
     FLID_TRY(tc_prepare_weight(w->fold_q, d.qd, d.zw, d.qd, &g_fwd.q, st));
     FLID_TRY(tc_prepare_weight(w->fold_o, d.zw, d.qd, d.zw, &g_fwd.o, st));
     FLID_TRY(tc_prepare_weight(w->fc1_w, d.qd + d.dn, d.dn, d.qd + d.dn, &g_fwd.f1, st));
@@ -463,18 +491,13 @@ extern "C" int flid_train_layer_fwd(const flid_train_weights* w, const float* q,
     return FLID_OK;
 }
 
-extern "C" int flid_train_layer_bwd(const flid_train_weights* w, const float* q, const float* merge_self,
-                                    const float* table, const int64_t* hrow, int64_t hrow_offset, const int64_t* nbr,
-                                    const int64_t* eid, const float* dt, const float* edge_feat, int64_t n, int k,
-                                    int num_heads, int node_dim,
-                                    int edge_dim, int time_dim, float p_drop, uint64_t seed, const flid_train_saved* s,
-                                    const float* d_out, float* d_q, float* d_cat, float* d_table,
-                                    const flid_train_grads* g, float* scratch, flid_stream stream) {
-    cudaStream_t st = (cudaStream_t)stream;
-    Dims d;
-    FLID_TRY(make_dims(n, k, num_heads, node_dim, edge_dim, time_dim, &d));
-    FLID_REQUIRE(w && s && g && q && d_out && d_q && d_cat && scratch, "flid_train_layer_bwd: null argument");
-    if (n == 0) return FLID_OK;
+static int layer_bwd(const flid_train_weights* w, const float* q, const float* merge_self, const float* table,
+                     const int64_t* hrow, int64_t hrow_offset, const int64_t* nbr, const int64_t* eid, const float* dt,
+                     const float* edge_feat, const Dims& d, float p_drop, uint64_t seed, const flid_train_saved* s,
+                     const float* d_out, float* d_q, float* d_cat, float* d_table, const flid_train_grads* g,
+                     float* scratch, cudaStream_t st) {
+    const int64_t n = d.n;
+    const int k = d.k, num_heads = d.H;
     float* d_hid = scratch;
     float* d_pre = d_hid + n * d.dn;
     float* dz = d_pre + n * d.qd;
@@ -526,5 +549,98 @@ extern "C" int flid_train_layer_bwd(const flid_train_weights* w, const float* q,
     add_kernel<<<(unsigned)ceil_div(n * d.qd / 4, 256), 256, 0, st>>>(reinterpret_cast<float4*>(d_q),
                                                                      reinterpret_cast<const float4*>(d_pre), n * d.qd / 4);
     FLID_LAUNCH_CHECK();
+    return FLID_OK;
+}
+
+// floats of per-layer backward scratch for n targets: d_hid | d_pre | dz | du | time partials | d_q | d_cat
+static int64_t layer_scratch(const Dims& d, int64_t n) {
+    return n * (d.dn + d.qd + 2 * (int64_t)d.zw) + attn_train_blocks(n) * 2 * d.T + n * (2 * d.qd + d.dn) + 64;
+}
+
+extern "C" int64_t flid_train_model_scratch_floats(int64_t n_roots, int k, int num_layers, int num_heads, int node_dim,
+                                                   int edge_dim, int time_dim) {
+    Dims d;
+    if (make_dims(n_roots, k, num_heads, node_dim, edge_dim, time_dim, &d) != FLID_OK || num_layers < 1) return -1;
+    int64_t n1 = n_roots, dh = 0;
+    for (int l = num_layers; l > 1; --l) n1 *= (1 + k), dh += n1 * node_dim;   // gradient buffers of layers 1 .. L-1
+    return layer_scratch(d, n1) + dh;
+}
+
+extern "C" int flid_train_model_fwd(const flid_train_weights* w, const flid_train_level* lv, const flid_train_saved* sv,
+                                    const float* node_feat, const float* edge_feat, const float* te0, int num_layers, int k,
+                                    int num_heads, int node_dim, int edge_dim, int time_dim, float p_drop,
+                                    const uint64_t* seeds_host, float* pre_scratch, flid_stream stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    FLID_REQUIRE(w && lv && sv && node_feat && edge_feat && te0 && seeds_host && pre_scratch && num_layers >= 1,
+                 "flid_train_model_fwd: bad argument");
+    FLID_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "train layer: dropout probability must be in [0, 1)");
+    FLID_REQUIRE(k > 0 && k <= 32, "training path: num_neighbors must be in 1..32 (got %d)", k);
+    for (int l = 1; l <= num_layers; ++l) {
+        const flid_train_level& L = lv[l - 1];
+        const flid_train_saved& S = sv[l - 1];
+        Dims d;
+        FLID_TRY(make_dims(L.n, k, num_heads, node_dim, edge_dim, time_dim, &d));
+        if (L.n == 0) continue;
+        const float* prev = l == 1 ? node_feat : sv[l - 2].out;
+        build_inputs_kernel<<<(unsigned)ceil_div(L.n * 32, 256), 256, 0, st>>>(prev, l == 1, node_feat, L.ids, te0, S.q,
+                                                                               S.merge_self, L.n, d.dn, d.T);
+        FLID_LAUNCH_CHECK();
+        FLID_TRY(layer_fwd(&w[l - 1], S.q, S.merge_self, prev, l == 1 ? L.nbr : nullptr, l == 1 ? 0 : L.n, L.nbr, L.eid, L.dt,
+                           edge_feat, d, p_drop, seeds_host[l - 1], &S, pre_scratch, S.out, st));
+    }
+    return FLID_OK;
+}
+
+extern "C" int flid_train_model_bwd(const flid_train_weights* w, const flid_train_level* lv, const flid_train_saved* sv,
+                                    const float* node_feat, const float* edge_feat, int num_layers, int k, int num_heads,
+                                    int node_dim, int edge_dim, int time_dim, float p_drop, const uint64_t* seeds_host,
+                                    const float* d_out, const flid_train_grads* g, float* d_te0, float* d_node_feat,
+                                    float* scratch, flid_stream stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    FLID_REQUIRE(w && lv && sv && node_feat && edge_feat && seeds_host && d_out && g && d_te0 && scratch && num_layers >= 1,
+                 "flid_train_model_bwd: bad argument");
+    Dims d1;
+    FLID_TRY(make_dims(lv[0].n, k, num_heads, node_dim, edge_dim, time_dim, &d1));
+    // gradient buffers of the intermediate layer outputs, zeroed: the attention backward accumulates into them
+    float* dh[16] = {nullptr};
+    FLID_REQUIRE(num_layers <= 16, "flid_train_model_bwd: too many layers");
+    float* p = scratch + layer_scratch(d1, lv[0].n);
+    for (int l = 1; l < num_layers; ++l) {
+        dh[l] = p;
+        p += lv[l - 1].n * node_dim;
+        FLID_CUDA(cudaMemsetAsync(dh[l], 0, lv[l - 1].n * node_dim * sizeof(float), st));
+    }
+    const float* d_cur = d_out;
+    for (int l = num_layers; l >= 1; --l) {
+        const flid_train_level& L = lv[l - 1];
+        const flid_train_saved& S = sv[l - 1];
+        Dims d;
+        FLID_TRY(make_dims(L.n, k, num_heads, node_dim, edge_dim, time_dim, &d));
+        if (L.n == 0) continue;
+        const int cw = d.qd + d.dn;
+        float* d_q = scratch + layer_scratch(d, L.n) - 64 - L.n * (2 * d.qd + d.dn);
+        float* d_cat = d_q + L.n * d.qd;
+        const float* table = l == 1 ? node_feat : sv[l - 2].out;
+        float* d_table = l == 1 ? d_node_feat : dh[l - 1];
+        FLID_TRY(layer_bwd(&w[l - 1], S.q, S.merge_self, table, l == 1 ? L.nbr : nullptr, l == 1 ? 0 : L.n, L.nbr, L.eid,
+                           L.dt, edge_feat, d, p_drop, seeds_host[l - 1], &S, d_cur, d_q, d_cat, d_table, &g[l - 1], scratch,
+                           st));
+        FLID_TRY(colsum(d_q + d.dn, d.qd, L.n, d.T, d_te0, st));                     // te0 = cos(time_b) part of the query
+        const unsigned blocks = (unsigned)ceil_div(L.n * 32, 256);
+        if (d_node_feat) {                                                             // MergeLayer's raw-feature input
+            add_rows_kernel<<<blocks, 256, 0, st>>>(d_cat + d.qd, cw, L.ids, d_node_feat, L.n, d.dn);
+            FLID_LAUNCH_CHECK();
+        }
+        if (l == 1) {
+            if (d_node_feat) {
+                add_rows_kernel<<<blocks, 256, 0, st>>>(d_q, d.qd, L.ids, d_node_feat, L.n, d.dn);
+                FLID_LAUNCH_CHECK();
+            }
+        } else {
+            add_rows_kernel<<<blocks, 256, 0, st>>>(d_q, d.qd, nullptr, dh[l - 1], L.n, d.dn);   // targets = rows [0, n)
+            FLID_LAUNCH_CHECK();
+            d_cur = dh[l - 1];
+        }
+    }
     return FLID_OK;
 }

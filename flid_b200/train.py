@@ -4,9 +4,9 @@ The M-step batches of the reference run ``compute_src_dst_node_temporal_embeddin
 enabled and ``model.train()`` (PTCL/M_step.py:196-325, NPL/NPL.py:185-314,
 PTCL/EM_warmup.py:113-238).  Here a layer is split where its cost is:
 
-* one attention + MergeLayer evaluation is ONE autograd node, ``TrainLayer``: its forward and its
-  backward are each one C-ABI call (``flid_train_layer_fwd`` / ``_bwd``, csrc/train_layer.cu) that
-  launches the tcgen05 GEMMs, the attention-stream kernels (gather, time encoding, masked softmax,
+* the whole L-layer stack is ONE autograd node, ``TrainStack``: its forward and its backward are
+  each one C-ABI call (``flid_train_model_fwd`` / ``_bwd``, csrc/train_layer.cu) that launches, per
+  layer, the tcgen05 GEMMs, the attention-stream kernels (gather, time encoding, masked softmax,
   score dropout, weighted sum and their hand-written backward, csrc/attn_train.cu), LayerNorm,
   dropout and the weight-gradient reductions back to back.  No ``[n, k, 444]`` / ``[n, k, 272]``
   tensor is ever materialised; the backward pass re-gathers the rows instead of saving them;
@@ -98,76 +98,97 @@ def score_keep_mask(seed, n, num_heads, k, p_drop, device):
 
 
 _LAYER_TENSORS = ("fold_q", "fold_o", "res_b", "ln_w", "ln_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b", "time_w", "time_b")
+_NW = len(_LAYER_TENSORS)
 
 
-class TrainLayer(torch.autograd.Function):
-    """One attention + merge layer through ``flid_train_layer_fwd`` / ``flid_train_layer_bwd`` (csrc/train_layer.cu).
+def _saved_layout(n, k, H, dn, de, T):
+    """float counts of one layer's flid_train_saved members, in struct order"""
+    qd, zw = dn + T, H * (dn + de + T)
+    return (n * qd, n * dn, n * zw, n * H * k, n * zw, n * qd, n * qd, n * dn, n * dn)   # q merge_self u probs z y ln hid out
 
-    Differentiable inputs: q [n, qd], merge_self [n, dn], table [R, dn] and the eleven weight tensors of
-    ``_LAYER_TENSORS`` (folded projections included); index tensors and edge features carry no gradient."""
+
+class TrainStack(torch.autograd.Function):
+    """The whole L-layer attention stack as ONE autograd node: forward = ``flid_train_model_fwd``, backward =
+    ``flid_train_model_bwd`` (csrc/train_layer.cu), one C call each.
+
+    Differentiable inputs: node_feat [R, dn] (the layer-0 table), te0 [T] = cos(time_b), and 11 weight tensors
+    per layer in ``_LAYER_TENSORS`` order (folded projections included).  ``levels`` / ``seeds`` are plain Python
+    lists (index l-1 for layer l)."""
 
     @staticmethod
-    def forward(ctx, q, merge_self, table, hrow, nbr, eid, dt, edge_feat, p_drop, seed, num_heads, *weights):
-        # hrow: int64 [n, k] rows of `table`, or a Python int r0: slot (i, j) reads table row r0 + i * k + j
-        q, merge_self, table = q.contiguous(), merge_self.contiguous(), table.contiguous()
+    def forward(ctx, node_feat, edge_feat, te0, levels, seeds, p_drop, num_heads, k, *weights):
+        node_feat, edge_feat, te0 = node_feat.contiguous(), edge_feat.contiguous(), te0.contiguous()
         weights = tuple(w.contiguous() for w in weights)
-        nbr, eid, dt = nbr.contiguous(), eid.contiguous(), dt.contiguous()
-        hrow_t, hrow_off = (None, int(hrow)) if isinstance(hrow, int) else (hrow.contiguous(), 0)
-        n, qd = q.shape
-        k, dn, de = nbr.shape[1], table.shape[1], edge_feat.shape[1]
-        T, H = qd - dn, int(num_heads)
-        zw = H * (dn + de + T)
-        for t in (q, merge_self, table, dt, edge_feat) + weights:
+        L, H = len(levels), int(num_heads)
+        dn, de, T = node_feat.shape[1], edge_feat.shape[1], te0.shape[0]
+        qd, zw = dn + T, H * (dn + de + T)
+        dev = node_feat.device
+        for t in (node_feat, edge_feat, te0) + weights:
             if t.dtype != torch.float32 or not t.is_cuda:
-                raise TypeError("TrainLayer: float32 CUDA tensors required (flid_b200 has no CPU path)")
-        if weights[0].shape != (zw, qd) or weights[1].shape != (qd, zw) or merge_self.shape != (n, dn):
-            raise ValueError("TrainLayer: inconsistent shapes")
-        dev = q.device
-        new = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
-        saved = (new(n, zw), new(n, H, k), new(n, zw), new(n, qd), new(n, qd), new(n, dn))   # u probs z y ln hid
-        out, pre = new(n, dn), new(n, qd)
-        wst = _lib.TrainWeights(*[w.data_ptr() for w in weights])
-        sst = _lib.TrainSaved(*[t.data_ptr() for t in saved])
+                raise TypeError("TrainStack: float32 CUDA tensors required (flid_b200 has no CPU path)")
+        if len(weights) != _NW * L or weights[0].shape != (zw, qd) or weights[1].shape != (qd, zw):
+            raise ValueError("TrainStack: inconsistent weight shapes")
+        n_top = levels[L - 1][0].shape[0]
+        out = torch.empty((n_top, dn), dtype=torch.float32, device=dev)
+        layouts = [_saved_layout(levels[l][0].shape[0], k, H, dn, de, T) for l in range(L)]
+        total = sum(sum(lay) for lay in layouts) - layouts[L - 1][-1] + levels[0][0].shape[0] * qd
+        buf = torch.empty((total,), dtype=torch.float32, device=dev)      # every saved activation + pre_scratch
+        base, off, saved_ptrs = buf.data_ptr(), 0, []
+        for l, lay in enumerate(layouts):
+            ptrs = []
+            for j, cnt in enumerate(lay):
+                if l == L - 1 and j == len(lay) - 1:
+                    ptrs.append(out.data_ptr())                           # the top layer's output is the result
+                else:
+                    ptrs.append(base + 4 * off)
+                    off += cnt
+            saved_ptrs.append(ptrs)
+        pre_ptr = base + 4 * off
+        wst = (_lib.TrainWeights * L)(*[_lib.TrainWeights(*[w.data_ptr() for w in weights[_NW * l:_NW * (l + 1)]])
+                                        for l in range(L)])
+        lst = (_lib.TrainLevel * L)(*[_lib.TrainLevel(lv[0].data_ptr(), lv[1].data_ptr(), lv[2].data_ptr(),
+                                                      lv[3].data_ptr(), lv[0].shape[0]) for lv in levels])
+        sst = (_lib.TrainSaved * L)(*[_lib.TrainSaved(*p) for p in saved_ptrs])
+        sds = (_lib.C.c_uint64 * L)(*[int(s) for s in list(seeds)[:L]])
         with torch.cuda.device(dev):
-            _lib.check(_lib.lib().flid_train_layer_fwd(
-                wst, _lib.ptr(q), _lib.ptr(merge_self), _lib.ptr(table), _lib.ptr(hrow_t), hrow_off, _lib.ptr(nbr),
-                _lib.ptr(eid), _lib.ptr(dt), _lib.ptr(edge_feat), n, k, H, dn, de, T, float(p_drop), int(seed), sst,
-                _lib.ptr(pre), _lib.ptr(out), _lib.stream()))
-        ctx.save_for_backward(q, merge_self, table, nbr, eid, dt, edge_feat, *weights, *saved)
-        ctx.hrow = hrow_t      # an index tensor without autograd history
-        ctx.meta = (float(p_drop), int(seed), H, len(weights), hrow_off)
+            _lib.check(_lib.lib().flid_train_model_fwd(wst, lst, sst, _lib.ptr(node_feat), _lib.ptr(edge_feat),
+                                                       _lib.ptr(te0), L, int(k), H, dn, de, T, float(p_drop), sds,
+                                                       _lib.c_void(pre_ptr), _lib.stream()))
+        ctx.save_for_backward(node_feat, edge_feat, te0, *weights)
+        ctx.keep = (levels, buf)                # index tensors and activations (no autograd history)
+        ctx.structs = (wst, lst, sst, sds)
+        ctx.meta = (L, H, int(k), float(p_drop))
         return out
 
     @staticmethod
     def backward(ctx, d_out):
-        p_drop, seed, H, nw, hrow_off = ctx.meta
-        q, merge_self, table, nbr, eid, dt, edge_feat = ctx.saved_tensors[:7]
-        weights, saved = ctx.saved_tensors[7:7 + nw], ctx.saved_tensors[7 + nw:]
-        hrow = ctx.hrow
-        n, qd = q.shape
-        k, dn, de = nbr.shape[1], table.shape[1], edge_feat.shape[1]
-        T = qd - dn
-        dev = q.device
+        L, H, k, p_drop = ctx.meta
+        node_feat, edge_feat, te0 = ctx.saved_tensors[:3]
+        weights = ctx.saved_tensors[3:]
+        wst, lst, sst, sds = ctx.structs
+        levels = ctx.keep[0]
+        dn, de, T = node_feat.shape[1], edge_feat.shape[1], te0.shape[0]
+        dev = node_feat.device
         d_out = d_out.contiguous()
-        flat = torch.zeros((sum(w.numel() for w in weights),), dtype=torch.float32, device=dev)   # one memset
-        grads, off = [], 0
-        for w in weights:
-            grads.append(flat[off:off + w.numel()].view(w.shape))
-            off += w.numel()
-        grads = tuple(grads)
-        d_q = torch.empty_like(q)
-        d_cat = torch.empty((n, qd + dn), dtype=torch.float32, device=dev)
-        d_table = torch.zeros_like(table) if ctx.needs_input_grad[2] else None
+        sizes = [w.numel() for w in weights]
+        flat = torch.zeros((sum(sizes) + T,), dtype=torch.float32, device=dev)      # one memset for every gradient
+        parts = flat.split(sizes + [T])
+        grads = tuple(g.view(w.shape) for g, w in zip(parts, weights))
+        d_te0 = parts[-1]
+        d_node = torch.zeros_like(node_feat) if ctx.needs_input_grad[0] else None
+        base = flat.data_ptr()
+        offs, o = [], 0
+        for sz in sizes:
+            offs.append(base + 4 * o)
+            o += sz
+        gst = (_lib.TrainWeights * L)(*[_lib.TrainWeights(*offs[_NW * l:_NW * (l + 1)]) for l in range(L)])
         with torch.cuda.device(dev):
-            floats = int(_lib.lib().flid_train_layer_scratch_floats(n, k, H, dn, de, T))
+            floats = int(_lib.lib().flid_train_model_scratch_floats(levels[L - 1][0].shape[0], k, L, H, dn, de, T))
             scratch = torch.empty((floats,), dtype=torch.float32, device=dev)
-            _lib.check(_lib.lib().flid_train_layer_bwd(
-                _lib.TrainWeights(*[w.data_ptr() for w in weights]), _lib.ptr(q), _lib.ptr(merge_self), _lib.ptr(table),
-                _lib.ptr(hrow), hrow_off, _lib.ptr(nbr), _lib.ptr(eid), _lib.ptr(dt), _lib.ptr(edge_feat), n, k, H, dn, de, T,
-                p_drop, seed, _lib.TrainSaved(*[t.data_ptr() for t in saved]), _lib.ptr(d_out), _lib.ptr(d_q),
-                _lib.ptr(d_cat), _lib.ptr(d_table), _lib.TrainWeights(*[g.data_ptr() for g in grads]), _lib.ptr(scratch),
-                _lib.stream()))
-        return (d_q, d_cat[:, qd:], d_table, None, None, None, None, None, None, None, None) + grads
+            _lib.check(_lib.lib().flid_train_model_bwd(wst, lst, sst, _lib.ptr(node_feat), _lib.ptr(edge_feat), L, k, H,
+                                                       dn, de, T, p_drop, sds, _lib.ptr(d_out), gst, _lib.ptr(d_te0),
+                                                       _lib.ptr(d_node), _lib.ptr(scratch), _lib.stream()))
+        return (d_node, None, d_te0, None, None, None, None, None) + grads
 
 
 def folded_weights(attn, kd, qd):
@@ -180,26 +201,6 @@ def folded_weights(attn, kd, qd):
     fold_q = (torch.matmul(wk.transpose(1, 2), wq) * attn.scaling_factor).reshape(H * kd, qd)
     fold_o = torch.matmul(attn.residual_fc.weight, torch.block_diag(*wv.unbind(0)))        # [qd, H*hd] . [H*hd, H*kd]
     return fold_q, fold_o
-
-
-def attention_layer(attn, merge, time_w, time_b, h_self, merge_self, table, hrow, nbr, eid, dt, edge_feat, training,
-                    seed=None):
-    """One MultiHeadAttention + MergeLayer evaluation (models/modules.py:167-245, :58-69) for n targets.
-
-    h_self [n, dn]: layer input of the targets; merge_self [n, dn]: MergeLayer's second input;
-    table / hrow: where the neighbour slots' layer inputs live.  ``seed`` fixes both dropouts."""
-    n, dn = h_self.shape
-    T = time_w.shape[0]
-    kd, qd = dn + edge_feat.shape[1] + T, dn + T
-    p = float(attn.dropout.p) if training else 0.0
-    te0 = torch.cos(time_b)                                    # cos(fma(0, w, b)), models/TGAT.py:90
-    query = torch.cat([h_self, te0.expand(n, T)], dim=1)      # also the residual (modules.py:186)
-    fold_q, fold_o = folded_weights(attn, kd, qd)
-    if p > 0.0 and seed is None:
-        seed = _score_seed()
-    return TrainLayer.apply(query, merge_self, table, hrow, nbr, eid, dt, edge_feat, p, seed or 0, attn.num_heads,
-                            fold_q, fold_o, attn.residual_fc.bias, attn.layer_norm.weight, attn.layer_norm.bias,
-                            merge.fc1.weight, merge.fc1.bias, merge.fc2.weight, merge.fc2.bias, time_w, time_b)
 
 
 def output_keep_mask(seed, n, qd, p_drop, device):
@@ -250,16 +251,16 @@ def autograd_forward(time_encoder, conv_layers, merge_layers, sampler, node_feat
         raise ValueError("flid_b200 training path: num_neighbors must be <= 32")
     levels = sample_levels(sampler, node_ids, node_interact_times, depth, k, device)
     w_t, b_t = time_encoder.w.weight.reshape(-1), time_encoder.w.bias
-    h_prev = node_feat[levels[1][0]]
-    out = h_prev
-    for l in range(1, depth + 1):
-        t_ids, nbr, eid, dt = levels[l]
-        n = t_ids.shape[0]
-        if l == 1:
-            table, hrow = node_feat, nbr          # rows by neighbour id
-        else:                                     # rows n.. of the previous level are this level's neighbours
-            table, hrow = h_prev, n
-        out = attention_layer(conv_layers[l - 1], merge_layers[l - 1], w_t, b_t, h_prev[:n], node_feat[t_ids], table,
-                              hrow, nbr, eid, dt, edge_feat, training, None if seeds is None else seeds[l - 1])
-        h_prev = out
-    return out
+    dn, T = node_feat.shape[1], b_t.shape[0]
+    kd, qd = dn + edge_feat.shape[1] + T, dn + T
+    p = float(conv_layers[0].dropout.p) if training else 0.0
+    weights = []
+    for l in range(depth):
+        attn, merge = conv_layers[l], merge_layers[l]
+        weights += [*folded_weights(attn, kd, qd), attn.residual_fc.bias, attn.layer_norm.weight, attn.layer_norm.bias,
+                    merge.fc1.weight, merge.fc1.bias, merge.fc2.weight, merge.fc2.bias, w_t, b_t]
+    if seeds is None:
+        seeds = [_score_seed() if p > 0.0 else 0 for _ in range(depth)]
+    te0 = torch.cos(b_t)                                       # cos(fma(0, w, b)), models/TGAT.py:90
+    return TrainStack.apply(node_feat, edge_feat, te0, [levels[l] for l in range(1, depth + 1)], list(seeds), p,
+                            conv_layers[0].num_heads, k, *weights)

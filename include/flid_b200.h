@@ -258,28 +258,26 @@ int flid_attn_train_bwd(const float* u, const float* table, const int64_t* hrow,
 int flid_attn_train_keep_mask(uint64_t seed, int64_t n, int num_heads, int k, float p_drop, uint8_t* keep,
                               flid_stream stream);
 
-/* One MultiHeadAttention + MergeLayer evaluation in training mode (models/modules.py:167-245, :58-69 under
- * autograd), forward and backward.  The caller folds the projections (differentiably) and passes
+/* Training-mode forward / backward of the whole L-layer attention stack (models/TGAT.py:68-144 and
+ * models/MemoryModel.py:632-715 under autograd; each layer is models/modules.py:167-245 + :58-69), level-batched.
+ *
+ * flid_train_sample_levels: the top-down sampling for n roots.  Level l (1..num_levels, index l-1 in the host
+ * arrays of device pointers) holds n*(1+k)^(num_levels-l) targets = [targets of level l+1 ; their neighbours]:
+ * ids int64, t64 float64 query times, nbr / eid int64 [n_l, k], dt float32 [n_l, k] with the reference's dtype
+ * rules (TGAT.py:120-125).  Root ids must be valid (the caller checks them on the host); times_are_f32 = the
+ * roots carry float32 times (widened).
+ *
+ * Weights per layer (flid_train_weights[l-1]); the caller folds the projections (differentiably) and passes
  *   fold_q [H*kd, qd] = scaling * Wk_h^T Wq_h stacked over heads,   fold_o [qd, H*kd] = residual_fc.weight . blockdiag(Wv_h)
  * (kd = node+edge+time, qd = node+time); the backward returns the gradients of those folded matrices.
- * q [n, qd] = [layer input | cos(time_b)] is the query and the residual; merge_self [n, node_dim] is
- * MergeLayer's second input.  flid_train_saved: caller-allocated tensors written by fwd and read by bwd:
- *   u, z [n, H*kd]; probs [n, H, k]; y, ln [n, qd]; hid [n, node_dim].   pre_scratch: [n, qd].
- * bwd: every member of flid_train_grads (same shapes as the weights) and d_table are ACCUMULATED into;
- * d_q [n, qd] and d_cat [n, qd + node_dim] (= [grad of ln | grad of merge_self]) are overwritten;
- * scratch: flid_train_layer_scratch_floats(...) floats.  Dropout (scores and residual_fc output) is
- * Philox4x32-10 keyed by `seed`, regenerated in bwd.  hrow may be NULL: slot (i, j) then reads table row
- * hrow_offset + i*k + j (the level-batched layout of flid_train_sample_levels).
- *
- * flid_train_sample_levels: the top-down sampling of models/TGAT.py:68-144 for n roots, level-batched.
- * Level l (1..num_levels, index l-1 in the host arrays of device pointers) holds n*(1+k)^(num_levels-l)
- * targets = [targets of level l+1 ; their neighbours]: ids int64, t64 float64 query times, nbr / eid int64
- * [n_l, k], dt float32 [n_l, k] with the reference's dtype rules (TGAT.py:120-125).  Root ids must be
- * valid (the caller checks them on the host); times_are_f32 = roots carry float32 times (widened).   */
-int flid_train_sample_levels(const flid_graph* g, const int64_t* roots, const double* times, int times_are_f32,
-                             int64_t n, int k, int num_levels, int64_t* const* ids_host, double* const* t64_host,
-                             int64_t* const* nbr_host, int64_t* const* eid_host, float* const* dt_host,
-                             flid_stream stream);
+ * te0 [time_dim] = cos(time_b), the time encoding of the query (TGAT.py:90); its gradient comes back in d_te0.
+ * flid_train_saved[l-1]: caller-allocated tensors written by fwd and read by bwd, n = lv[l-1].n:
+ *   q, y, ln [n, qd]; merge_self, hid, out [n, node_dim]; u, z [n, H*kd]; probs [n, H, k].
+ * The result is saved[num_layers-1].out.  pre_scratch: [lv[0].n, qd] floats.
+ * bwd: every member of flid_train_grads[l-1], d_te0 and d_node_feat (nullable: [rows, node_dim], the gradient of
+ * the layer-0 table, e.g. TGN's memories + raw features) are ACCUMULATED into (zero them first);
+ * scratch: flid_train_model_scratch_floats(...) floats.  Dropout (scores, modules.py:224, and residual_fc
+ * output, :235) is Philox4x32-10 keyed by seeds_host[l-1], regenerated in bwd.                              */
 typedef struct {
     const float *fold_q, *fold_o, *res_b, *ln_w, *ln_b, *fc1_w, *fc1_b, *fc2_w, *fc2_b, *time_w, *time_b;
 } flid_train_weights;
@@ -287,22 +285,30 @@ typedef struct {
     float *fold_q, *fold_o, *res_b, *ln_w, *ln_b, *fc1_w, *fc1_b, *fc2_w, *fc2_b, *time_w, *time_b;
 } flid_train_grads;
 typedef struct {
-    float *u, *probs, *z, *y, *ln, *hid;
+    float *q, *merge_self, *u, *probs, *z, *y, *ln, *hid, *out;
 } flid_train_saved;
-/* test hook: the residual_fc-output dropout bits of a layer call with this seed (uint8 [n, qd], 1 = kept) */
+typedef struct {
+    const int64_t *ids, *nbr, *eid;
+    const float* dt;
+    int64_t n;
+} flid_train_level;
+int flid_train_sample_levels(const flid_graph* g, const int64_t* roots, const double* times, int times_are_f32,
+                             int64_t n, int k, int num_levels, int64_t* const* ids_host, double* const* t64_host,
+                             int64_t* const* nbr_host, int64_t* const* eid_host, float* const* dt_host,
+                             flid_stream stream);
+int64_t flid_train_model_scratch_floats(int64_t n_roots, int k, int num_layers, int num_heads, int node_dim,
+                                        int edge_dim, int time_dim);
+int flid_train_model_fwd(const flid_train_weights* w, const flid_train_level* lv, const flid_train_saved* sv,
+                         const float* node_feat, const float* edge_feat, const float* te0, int num_layers, int k,
+                         int num_heads, int node_dim, int edge_dim, int time_dim, float p_drop,
+                         const uint64_t* seeds_host, float* pre_scratch, flid_stream stream);
+int flid_train_model_bwd(const flid_train_weights* w, const flid_train_level* lv, const flid_train_saved* sv,
+                         const float* node_feat, const float* edge_feat, int num_layers, int k, int num_heads,
+                         int node_dim, int edge_dim, int time_dim, float p_drop, const uint64_t* seeds_host,
+                         const float* d_out, const flid_train_grads* grads, float* d_te0, float* d_node_feat,
+                         float* scratch, flid_stream stream);
+/* test hook: the residual_fc-output dropout bits of a layer evaluated with this seed (uint8 [n, qd], 1 = kept) */
 int flid_train_layer_out_keep_mask(uint64_t seed, int64_t n, int qd, float p_drop, uint8_t* keep, flid_stream stream);
-int64_t flid_train_layer_scratch_floats(int64_t n, int k, int num_heads, int node_dim, int edge_dim, int time_dim);
-int flid_train_layer_fwd(const flid_train_weights* w, const float* q, const float* merge_self, const float* table,
-                         const int64_t* hrow, int64_t hrow_offset, const int64_t* nbr, const int64_t* eid,
-                         const float* dt, const float* edge_feat, int64_t n, int k, int num_heads, int node_dim,
-                         int edge_dim, int time_dim, float p_drop, uint64_t seed, const flid_train_saved* saved, float* pre_scratch,
-                         float* out, flid_stream stream);
-int flid_train_layer_bwd(const flid_train_weights* w, const float* q, const float* merge_self, const float* table,
-                         const int64_t* hrow, int64_t hrow_offset, const int64_t* nbr, const int64_t* eid,
-                         const float* dt, const float* edge_feat, int64_t n, int k, int num_heads, int node_dim,
-                         int edge_dim, int time_dim, float p_drop, uint64_t seed, const flid_train_saved* saved, const float* d_out,
-                         float* d_q, float* d_cat, float* d_table, const flid_train_grads* grads, float* scratch,
-                         flid_stream stream);
 
 #ifdef __cplusplus
 }
