@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(128) attn_train_bwd_kernel(AttnTrainArgs a, At
 #pragma unroll
                 for (int r = 0; r < MAX_TC; ++r) {
                     if (lane + 32 * r < a.T) {
-                        const float sn = -sinf(fmaf(dt, tw[r], tb[r])) * dte[r];  // d cos(arg) = -sin(arg) d arg
+                        const float sn = -sin_accurate(fmaf(dt, tw[r], tb[r])) * dte[r];  // d cos(arg) = -sin(arg) d arg
                         gw[r] = fmaf(sn, dt, gw[r]);
                         gb[r] += sn;
                     }

@@ -132,6 +132,35 @@ __device__ __forceinline__ float cos_slow(float x) {
 }
 __device__ __forceinline__ float cos_accurate(float x) { return fabsf(x) < COS_FAST_LIMIT ? cos_fast(x) : cos_slow(x); }
 
+// sin(x) with the same range reduction (the time-encoder gradient of the training path, attn_train.cu):
+// sin(x) = (-1)^k sin(x - k*pi), sin(r) = r * P(r^2) on |r| <= 1.75, degree-9 least-squares fit, abs. error 1.8e-7
+#define FLID_SIN_C1 -0.16666646301746368f
+#define FLID_SIN_C2 0.008332798257470131f
+#define FLID_SIN_C3 -0.0001979204243980348f
+#define FLID_SIN_C4 2.570016476965975e-06f
+__device__ __forceinline__ float sin_poly_signed(float rf, int n) {
+    const float r2 = rf * rf;
+    float p = fmaf(r2, FLID_SIN_C4, FLID_SIN_C3);
+    p = fmaf(p, r2, FLID_SIN_C2);
+    p = fmaf(p, r2, FLID_SIN_C1);
+    p = fmaf(p * r2, rf, rf);
+    return __int_as_float(__float_as_int(p) ^ (n << 31));
+}
+__device__ __forceinline__ float sin_accurate(float x) {
+    if (fabsf(x) < COS_FAST_LIMIT) {
+        const float t = fmaf(x, 0.31830987334251404f, 12582912.0f);
+        const float kf = t - 12582912.0f;
+        float rf = fmaf(kf, -3.1415927410125732f, x);
+        rf = fmaf(kf, 8.742277657347586e-08f, rf);
+        return sin_poly_signed(rf, __float_as_int(t));
+    }
+    const double xd = (double)x;
+    const double q = rint(xd * 0.31830988618379067154);
+    double r = fma(q, -3.14159265358979311600, xd);
+    r = fma(q, -1.2246467991473532072e-16, r);
+    return sin_poly_signed((float)r, (int)q);
+}
+
 // TimeEncoder (models/modules.py:35-38): cos of the single-rounded fma(dt, w, b).
 __device__ __forceinline__ float time_channel(float dt, float w, float b) { return cos_accurate(fmaf(dt, w, b)); }
 #endif  // __CUDACC__
