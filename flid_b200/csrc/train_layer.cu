@@ -13,6 +13,8 @@
 // query / key / value_projection and residual_fc.  Forward and data-gradient products run on the
 // tcgen05 3xTF32 GEMM (gemm_tc.cu; the transposed weights are re-tiled per call); the
 // weight-gradient products (reduction over the n rows) on a split-row fp32 kernel below.
+#include <stdlib.h>
+
 #include "attn_train.cuh"
 #include "gemm_tc.cuh"
 #include "graph.cuh"
@@ -322,22 +324,37 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ Y,
     for (int i = 0; i < RI; ++i)
 #pragma unroll
         for (int j = 0; j < RJ; ++j) acc[i][j] = 0.f;
+    // register prefetch: the next row tile is in flight while this one is multiplied out of shared memory
+    constexpr int LY = WG_R * TI / 4 / 256, LX = WG_R * TJ / 4 / 256;
+    float4 py[LY], px[LX];
+    auto fetch = [&](int64_t m0) {
+#pragma unroll
+        for (int u = 0; u < LY; ++u) {
+            const int v = t + 256 * u, r = v / (TI / 4), c4 = (v % (TI / 4)) * 4;
+            py[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m0 + r < hi && i0 + c4 < NI) py[u] = __ldg(reinterpret_cast<const float4*>(Y + (m0 + r) * ldy + i0 + c4));
+        }
+#pragma unroll
+        for (int u = 0; u < LX; ++u) {
+            const int v = t + 256 * u, r = v / (TJ / 4), c4 = (v % (TJ / 4)) * 4;
+            px[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m0 + r < hi && j0 + c4 < NJ) px[u] = __ldg(reinterpret_cast<const float4*>(X + (m0 + r) * ldx + j0 + c4));
+        }
+    };
+    if (lo < hi) fetch(lo);
     for (int64_t m0 = lo; m0 < hi; m0 += WG_R) {
 #pragma unroll
-        for (int v = t; v < WG_R * TI / 4; v += 256) {
-            const int r = v / (TI / 4), c4 = (v % (TI / 4)) * 4;
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (m0 + r < hi && i0 + c4 < NI) a = __ldg(reinterpret_cast<const float4*>(Y + (m0 + r) * ldy + i0 + c4));
-            *reinterpret_cast<float4*>(&Ys[r][c4]) = a;
+        for (int u = 0; u < LY; ++u) {
+            const int v = t + 256 * u;
+            *reinterpret_cast<float4*>(&Ys[v / (TI / 4)][(v % (TI / 4)) * 4]) = py[u];
         }
 #pragma unroll
-        for (int v = t; v < WG_R * TJ / 4; v += 256) {
-            const int r = v / (TJ / 4), c4 = (v % (TJ / 4)) * 4;
-            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (m0 + r < hi && j0 + c4 < NJ) b = __ldg(reinterpret_cast<const float4*>(X + (m0 + r) * ldx + j0 + c4));
-            *reinterpret_cast<float4*>(&Xs[r][c4]) = b;
+        for (int u = 0; u < LX; ++u) {
+            const int v = t + 256 * u;
+            *reinterpret_cast<float4*>(&Xs[v / (TJ / 4)][(v % (TJ / 4)) * 4]) = px[u];
         }
         __syncthreads();
+        if (m0 + WG_R < hi) fetch(m0 + WG_R);
 #pragma unroll 4
         for (int r = 0; r < WG_R; ++r) {
             float av[RI], bv[RJ];
@@ -371,7 +388,14 @@ template <int RI, int RJ>
 int wgrad_launch(const float* Y, int64_t ldy, int NI, const float* X, int64_t ldx, int NJ, float* dW, int64_t ldw, int64_t n,
                  cudaStream_t st) {
     const int ti = (int)ceil_div(NI, 16 * RI), tj = (int)ceil_div(NJ, 16 * RJ);
-    int64_t slabs = ceil_div(4 * 148, (int64_t)ti * tj);
+    // target blocks per SM: measured 4 best at n ~ 8 800 rows (one B = 200 batch), 8 at n ~ 88 000; FLID_WGRAD_BLOCKS overrides
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("FLID_WGRAD_BLOCKS");
+        forced = (e && atoi(e) > 0) ? atoi(e) : 0;
+    }
+    const int per_sm = forced ? forced : (n >= 32768 ? 8 : 4);
+    int64_t slabs = ceil_div((int64_t)per_sm * 148, (int64_t)ti * tj);
     const int64_t max_slabs = ceil_div(n, 2 * WG_R);
     if (slabs > max_slabs) slabs = max_slabs;
     if (slabs < 1) slabs = 1;
