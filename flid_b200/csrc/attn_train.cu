@@ -384,6 +384,152 @@ __global__ void __launch_bounds__(128) attn_train_bwd_kernel(AttnTrainArgs a, At
     }
 }
 
+// Backward when no table gradient is wanted (TGAT layer 1: raw node features are constants) -- ONE pass over
+// the neighbour rows instead of two.  With S_h = sum_j a_hj da_hj the softmax backward ds_hj = a_hj (da_hj - S_h)
+// separates into sums that can be accumulated before S_h is known:
+//   du_h = sum_j (a_hj da_hj) x_j - S_h sum_j a_hj x_j
+//   d(w,b)_c = sum_j s_jc (dt_j, 1) sum_h (ad_hj dz_hc + a_hj da_hj u_hc)  -  sum_h S_h u_hc sum_j s_jc (dt_j, 1) a_hj
+// (s_jc = -sin(arg_jc); a target without neighbours has da = 0, masked slots have a = 0).
+template <int H, int NV>
+__global__ void __launch_bounds__(128) attn_train_bwd_onepass_kernel(AttnTrainArgs a, AttnTrainGrads g) {
+    __shared__ float red[4][2 * 32 * MAX_TC];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int k = a.k, nv4 = a.dn >> 2, tot4 = (a.dn + a.de) >> 2, row_w = a.dn + a.de, kd = row_w + a.T;
+    float gw[MAX_TC], gb[MAX_TC];
+#pragma unroll
+    for (int r = 0; r < MAX_TC; ++r) gw[r] = gb[r] = 0.f;
+
+    if (i < a.n) {
+        int64_t hrow_l = 0;
+        int e_l = 0;
+        float dt_l = 0.f;
+        bool masked_l = true;
+        if (lane < k) {
+            hrow_l = a.hrow ? __ldg(a.hrow + i * k + lane) : a.hrow_offset + i * k + lane;
+            e_l = (int)__ldg(a.eid + i * k + lane);
+            dt_l = __ldg(a.dt + i * k + lane);
+            masked_l = __ldg(a.nbr + i * k + lane) == 0;
+        }
+        const unsigned in_k = (k >= 32) ? FULL : ((1u << k) - 1u);
+        const unsigned valid = __ballot_sync(FULL, !masked_l) & in_k;
+        const bool all_masked = valid == 0u;
+        float tw[MAX_TC], tb[MAX_TC];
+#pragma unroll
+        for (int r = 0; r < MAX_TC; ++r) {
+            const int c = lane + 32 * r;
+            tw[r] = c < a.T ? __ldg(a.time_w + c) : 0.f;
+            tb[r] = c < a.T ? __ldg(a.time_b + c) : 0.f;
+        }
+        float4 dzx[H][NV], px[H][NV], qx[H][NV];
+        float dzt[H][MAX_TC], pt[H][MAX_TC], qt[H][MAX_TC], ut[H][MAX_TC], rw[H][MAX_TC], rb[H][MAX_TC];
+        load_vec<H, NV>(g.dz + i * (int64_t)(H * kd), lane, nv4, tot4, a.T, kd, row_w, dzx, dzt);
+        const float* u = a.u + i * (int64_t)(H * kd);
+        float S[H], prob[H];
+        const unsigned thr = drop_threshold(a.p_drop);
+        const float keep_scale = 1.0f / (1.0f - a.p_drop);
+        const unsigned kb = (lane < k) ? keep_bits(a.seed, i, lane, H, thr) : 0u;
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            S[h] = 0.f;
+            prob[h] = lane < k ? __ldg(g.probs + (i * H + h) * k + lane) : 0.f;
+#pragma unroll
+            for (int r = 0; r < NV; ++r) px[h][r] = qx[h][r] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int r = 0; r < MAX_TC; ++r) {
+                const int c = lane + 32 * r;
+                pt[h][r] = qt[h][r] = rw[h][r] = rb[h][r] = 0.f;
+                ut[h][r] = c < a.T ? __ldg(u + h * kd + row_w + c) : 0.f;
+            }
+        }
+        for (unsigned todo = all_masked ? in_k : valid; todo; todo &= todo - 1) {
+            const int j = __ffs(todo) - 1;
+            const float dt = __shfl_sync(FULL, dt_l, j);
+            const unsigned kbj = __shfl_sync(FULL, kb, j);
+            float4 x[NV];
+            float te[MAX_TC];
+            load_row<NV>(a, lane, __shfl_sync(FULL, hrow_l, j), __shfl_sync(FULL, e_l, j), dt, nv4, tot4, tw, tb, x, te);
+            float e[MAX_TC];
+#pragma unroll
+            for (int r = 0; r < MAX_TC; ++r) e[r] = 0.f;
+            float ah[H];
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                float d = 0.f;
+#pragma unroll
+                for (int r = 0; r < NV; ++r) d = dot4(x[r], dzx[h][r], d);
+#pragma unroll
+                for (int r = 0; r < MAX_TC; ++r) d = fmaf(te[r], dzt[h][r], d);
+                d = warp_sum(d);
+                const bool kept = (kbj >> h) & 1u;
+                const float av = __shfl_sync(FULL, prob[h], j);
+                const float da = (kept && !all_masked) ? d * keep_scale : 0.f;
+                const float ad = kept ? av * keep_scale : 0.f;
+                const float c1 = av * da;
+                ah[h] = av;
+                S[h] += c1;
+#pragma unroll
+                for (int r = 0; r < NV; ++r) {
+                    axpy4(c1, x[r], px[h][r]);
+                    axpy4(av, x[r], qx[h][r]);
+                }
+#pragma unroll
+                for (int r = 0; r < MAX_TC; ++r) {
+                    pt[h][r] = fmaf(c1, te[r], pt[h][r]);
+                    qt[h][r] = fmaf(av, te[r], qt[h][r]);
+                    e[r] = fmaf(ad, dzt[h][r], fmaf(c1, ut[h][r], e[r]));
+                }
+            }
+            if (g.dtime_partial) {
+#pragma unroll
+                for (int r = 0; r < MAX_TC; ++r) {
+                    if (lane + 32 * r < a.T) {
+                        const float sn = -sin_accurate(fmaf(dt, tw[r], tb[r]));
+                        gw[r] = fmaf(sn * dt, e[r], gw[r]);
+                        gb[r] = fmaf(sn, e[r], gb[r]);
+#pragma unroll
+                        for (int h = 0; h < H; ++h) {
+                            rw[h][r] = fmaf(sn * dt, ah[h], rw[h][r]);
+                            rb[h][r] = fmaf(sn, ah[h], rb[h][r]);
+                        }
+                    }
+                }
+            }
+        }
+        // du = P - S Q ; a target without neighbours passes no score gradient
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            const float s = all_masked ? 0.f : S[h];
+#pragma unroll
+            for (int r = 0; r < NV; ++r) {
+                px[h][r].x = all_masked ? 0.f : fmaf(-s, qx[h][r].x, px[h][r].x);
+                px[h][r].y = all_masked ? 0.f : fmaf(-s, qx[h][r].y, px[h][r].y);
+                px[h][r].z = all_masked ? 0.f : fmaf(-s, qx[h][r].z, px[h][r].z);
+                px[h][r].w = all_masked ? 0.f : fmaf(-s, qx[h][r].w, px[h][r].w);
+            }
+#pragma unroll
+            for (int r = 0; r < MAX_TC; ++r) {
+                pt[h][r] = all_masked ? 0.f : fmaf(-s, qt[h][r], pt[h][r]);
+                gw[r] = fmaf(-s * ut[h][r], rw[h][r], gw[r]);
+                gb[r] = fmaf(-s * ut[h][r], rb[h][r], gb[r]);
+            }
+        }
+        store_vec<H, NV>(g.du + i * (int64_t)(H * kd), lane, tot4, a.T, kd, row_w, px, pt);
+    }
+    if (g.dtime_partial) {
+#pragma unroll
+        for (int r = 0; r < MAX_TC; ++r) {
+            red[warp][lane + 32 * r] = gw[r];
+            red[warp][32 * MAX_TC + lane + 32 * r] = gb[r];
+        }
+        __syncthreads();
+        for (int c = threadIdx.x; c < 2 * a.T; c += blockDim.x) {
+            const int q = (c < a.T) ? c : 32 * MAX_TC + (c - a.T);
+            g.dtime_partial[(int64_t)blockIdx.x * 2 * a.T + c] = red[0][q] + red[1][q] + red[2][q] + red[3][q];
+        }
+    }
+}
+
 __global__ void keep_mask_kernel(uint64_t seed, int64_t n, int H, int k, float p, uint8_t* keep) {
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= n * k) return;
@@ -434,7 +580,10 @@ int launch_attn_train_fwd(const AttnTrainArgs& a, int H, cudaStream_t st) {
 int launch_attn_train_bwd(const AttnTrainArgs& a, const AttnTrainGrads& g, int H, cudaStream_t st) {
     FLID_TRY(check_args(a, H));
     if (a.n == 0) return FLID_OK;
-    FLID_TRAIN_DISPATCH(attn_train_bwd_kernel, a, g);
+    if (g.dtable == nullptr)
+        FLID_TRAIN_DISPATCH(attn_train_bwd_onepass_kernel, a, g);
+    else
+        FLID_TRAIN_DISPATCH(attn_train_bwd_kernel, a, g);
     return FLID_OK;
 }
 

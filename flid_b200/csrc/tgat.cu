@@ -616,6 +616,8 @@ int flid_tgat_create(int node_dim, int edge_dim, int time_dim, int num_layers, i
     m->self_from_memo = !(sm && sm[0] == '0');
     const char* so = getenv("FLID_SORT_QUERIES");
     m->sort_bulk_queries = !(so && so[0] == '0');
+    if (const char* ct = getenv("FLID_CHUNK_TARGETS"))   // development knob, same as flid_tgat_set_chunk_targets
+        if (atoll(ct) >= 1024) m->max_l1_targets = atoll(ct);
     *out = m;
     return FLID_OK;
 }
