@@ -30,7 +30,10 @@ struct flid_tgat {
     int64_t table_rows = 0;
     flid::DevBuf table;
     // workspace
-    int64_t max_l1_targets = 75776;  // 148 SMs x 512: every 128-row GEMM tile round and every 4-target attention block round is full
+    // 148 SMs x 4096: every 128-row GEMM tile round and every 4-target attention block round is full, and the launch /
+    // tail cost of a level is paid once per 0.6 M targets (measured per Reddit-shape pass: 75 776 -> 33.0 ms, 151 552 -> 31.4,
+    // 303 104 -> 30.6, 606 208 -> 30.2, 1 363 968 -> 29.9; smaller is worse: 37 888 -> 36.0).  ~7 GB of workspace at L = 2.
+    int64_t max_l1_targets = 606208;
     bool sort_bulk_queries = true;  // bulk memoised calls evaluate their roots in (node, time) order (FLID_SORT_QUERIES=0 disables)
     bool self_from_memo = true;  // roots that are graph events read their own lower layers from the memo (FLID_SELF_MEMO=0 disables)
     flid::DevBuf ws_ids, ws_times, ws_nbr, ws_eid, ws_dt, ws_h, ws_u, ws_z, ws_o, ws_a, ws_hd, ws_misc, ws_pos, ws_self, ws_sort;

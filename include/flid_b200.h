@@ -155,7 +155,7 @@ int flid_tgat_embed_memo(flid_tgat* m, const flid_graph* g, const float* node_fe
  * this switch exists for tests and A/B timing.                                            */
 int flid_tgat_set_self_from_memo(flid_tgat* m, int enable);
 /* upper bound on layer-1 targets processed per internal chunk (workspace ~7 KB per target;
- * default 75776 = 148 x 512).  Results do not depend on it.                                     */
+ * default 606208 = 148 x 4096).  Results do not depend on it.                                   */
 int flid_tgat_set_chunk_targets(flid_tgat* m, int64_t max_layer1_targets);
 /* Per-kernel-class CUDA-event timing of flid_tgat_embed (events recorded on the launch
  * stream around each launch group).  Classes: 0 level sampler, 1 query-fold GEMM,

@@ -245,7 +245,7 @@ def test_tgat_chunking_and_table_do_not_change_bits():
         h = m._engine.handles[2]
         _lib.check(_lib.lib().flid_tgat_set_chunk_targets(h, 21 * 37))
         a1, b1 = m.compute_src_dst_node_temporal_embeddings(*args)
-        _lib.check(_lib.lib().flid_tgat_set_chunk_targets(h, 75776))
+        _lib.check(_lib.lib().flid_tgat_set_chunk_targets(h, 606208))
         a2 = torch.cat([m.compute_src_dst_node_temporal_embeddings(args[0][i:i + 125], args[1][i:i + 125],
                                                                      args[2][i:i + 125], 20)[0]
                         for i in range(0, 500, 125)])
