@@ -244,9 +244,11 @@ def run_ours(args, rank, world, local_rank):
         if not use_memo:
             return
         model._engine.memo.clear()
+        model._engine.build_stats = [0, 0, 0] if collect else None     # summed over the pieces of a sharded build
         model.build_layer_memo(K_NBR, sharded=world > 1)
         if collect:
-            pass_stats["build"] = model.last_stats()
+            pass_stats["build"] = tuple(model._engine.build_stats)
+            model._engine.build_stats = None
 
     def step_device(store_prev, collect=False):
         with torch.no_grad():

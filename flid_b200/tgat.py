@@ -82,6 +82,7 @@ class _Engine:
         self.memo = {}       # depth -> (key, [level tables])   layer memo of bulk passes
         self.memo_mode = "auto"   # False | True | "auto"
         self.memo_builds = 0      # how many times a memo was (re)built (diagnostics)
+        self.build_stats = None   # set to [0, 0, 0] to accumulate (evaluations, valid slots, queries) over memo builds
         self.served = {}     # depth -> (key, root queries answered without a memo)
 
     def close(self):
@@ -172,18 +173,34 @@ def build_layer_memo(engine, depth, time_encoder, conv_layers, merge_layers, sam
         if sharded:
             import torch.distributed as dist
             rank, world = dist.get_rank(), dist.get_world_size()
-        per = -(-rows // world)
+        # Sharded build, pipelined with its exchange: the table is cut into `pieces` super-blocks of world * per rows;
+        # inside each, rank r builds rows [r * per, (r + 1) * per) and the super-block is all-gathered in place
+        # (asynchronously, on NCCL's stream) while the next piece is being built.
+        pieces = 2 if world > 1 else 1
+        per = -(-rows // (world * pieces))
         dn = node_feat.shape[1]
         tables = []
         prev = None
         for level in range(1, depth):
-            t = torch.empty((per * world, dn), dtype=torch.float32, device=device)
-            lo, hi = min(rank * per, rows), min((rank + 1) * per, rows)
-            _lib.check(lib.flid_tgat_memo_build(h, sampler.handle, _lib.ptr(node_feat), _lib.ptr(edge_feat),
-                                                int(num_neighbors), level, _lib.ptr(prev), lo, hi, _lib.ptr(t),
-                                                _lib.stream()))
-            if world > 1:
-                dist.all_gather_into_tensor(t, t[rank * per:(rank + 1) * per])     # in place
+            t = torch.empty((per * world * pieces, dn), dtype=torch.float32, device=device)
+            pending = []
+            for piece in range(pieces):
+                base = piece * per * world
+                lo, hi = min(base + rank * per, rows), min(base + (rank + 1) * per, rows)
+                if hi > lo:
+                    _lib.check(lib.flid_tgat_memo_build(h, sampler.handle, _lib.ptr(node_feat), _lib.ptr(edge_feat),
+                                                        int(num_neighbors), level, _lib.ptr(prev), lo, hi, _lib.ptr(t),
+                                                        _lib.stream()))
+                    if engine.build_stats is not None:      # measurement runs only: reading the counters synchronises
+                        st = (C.c_int64 * 4)()
+                        _lib.check(lib.flid_tgat_last_stats(h, st))
+                        engine.build_stats = [a + int(b) for a, b in zip(engine.build_stats, st[:3])]
+                if world > 1:
+                    block = t[base:base + per * world]
+                    pending.append(dist.all_gather_into_tensor(block, block[rank * per:(rank + 1) * per],
+                                                               async_op=True))     # in place
+            for work in pending:
+                work.wait()
             tables.append(t)
             prev = t
         engine.memo[depth] = (key, tables)
