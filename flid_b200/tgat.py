@@ -151,6 +151,19 @@ def _memo_key(engine, depth, sampler, node_feat, edge_feat, k):
             edge_feat.data_ptr(), edge_feat._version, int(k))
 
 
+def memo_piece_bounds(rows, rank, world, pieces):
+    """Row ranges of the sharded memo build.  The table (``per * world * pieces`` rows, ``per`` =
+    ceil(rows / (world * pieces))) is cut into ``pieces`` super-blocks of ``world * per`` rows; inside
+    super-block p rank r owns rows [p*world*per + r*per, ... + per), clipped to ``rows``.
+    Returns (per, [(block_start, lo, hi), ...])."""
+    per = -(-rows // (world * pieces))
+    out = []
+    for piece in range(pieces):
+        base = piece * per * world
+        out.append((base, min(base + rank * per, rows), min(base + (rank + 1) * per, rows)))
+    return per, out
+
+
 def build_layer_memo(engine, depth, time_encoder, conv_layers, merge_layers, sampler, node_feat, edge_feat,
                      num_neighbors, sharded=False):
     """Fill the layer memo (include/flid_b200.h, flid_tgat_memo_build) for levels 1..depth-1.
@@ -177,16 +190,14 @@ def build_layer_memo(engine, depth, time_encoder, conv_layers, merge_layers, sam
         # inside each, rank r builds rows [r * per, (r + 1) * per) and the super-block is all-gathered in place
         # (asynchronously, on NCCL's stream) while the next piece is being built.
         pieces = 2 if world > 1 else 1
-        per = -(-rows // (world * pieces))
+        per, bounds = memo_piece_bounds(rows, rank, world, pieces)
         dn = node_feat.shape[1]
         tables = []
         prev = None
         for level in range(1, depth):
             t = torch.empty((per * world * pieces, dn), dtype=torch.float32, device=device)
             pending = []
-            for piece in range(pieces):
-                base = piece * per * world
-                lo, hi = min(base + rank * per, rows), min(base + (rank + 1) * per, rows)
+            for base, lo, hi in bounds:
                 if hi > lo:
                     _lib.check(lib.flid_tgat_memo_build(h, sampler.handle, _lib.ptr(node_feat), _lib.ptr(edge_feat),
                                                         int(num_neighbors), level, _lib.ptr(prev), lo, hi, _lib.ptr(t),

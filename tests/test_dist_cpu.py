@@ -75,3 +75,21 @@ def test_shard_bounds_properties():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             assert all(hi - lo <= per for lo, hi, per in spans)
             assert len({per for _, _, per in spans}) == 1
+
+
+def test_memo_piece_bounds_cover_every_row_once():
+    """Sharded memo build: the (rank, piece) row ranges tile [0, rows) exactly and every super-block is one
+    contiguous all-gather output whose r-th slice is rank r's range."""
+    from flid_b200.tgat import memo_piece_bounds
+    for rows in (1, 7, 1000, 1344895):
+        for world in (1, 2, 3, 8):
+            for pieces in (1, 2, 3):
+                seen = np.zeros(rows, dtype=np.int32)
+                for rank in range(world):
+                    per, bounds = memo_piece_bounds(rows, rank, world, pieces)
+                    assert per * world * pieces >= rows and len(bounds) == pieces
+                    for p, (base, lo, hi) in enumerate(bounds):
+                        assert base == p * per * world
+                        assert lo == min(base + rank * per, rows) and hi - lo <= per
+                        seen[lo:hi] += 1
+                assert (seen == 1).all(), (rows, world, pieces)
