@@ -23,6 +23,8 @@ Restated, in the reference's literal order, with its dict-of-lists message store
 """
 from collections import defaultdict
 
+import contextlib
+
 import numpy as np
 import torch
 import torch.nn.functional as F
@@ -107,22 +109,25 @@ class OracleTGN:
         idx = torch.from_numpy(ids)
         tf = torch.from_numpy(ts).float()
         assert (self.last_upd[idx] <= tf).all().item(), "Trying to update memory to time in the past!"
-        self.mem[idx] = self._gru(ms, self.mem[idx])
+        self.mem[idx] = self._gru(ms, self.mem[idx]).detach()
         self.last_upd[idx] = tf
 
     def new_raw_messages(self, a_ids, b_ids, times, eids):
         a, b = torch.from_numpy(a_ids), torch.from_numpy(b_ids)
         dt = torch.from_numpy(times).float() - self.last_upd[a]
         te = otgat.time_encode(self.p, dt.unsqueeze(1)).reshape(len(a_ids), -1)
-        rows = torch.cat([self.mem[a], self.mem[b], te, self.edge_feat[torch.from_numpy(eids)]], dim=1)
+        rows = torch.cat([self.mem[a], self.mem[b], te, self.edge_feat[torch.from_numpy(eids)]], dim=1).detach()
         out = defaultdict(list)
         for i in range(len(a_ids)):
             out[int(a_ids[i])].append((rows[i], times[i]))
         return np.unique(a_ids), out
 
     # -- the call -------------------------------------------------------------
-    def step(self, src, dst, times, eids, positive=True):
-        with torch.no_grad():
+    def step(self, src, dst, times, eids, positive=True, grad=False):
+        """``grad=True``: the embeddings keep their autograd graph (training-mode parity tests; the parameters
+        must then be leaf tensors).  The state written back is detached either way, as the reference's is after
+        ``detach_memory_bank`` (models/MemoryModel.py:440-445)."""
+        with (contextlib.nullcontext() if grad else torch.no_grad()):
             node_ids = np.concatenate([src, dst])
             mem2, _ = self.get_updated_memories()
             emb = otgat.embed(self.p, self.node_feat, self.edge_feat, self.sampler, node_ids,

@@ -583,6 +583,50 @@ def test_tgn_training_mode_matches_eval_kernels_and_finite_differences():
         assert abs(fd - an) <= 3e-2 * max(1.0, abs(an)), (name, fd, an)
 
 
+@pytest.mark.parametrize("L,k", [(1, 5), (2, 4)])
+def test_tgn_training_gradients_match_oracle_autograd(L, k):
+    """Training-mode TGN batch after a few state-building batches: embeddings and EVERY parameter gradient
+    (GRU updater, time encoder, attention, merge) against the oracle's autograd on the same state."""
+    src, dst, eid, ts, nf, ef = cases.small_stream()
+    bs = 20
+    p = otgn.default_params(172, 172, 100, L, 2, seed=12, time_bias_scale=0.2)
+    s = make_sampler(src, dst, eid, ts, nf.shape[0] - 1)
+    m = flid_b200.MemoryModel(nf, ef, s, 100, "TGN", L, 2, 0.0, device=DEV).to(DEV)
+    missing = m.load_state_dict({kk: v for kk, v in p.items() if not kk.startswith("_")}, strict=False)
+    assert not missing.unexpected_keys
+    m.memory_bank.__init_memory_bank__()
+    m.train()
+    po = {kk: (v.clone().requires_grad_(True) if torch.is_tensor(v) and v.dtype.is_floating_point else v)
+          for kk, v in p.items()}
+    o = otgn.OracleTGN(po, torch.from_numpy(nf), torch.from_numpy(ef),
+                       osamp.OracleSampler.from_events(src, dst, eid, ts, nf.shape[0] - 1), L, k)
+    for bi in range(5):
+        sl = slice(300 + bi * bs, 300 + (bi + 1) * bs)
+        last = bi == 4
+        a, b = m.compute_src_dst_node_temporal_embeddings(src[sl], dst[sl], ts[sl], eid[sl], True, k)
+        oa, ob = o.step(src[sl], dst[sl], ts[sl], eid[sl], True, grad=last)
+        assert_fp32_close(a.detach().cpu().numpy(), oa.detach().numpy(), f"batch {bi} src")
+        assert_fp32_close(b.detach().cpu().numpy(), ob.detach().numpy(), f"batch {bi} dst")
+        if not last:
+            m.memory_bank.detach_memory_bank()
+    g = torch.Generator().manual_seed(4)
+    wa, wb = torch.randn(a.shape, generator=g), torch.randn(b.shape, generator=g)
+    ((a * wa.to(DEV)).sum() + (b * wb.to(DEV)).sum()).backward()
+    ((oa * wa).sum() + (ob * wb).sum()).backward()
+    checked = 0
+    for name, prm in m.named_parameters():
+        if name.startswith("memory_bank.") or name.startswith("memory_updater.memory_bank."):
+            continue                      # the bank is state, detached between batches (models/MemoryModel.py:440-445)
+        want = po[name].grad if name in po else None
+        if want is None:
+            continue
+        assert prm.grad is not None, name
+        rel = float((prm.grad.cpu() - want).norm()) / max(float(want.norm()), 1e-6)
+        assert rel <= 2e-3, (name, rel)
+        checked += 1
+    assert checked >= 2 + 11 * L + 4
+
+
 # ===================================================================== pseudo labels
 @pytest.mark.parametrize("C", [2, 5])
 def test_pseudo_label_golden(C):
