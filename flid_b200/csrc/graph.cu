@@ -288,6 +288,11 @@ static int build_common(const int64_t* a, const int64_t* b, const int64_t* eid, 
         flid_graph_free(g);
         return status;
     }
+    if (cudaMalloc(&g->bad_flag, sizeof(int)) != cudaSuccess || cudaMemsetAsync(g->bad_flag, 0, sizeof(int), st) != cudaSuccess) {
+        flid_graph_free(g);
+        set_error("flid_graph_build: cannot allocate the status flag");
+        return FLID_ERR_CUDA;
+    }
     *out = g;
     return FLID_OK;
 }
@@ -311,7 +316,7 @@ int flid_graph_build_entries(const int64_t* owner, const int64_t* nbr, const int
 
 void flid_graph_free(flid_graph* g) {
     if (!g) return;
-    cudaFree(g->indptr), cudaFree(g->adj), cudaFree(g->ts), cudaFree(g->mirror);
+    cudaFree(g->indptr), cudaFree(g->adj), cudaFree(g->ts), cudaFree(g->mirror), cudaFree(g->bad_flag);
     delete g;
 }
 

@@ -11,6 +11,7 @@ struct flid_graph {
     double* ts = nullptr;       // [M]
     int32_t* mirror = nullptr;  // [M] position of the same event's entry in the other endpoint's list
                                 // (graphs built from events with M < 2^31 only, else null)
+    int* bad_flag = nullptr;    // device int, zero between calls: out-of-range query ids of the sampler entry points
 };
 
 namespace flid {

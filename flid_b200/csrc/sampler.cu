@@ -71,12 +71,14 @@ __global__ void __launch_bounds__(256) sample_cut_kernel(const int64_t* __restri
     if (lane == 0) out_start[q] = start, out_cut[q] = cut;
 }
 
+// the graph's status flag is zero between calls: read it back (the host result arrays need the sync anyway) and
+// clear it again only on the error path -- no allocation, no memset per call
 static int check_bad(int* bad, cudaStream_t st, const char* who) {
     int h = 0;
     FLID_CUDA(cudaMemcpyAsync(&h, bad, sizeof(int), cudaMemcpyDeviceToHost, st));
     FLID_CUDA(cudaStreamSynchronize(st));
-    cudaFree(bad);
     if (h) {
+        cudaMemsetAsync(bad, 0, sizeof(int), st);
         set_error("%s: node id outside the graph", who);
         return FLID_ERR_RANGE;
     }
@@ -96,9 +98,7 @@ int flid_sample_recent(const flid_graph* g, const int64_t* nodes, const void* ti
     FLID_REQUIRE(n >= 0, "flid_sample_recent: negative n");
     if (n == 0) return FLID_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    int* bad = nullptr;
-    FLID_CUDA(cudaMalloc(&bad, sizeof(int)));
-    FLID_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), st));
+    int* bad = g->bad_flag;
     const unsigned blocks = (unsigned)ceil_div(n * 32, 256);
     if (times_are_f32)
         sample_recent_kernel<true><<<blocks, 256, 0, st>>>(g->indptr, g->adj, g->ts, g->num_nodes, nodes, times, n, k,
@@ -116,9 +116,7 @@ int flid_sample_cut(const flid_graph* g, const int64_t* nodes, const void* times
     FLID_REQUIRE(g != nullptr, "flid_sample_cut: null graph");
     if (n <= 0) return FLID_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    int* bad = nullptr;
-    FLID_CUDA(cudaMalloc(&bad, sizeof(int)));
-    FLID_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), st));
+    int* bad = g->bad_flag;
     const unsigned blocks = (unsigned)ceil_div(n * 32, 256);
     if (times_are_f32)
         sample_cut_kernel<true><<<blocks, 256, 0, st>>>(g->indptr, g->ts, g->num_nodes, nodes, times, n, out_start,

@@ -4,7 +4,8 @@
 
     python tests/golden/make_golden.py
 
-Outputs (committed): tests/golden/{sampler,tgat,tgn,pseudo}.npz
+Outputs (committed): tests/golden/{sampler,tgat,tgn,pseudo,graphmixer}.npz
+(``python tests/golden/make_golden.py graphmixer`` regenerates one file)
 """
 import os
 import sys
@@ -18,7 +19,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, HERE)
 
 import cases  # noqa: E402
-from oracle import ref_shim, tgat as otgat, tgn as otgn, pseudo as opseudo  # noqa: E402
+from oracle import ref_shim, tgat as otgat, tgn as otgn, pseudo as opseudo, graphmixer as omix  # noqa: E402
 
 torch.set_num_threads(4)
 ref = ref_shim.load()
@@ -133,6 +134,33 @@ def golden_tgn():
     np.savez_compressed(os.path.join(HERE, "tgn.npz"), **out)
 
 
+MIXER_CASES = [
+    # name, layers, k (= num_tokens), time_gap, bias, node_zeros, n_events
+    ("L2_k20_g2000", 2, 20, 2000, 0.0, False, 40),
+    ("L2_k5_g7", 2, 5, 7, 0.3, False, 40),
+    ("L1_k10_g50_zeros", 1, 10, 50, 0.2, True, 25),
+]
+
+
+def golden_graphmixer():
+    """GraphMixer (models/GraphMixer.py): SURVEY 8(f) rank 4, another consumer of the sampler."""
+    out = {}
+    for name, L, k, gap, bias, zeros, nev in MIXER_CASES:
+        src, dst, eid, ts, nf, ef = cases.small_stream(node_zeros=zeros)
+        s = ref_sampler(src, dst, eid, ts, nf.shape[0] - 1)
+        p = omix.default_params(172, 100, k, L, seed=5, time_bias_scale=bias)
+        m = ref.GraphMixer(nf, ef, s, time_feat_dim=100, num_tokens=k, num_layers=L, dropout=0.1, device="cpu")
+        m.load_state_dict(p)
+        m.eval()
+        sel = np.linspace(0, len(src) - 1, nev).astype(np.int64)       # includes nodes without any history
+        with torch.no_grad():
+            a, b = m.compute_src_dst_node_temporal_embeddings(src[sel], dst[sel], ts[sel], num_neighbors=k, time_gap=gap)
+        out[name + "_src"], out[name + "_dst"], out[name + "_sel"] = a.numpy(), b.numpy(), sel
+        out[name + "_checksum"] = cases.checksum(src, dst, ts, nf, *[v.numpy() for v in p.values()])
+        print("graphmixer", name, a.shape, float(a.abs().mean()))
+    np.savez_compressed(os.path.join(HERE, "graphmixer.npz"), **out)
+
+
 def golden_pseudo():
     out = {}
     rs = np.random.RandomState(21)
@@ -179,7 +207,8 @@ def golden_pseudo():
 
 
 if __name__ == "__main__":
-    golden_sampler()
-    golden_tgat()
-    golden_tgn()
-    golden_pseudo()
+    only = sys.argv[1:]
+    for name, fn in (("sampler", golden_sampler), ("tgat", golden_tgat), ("tgn", golden_tgn), ("pseudo", golden_pseudo),
+                     ("graphmixer", golden_graphmixer)):
+        if not only or name in only:
+            fn()

@@ -8,7 +8,7 @@ import pytest
 import torch
 
 import cases
-from oracle import sampler as osamp, tgat as otgat, tgn as otgn, pseudo as opseudo, ref_shim
+from oracle import sampler as osamp, tgat as otgat, tgn as otgn, pseudo as opseudo, graphmixer as omix, ref_shim
 
 G = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -179,6 +179,27 @@ def test_pseudo_golden(C):
         ps = glab.to(torch.float32).reshape(1, -1).clone()
         r = opseudo.update_pseudo_labels(g[f"C{C}_true"], g[f"C{C}_lt"], g[f"C{C}_it"], 400, ps, store, "ps", ut, 0.6, "entropy")
         assert np.array_equal(r.numpy(), g[f"C{C}_upd_ut{ut}"])
+
+
+# ---------------------------------------------------------------- GraphMixer
+MIXER_CASES = [("L2_k20_g2000", 2, 20, 2000, 0.0, False), ("L2_k5_g7", 2, 5, 7, 0.3, False),
+               ("L1_k10_g50_zeros", 1, 10, 50, 0.2, True)]
+
+
+@pytest.mark.parametrize("name,L,k,gap,bias,zeros", MIXER_CASES)
+def test_graphmixer_golden(name, L, k, gap, bias, zeros):
+    """GraphMixer restatement (oracle/graphmixer.py) against the live reference's outputs."""
+    g = load("graphmixer.npz")
+    src, dst, eid, ts, nf, ef = cases.small_stream(node_zeros=zeros)
+    p = omix.default_params(172, 100, k, L, seed=5, time_bias_scale=bias)
+    assert cases.checksum(src, dst, ts, nf, *[v.numpy() for v in p.values()]) == g[name + "_checksum"]
+    s = osamp.OracleSampler.from_events(src, dst, eid, ts, nf.shape[0] - 1)
+    sel = g[name + "_sel"]
+    with torch.no_grad():
+        a = omix.embed(p, torch.from_numpy(nf), s, src[sel], ts[sel], L, k, gap).numpy()
+        b = omix.embed(p, torch.from_numpy(nf), s, dst[sel], ts[sel], L, k, gap).numpy()
+    for got, want in ((a, g[name + "_src"]), (b, g[name + "_dst"])):
+        assert np.abs(got - want).max() <= 2e-6 * max(1.0, np.abs(want).max())
 
 
 # ---------------------------------------------------------------- live reference (build container only)
