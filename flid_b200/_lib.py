@@ -91,6 +91,8 @@ _SIGNATURES = {
     "flid_pseudo_label": (C.c_int, [C.POINTER(MlpWeights), c_void, C.c_int64, c_void, c_void, c_void, c_void]),
     "flid_entropy_filter": (C.c_int, [C.POINTER(c_void), C.c_int, C.c_int64, C.c_int, C.c_float, c_void, c_void]),
     "flid_prob_filter": (C.c_int, [c_void, C.c_int64, C.c_int, C.c_float, c_void, c_void]),
+    "flid_neighbor_mean": (C.c_int, [c_void, c_void, C.c_int, c_void, c_void, C.c_int, C.c_int64, C.c_int, C.c_int, c_void,
+                                     c_void]),
     "flid_attn_train_partials": (C.c_int64, [C.c_int64]),
     "flid_attn_train_fwd": (C.c_int, [c_void] * 9 + [C.c_int64] + [C.c_int] * 5 + [C.c_float, C.c_uint64, c_void,
                                                                                   c_void, c_void]),

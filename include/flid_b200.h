@@ -310,6 +310,15 @@ int flid_train_model_bwd(const flid_train_weights* w, const flid_train_level* lv
 /* test hook: the residual_fc-output dropout bits of a layer evaluated with this seed (uint8 [n, qd], 1 = kept) */
 int flid_train_layer_out_keep_mask(uint64_t seed, int64_t n, int qd, float p_drop, uint8_t* keep, flid_stream stream);
 
+/* ------------------------------------------------------------------ GraphMixer node encoder ---
+ * models/GraphMixer.py:119-146 (other consumers of the sampler): for n queries
+ * (nodes int64, times float64 or float32) the `time_gap` most recent neighbours before the query time,
+ * out[i] = mean_j(node_feat[nbr_j] * softmax_j({1 real, -1e10 padded})) (+ node_feat[nodes[i]] when
+ * add_self), float32 [n, node_dim].  Node ids must be valid (the caller checks them on the host).   */
+int flid_neighbor_mean(const flid_graph* g, const float* node_feat, int node_dim, const int64_t* nodes,
+                       const void* times, int times_are_f32, int64_t n, int time_gap, int add_self, float* out,
+                       flid_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

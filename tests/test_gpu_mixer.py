@@ -1,0 +1,109 @@
+"""GPU parity of the GraphMixer drop-in (flid_b200/graphmixer.py, csrc/mixer.cu) against the golden vectors
+minted from the live reference and against the CPU oracle (oracle/graphmixer.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+import flid_b200
+from flid_b200 import _lib
+from oracle import sampler as osamp, graphmixer as omix
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+DEV = "cuda:0"
+MIXER_CASES = [("L2_k20_g2000", 2, 20, 2000, 0.0, False), ("L2_k5_g7", 2, 5, 7, 0.3, False),
+               ("L1_k10_g50_zeros", 1, 10, 50, 0.2, True)]
+
+
+def close(got, want, what):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    scale = max(1.0, float(np.abs(want).max()))
+    err = float(np.abs(got - want).max())
+    assert err <= 1e-4 * scale, (what, err, scale)
+
+
+def build(nf, ef, src, dst, eid, ts, k, L, p, dropout=0.1):
+    s = flid_b200.NeighborSampler(None, "recent", seed=1, device=DEV, _events=(src, dst, eid, ts, nf.shape[0] - 1))
+    m = flid_b200.GraphMixer(nf, ef, s, 100, k, L, dropout=dropout, device=DEV).to(DEV)
+    m.load_state_dict(p)
+    return m, s
+
+
+@pytest.mark.parametrize("name,L,k,gap,bias,zeros", MIXER_CASES)
+def test_graphmixer_golden_and_oracle(name, L, k, gap, bias, zeros):
+    g = np.load(os.path.join(G, "graphmixer.npz"))
+    src, dst, eid, ts, nf, ef = cases.small_stream(node_zeros=zeros)
+    p = omix.default_params(172, 100, k, L, seed=5, time_bias_scale=bias)
+    m, _ = build(nf, ef, src, dst, eid, ts, k, L, p)
+    m.eval()
+    sel = g[name + "_sel"]
+    with torch.no_grad():
+        a, b = m.compute_src_dst_node_temporal_embeddings(src[sel], dst[sel], ts[sel], num_neighbors=k, time_gap=gap)
+    close(a.cpu().numpy(), g[name + "_src"], name + " src vs reference")
+    close(b.cpu().numpy(), g[name + "_dst"], name + " dst vs reference")
+    # all events, float32 times, chunked: against the oracle
+    o = osamp.OracleSampler.from_events(src, dst, eid, ts, nf.shape[0] - 1)
+    t32 = ts.astype(np.float32)
+    m.chunk_queries = 300
+    with torch.no_grad():
+        got = m.compute_node_temporal_embeddings(src, t32, k, gap)
+        want = omix.embed(p, torch.from_numpy(nf), o, src, t32, L, k, gap)
+    close(got.cpu().numpy(), want.numpy(), name + " float32 times vs oracle")
+
+
+@pytest.mark.parametrize("gap", [1, 5, 2000])
+def test_neighbor_mean_kernel_vs_numpy(gap):
+    src, dst, eid, ts, n = cases.adversarial_events()
+    rs = np.random.RandomState(3)
+    nf = rs.standard_normal((n + 1, 64)).astype(np.float32)
+    nf[0] = rs.standard_normal(64).astype(np.float32) * 0.1          # a non-zero padding row must be followed too
+    s = flid_b200.NeighborSampler(None, "recent", seed=1, device=DEV, _events=(src, dst, eid, ts, n))
+    o = osamp.OracleSampler.from_events(src, dst, eid, ts, n)
+    nodes, times = cases.adversarial_queries()
+    d_nf = torch.from_numpy(nf).to(DEV)
+    d_ids = torch.from_numpy(nodes).to(DEV)
+    d_t = torch.from_numpy(times).to(DEV)
+    out = torch.empty((len(nodes), 64), dtype=torch.float32, device=DEV)
+    _lib.check(_lib.lib().flid_neighbor_mean(s.handle, _lib.ptr(d_nf), 64, _lib.ptr(d_ids), _lib.ptr(d_t), 0, len(nodes),
+                                             gap, 1, _lib.ptr(out), _lib.stream()))
+    nbr, _, _ = o.get_historical_neighbors(nodes, times, gap)
+    feats = torch.from_numpy(nf)[torch.from_numpy(nbr)]
+    mask = torch.from_numpy((nbr > 0).astype(np.float32))
+    mask[mask == 0] = -1e10
+    want = torch.mean(feats * torch.softmax(mask, dim=1).unsqueeze(-1), dim=1) + torch.from_numpy(nf)[torch.from_numpy(nodes)]
+    close(out.cpu().numpy(), want.numpy(), f"neighbor mean gap={gap}")
+    assert (nbr > 0).sum(1).min() == 0 and (nbr > 0).sum(1).max() >= min(gap, 5)      # empty and full windows covered
+
+
+def test_graphmixer_training_gradients_and_api():
+    src, dst, eid, ts, nf, ef = cases.small_stream()
+    L, k, gap = 2, 6, 30
+    p = omix.default_params(172, 100, k, L, seed=9, time_bias_scale=0.1)
+    m, s = build(nf, ef, src, dst, eid, ts, k, L, p, dropout=0.0)
+    m.train()
+    sel = np.arange(100, 160)
+    a, b = m.compute_src_dst_node_temporal_embeddings(src[sel], dst[sel], ts[sel], k, gap)
+    assert a.requires_grad
+    w = torch.randn(a.shape, generator=torch.Generator().manual_seed(1))
+    ((a * w.to(DEV)).sum() + (b * w.to(DEV)).sum()).backward()
+    po = {kk: v.clone().requires_grad_(not kk.startswith("time_encoder")) for kk, v in p.items()}
+    o = osamp.OracleSampler.from_events(src, dst, eid, ts, nf.shape[0] - 1)
+    oa = omix.embed(po, torch.from_numpy(nf), o, src[sel], ts[sel], L, k, gap)
+    ob = omix.embed(po, torch.from_numpy(nf), o, dst[sel], ts[sel], L, k, gap)
+    ((oa * w).sum() + (ob * w).sum()).backward()
+    close(a.detach().cpu().numpy(), oa.detach().numpy(), "train-mode values")
+    for name, prm in m.named_parameters():
+        if name.startswith("time_encoder"):
+            assert not prm.requires_grad          # frozen in GraphMixer (models/GraphMixer.py:43-45)
+            continue
+        rel = float((prm.grad.cpu() - po[name].grad).norm()) / max(float(po[name].grad.norm()), 1e-6)
+        assert rel <= 2e-3, (name, rel)
+    assert set(m.state_dict().keys()) == set(p.keys())
+    with pytest.raises(AssertionError):
+        m.compute_node_temporal_embeddings(src[:4], ts[:4], 0)
+    with pytest.raises(IndexError):
+        m.compute_node_temporal_embeddings(np.array([10 ** 6]), np.array([5.0]), k)
+    m.set_neighbor_sampler(s)
