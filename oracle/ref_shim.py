@@ -76,6 +76,7 @@ def load():
     from models.TGAT import TGAT  # noqa: E402
     from models.MemoryModel import MemoryModel  # noqa: E402
     from models.GraphMixer import GraphMixer  # noqa: E402
+    from models.TCL import TCL  # noqa: E402
     from PTCL.utils import entropy_filter, prob_filter, update_pseudo_labels  # noqa: E402
 
     ns.Data = _Data
@@ -88,6 +89,7 @@ def load():
     ns.TGAT = TGAT
     ns.MemoryModel = MemoryModel
     ns.GraphMixer = GraphMixer
+    ns.TCL = TCL
     ns.entropy_filter = entropy_filter
     ns.prob_filter = prob_filter
     ns.update_pseudo_labels = update_pseudo_labels

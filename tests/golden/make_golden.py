@@ -4,7 +4,7 @@
 
     python tests/golden/make_golden.py
 
-Outputs (committed): tests/golden/{sampler,tgat,tgn,pseudo,graphmixer}.npz
+Outputs (committed): tests/golden/{sampler,tgat,tgn,pseudo,graphmixer,tcl}.npz
 (``python tests/golden/make_golden.py graphmixer`` regenerates one file)
 """
 import os
@@ -19,7 +19,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, HERE)
 
 import cases  # noqa: E402
-from oracle import ref_shim, tgat as otgat, tgn as otgn, pseudo as opseudo, graphmixer as omix  # noqa: E402
+from oracle import ref_shim, tgat as otgat, tgn as otgn, pseudo as opseudo, graphmixer as omix, tcl as otcl  # noqa: E402
 
 torch.set_num_threads(4)
 ref = ref_shim.load()
@@ -161,6 +161,33 @@ def golden_graphmixer():
     np.savez_compressed(os.path.join(HERE, "graphmixer.npz"), **out)
 
 
+TCL_CASES = [
+    # name, layers, k (num_depths = k + 1), bias, node_zeros, n_events
+    ("L2_k20", 2, 20, 0.0, False, 30),
+    ("L1_k6_bias", 1, 6, 0.3, False, 40),
+    ("L2_k4_zeros", 2, 4, 0.2, True, 25),
+]
+
+
+def golden_tcl():
+    """TCL (models/TCL.py): SURVEY 8(f) rank 4, another consumer of the sampler."""
+    out = {}
+    for name, L, k, bias, zeros, nev in TCL_CASES:
+        src, dst, eid, ts, nf, ef = cases.small_stream(node_zeros=zeros)
+        s = ref_sampler(src, dst, eid, ts, nf.shape[0] - 1)
+        p = otcl.default_params(172, 172, 100, L, k + 1, seed=6, time_bias_scale=bias)
+        m = ref.TCL(nf, ef, s, time_feat_dim=100, num_layers=L, num_heads=2, num_depths=k + 1, dropout=0.1, device="cpu")
+        m.load_state_dict(p)
+        m.eval()
+        sel = np.linspace(0, len(src) - 1, nev).astype(np.int64)
+        with torch.no_grad():
+            a, b = m.compute_src_dst_node_temporal_embeddings(src[sel], dst[sel], ts[sel], num_neighbors=k)
+        out[name + "_src"], out[name + "_dst"], out[name + "_sel"] = a.numpy(), b.numpy(), sel
+        out[name + "_checksum"] = cases.checksum(src, dst, ts, nf, ef, *[v.numpy() for v in p.values()])
+        print("tcl", name, a.shape, float(a.abs().mean()))
+    np.savez_compressed(os.path.join(HERE, "tcl.npz"), **out)
+
+
 def golden_pseudo():
     out = {}
     rs = np.random.RandomState(21)
@@ -209,6 +236,6 @@ def golden_pseudo():
 if __name__ == "__main__":
     only = sys.argv[1:]
     for name, fn in (("sampler", golden_sampler), ("tgat", golden_tgat), ("tgn", golden_tgn), ("pseudo", golden_pseudo),
-                     ("graphmixer", golden_graphmixer)):
+                     ("graphmixer", golden_graphmixer), ("tcl", golden_tcl)):
         if not only or name in only:
             fn()

@@ -9,7 +9,7 @@ import torch
 import cases
 import flid_b200
 from flid_b200 import _lib
-from oracle import sampler as osamp, graphmixer as omix
+from oracle import sampler as osamp, graphmixer as omix, tcl as otcl
 
 pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(__file__), "golden")
@@ -107,3 +107,37 @@ def test_graphmixer_training_gradients_and_api():
     with pytest.raises(IndexError):
         m.compute_node_temporal_embeddings(np.array([10 ** 6]), np.array([5.0]), k)
     m.set_neighbor_sampler(s)
+
+
+# ===================================================================== TCL
+TCL_CASES = [("L2_k20", 2, 20, 0.0, False), ("L1_k6_bias", 1, 6, 0.3, False), ("L2_k4_zeros", 2, 4, 0.2, True)]
+
+
+@pytest.mark.parametrize("name,L,k,bias,zeros", TCL_CASES)
+def test_tcl_golden_and_oracle(name, L, k, bias, zeros):
+    g = np.load(os.path.join(G, "tcl.npz"))
+    src, dst, eid, ts, nf, ef = cases.small_stream(node_zeros=zeros)
+    p = otcl.default_params(172, 172, 100, L, k + 1, seed=6, time_bias_scale=bias)
+    s = flid_b200.NeighborSampler(None, "recent", seed=1, device=DEV, _events=(src, dst, eid, ts, nf.shape[0] - 1))
+    m = flid_b200.TCL(nf, ef, s, 100, L, 2, k + 1, 0.1, DEV).to(DEV)
+    m.load_state_dict(p)
+    assert set(m.state_dict().keys()) == set(p.keys())
+    m.eval()
+    sel = g[name + "_sel"]
+    with torch.no_grad():
+        a, b = m.compute_src_dst_node_temporal_embeddings(src[sel], dst[sel], ts[sel], k)
+    close(a.cpu().numpy(), g[name + "_src"], name + " src vs reference")
+    close(b.cpu().numpy(), g[name + "_dst"], name + " dst vs reference")
+    # all events, float32 times, chunked: against the oracle
+    o = osamp.OracleSampler.from_events(src, dst, eid, ts, nf.shape[0] - 1)
+    t32 = ts.astype(np.float32)
+    m.chunk_events = 128
+    with torch.no_grad():
+        ga, gb = m.compute_src_dst_node_temporal_embeddings(src, dst, t32, k)
+        wa, wb = otcl.embed_src_dst(p, torch.from_numpy(nf), torch.from_numpy(ef), o, src, dst, t32, L, 2, k)
+    close(ga.cpu().numpy(), wa.numpy(), name + " float32 times src vs oracle")
+    close(gb.cpu().numpy(), wb.numpy(), name + " float32 times dst vs oracle")
+    with pytest.raises(AssertionError):
+        m.compute_src_dst_node_temporal_embeddings(src[:4], dst[:4], ts[:4], k + 1)     # num_depths mismatch (TCL.py:184)
+    with pytest.raises(IndexError):
+        m.compute_src_dst_node_temporal_embeddings(np.array([10 ** 6]), np.array([1]), np.array([5.0]), k)

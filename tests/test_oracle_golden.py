@@ -8,7 +8,7 @@ import pytest
 import torch
 
 import cases
-from oracle import sampler as osamp, tgat as otgat, tgn as otgn, pseudo as opseudo, graphmixer as omix, ref_shim
+from oracle import sampler as osamp, tgat as otgat, tgn as otgn, pseudo as opseudo, graphmixer as omix, tcl as otcl, ref_shim
 
 G = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -200,6 +200,25 @@ def test_graphmixer_golden(name, L, k, gap, bias, zeros):
         b = omix.embed(p, torch.from_numpy(nf), s, dst[sel], ts[sel], L, k, gap).numpy()
     for got, want in ((a, g[name + "_src"]), (b, g[name + "_dst"])):
         assert np.abs(got - want).max() <= 2e-6 * max(1.0, np.abs(want).max())
+
+
+# ---------------------------------------------------------------- TCL
+TCL_CASES = [("L2_k20", 2, 20, 0.0, False), ("L1_k6_bias", 1, 6, 0.3, False), ("L2_k4_zeros", 2, 4, 0.2, True)]
+
+
+@pytest.mark.parametrize("name,L,k,bias,zeros", TCL_CASES)
+def test_tcl_golden(name, L, k, bias, zeros):
+    """TCL restatement (oracle/tcl.py) against the live reference's outputs."""
+    g = load("tcl.npz")
+    src, dst, eid, ts, nf, ef = cases.small_stream(node_zeros=zeros)
+    p = otcl.default_params(172, 172, 100, L, k + 1, seed=6, time_bias_scale=bias)
+    assert cases.checksum(src, dst, ts, nf, ef, *[v.numpy() for v in p.values()]) == g[name + "_checksum"]
+    s = osamp.OracleSampler.from_events(src, dst, eid, ts, nf.shape[0] - 1)
+    sel = g[name + "_sel"]
+    with torch.no_grad():
+        a, b = otcl.embed_src_dst(p, torch.from_numpy(nf), torch.from_numpy(ef), s, src[sel], dst[sel], ts[sel], L, 2, k)
+    for got, want in ((a.numpy(), g[name + "_src"]), (b.numpy(), g[name + "_dst"])):
+        assert np.abs(got - want).max() <= 5e-6 * max(1.0, np.abs(want).max())
 
 
 # ---------------------------------------------------------------- live reference (build container only)
