@@ -181,3 +181,44 @@ def test_attn_stream_argument_checks():
         train.AttnStream.apply(u, tab, w, b, idx, idx, idx, z(4, 5, device=DEV), edge, 1.0, 0)
     with pytest.raises(TypeError):
         train.AttnStream.apply(u.double(), tab, w, b, idx, idx, idx, z(4, 5, device=DEV), edge, 0.0, 0)
+
+
+def test_m_step_then_e_step_round_trip():
+    """A miniature PTCL round the way the reference drives it (PTCL/M_step.py:196-325 then PTCL/E_step.py:305-352):
+    a few M-step epochs of nn.Sequential(backbone, decoder) on pseudo labels with Adam -- training-mode kernels,
+    dropout on -- must reduce the loss; the E-step pass that follows must see the new weights (memo rebuilt) and
+    agree with the per-batch eval calls."""
+    from flid_b200 import passes
+    src, dst, eid, ts, nf, ef = cases.small_stream()
+    rs = np.random.RandomState(0)
+    labels = (nf[src, 0] + 0.5 * ef[eid, 1] > 0).astype(np.int64)          # learnable from node + edge features
+    s = flid_b200.NeighborSampler(None, "recent", seed=1, device=DEV, _events=(src, dst, eid, ts, nf.shape[0] - 1))
+    torch.manual_seed(0)
+    backbone = flid_b200.TGAT(nf, ef, s, 100, 2, 2, 0.1, DEV).to(DEV)
+    decoder = flid_b200.MLPClassifier(172, 0.1, 2).to(DEV)
+    model = torch.nn.Sequential(backbone, decoder)
+    opt = torch.optim.Adam(model.parameters(), lr=2e-3)
+    loss_fn = torch.nn.CrossEntropyLoss()
+    bs, losses = 50, []
+    for epoch in range(4):
+        model.train()
+        tot = 0.0
+        for lo in range(100, 500, bs):
+            sl = slice(lo, lo + bs)
+            emb, _ = model[0].compute_src_dst_node_temporal_embeddings(src[sl], dst[sl], ts[sl], 10)
+            loss = loss_fn(model[1](emb), torch.from_numpy(labels[sl]).to(DEV))
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            tot += float(loss.detach())
+        losses.append(tot)
+    assert all(np.isfinite(losses)) and losses[-1] < 0.8 * losses[0], losses
+    model.eval()
+    pseudo, probs, emb = passes.e_step_pass(model[0], model[1], src, dst, ts, 10, [], "entropy", 0.9, return_embeddings=True)
+    with torch.no_grad():
+        a, _ = model[0].compute_src_dst_node_temporal_embeddings(src[200:260], dst[200:260], ts[200:260], 10)
+    scale = max(1.0, float(a.abs().max()))
+    assert float((emb[0][200:260] - a).abs().max()) <= 1e-5 * scale
+    assert pseudo.shape == (1, len(src)) and probs.shape == (len(src), 2)
+    acc = float((probs.argmax(1).cpu().numpy()[100:500] == labels[100:500]).mean())
+    assert acc > 0.6, acc
