@@ -8,7 +8,6 @@ sharded ("replicas only").
 import numpy as np
 import torch
 
-from . import _lib
 from .pseudo_label import MLPClassifier, emit_pseudo_labels, entropy_filter, prob_filter
 
 

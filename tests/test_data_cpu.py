@@ -1,5 +1,4 @@
 """Host-side loader of the reference's processed-dataset files (flid_b200/data.py)."""
-import os
 
 import numpy as np
 import pytest
