@@ -84,6 +84,10 @@ __global__ void roots_kernel(const int64_t* __restrict__ nodes, const double* __
 // kernels consume: int32 ids, float32 dt (with the reference's dtype rule: float64
 // subtraction for the first n_f64 targets, float32 below; models/TGAT.py:120-125), and
 // the next (lower) level's target list [self targets ; neighbour targets].
+// Two queries per warp (16 lanes each): a query needs one 16-way probe search (the same number of dependent
+// rounds as a 32-way one up to degree 256, one more beyond) and k = 20 output slots, so a full warp per query left
+// most lanes idle; halving the warps per query took the kernel from 1.25 to 0.82 ms per Reddit-shape pass.
+constexpr int LS_W = 16;
 __global__ void __launch_bounds__(256) level_sample_kernel(
     const int64_t* __restrict__ indptr, const int2* __restrict__ adj, const double* __restrict__ ts,
     const int32_t* __restrict__ ids, const double* __restrict__ times, int64_t n, int64_t n_f64, int k,
@@ -93,31 +97,55 @@ __global__ void __launch_bounds__(256) level_sample_kernel(
     __shared__ int s_cnt;
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int64_t q = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    if (q < n) {
-        const int32_t v = __ldg(ids + q);
-        const double t = __ldg(times + q);
-        const int64_t start = __ldg(indptr + v);
-        const int64_t cut = warp_lower_bound(ts, start, __ldg(indptr + v + 1), t, lane);
+    const int lane = threadIdx.x & 31, sub = lane & (LS_W - 1), shift = lane & LS_W;   // shift: 0 or 16
+    const int64_t q = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LS_W;
+    const bool active = q < n;
+    int32_t v = 0;
+    double t = 0.0;
+    int64_t start = 0, end = 0;
+    if (active) {
+        v = __ldg(ids + q);
+        t = __ldg(times + q);
+        start = __ldg(indptr + v);
+        end = __ldg(indptr + v + 1);
+    }
+    // searchsorted(ts[start:end), t, side='left') with 16 probes per round; both halves of the warp iterate together
+    int64_t lo = start, hi = end;
+    while (__any_sync(FULL, lo < hi)) {
+        const int64_t len = hi - lo;
+        const int64_t stride = (len + LS_W - 1) / LS_W;
+        const int64_t p = lo + (int64_t)sub * stride;
+        const bool before = (lo < hi) && (p < hi) && (__ldg(ts + p) < t);
+        const int c = __popc((__ballot_sync(FULL, before) >> shift) & 0xFFFFu);
+        if (lo < hi) {
+            if (c == 0) {
+                hi = lo;
+            } else {
+                const int64_t first_false = lo + (int64_t)c * stride;
+                lo = lo + (int64_t)(c - 1) * stride + 1;
+                hi = first_false < hi ? first_false : hi;
+            }
+        }
+    }
+    if (active) {
+        const int64_t cut = lo;
         const int64_t have = cut - start;
         const int cnt = have < (int64_t)k ? (int)have : k;
-        if (next_ids && lane == 0) next_ids[q] = v, next_times[q] = t;
-        if (self_pos && lane == 0) {
+        if (next_ids && sub == 0) next_ids[q] = v, next_times[q] = t;
+        if (self_pos && sub == 0) {
             // Is (v, t) itself an event of the graph at a float32-exact time?  Then the lower-layer
             // embeddings of this root are already in the layer memo: the row of the event's entry in
             // the other endpoint's list is h_l(v, float32(t)), and with float32(t) == t both the
             // neighbourhood (ts < t) and every float32 dt of the root (models/TGAT.py:120-125:
             // float64 subtraction rounded once == float32 subtraction of the same two values) coincide.
             int32_t sp = -1;
-            const int64_t end = __ldg(indptr + v + 1);
             if (cut < end && __ldg(ts + cut) == t && (double)(float)t == t) sp = __ldg(mirror + cut);
             self_pos[q] = sp;
             if (sp < 0) atomicAdd(valid_slots + 1, 1ull);  // misses
         }
         const bool f64_rule = q < n_f64;
         const float tf = (float)t;
-        for (int j = lane; j < k; j += 32) {
+        for (int j = sub; j < k; j += LS_W) {
             int a = 0, e = 0, pp = pad_pos;
             float tsf = 0.f;
             if (j >= k - cnt) {
@@ -131,7 +159,7 @@ __global__ void __launch_bounds__(256) level_sample_kernel(
             if (pos) pos[o] = pp;
             if (next_ids) next_ids[n + o] = a, next_times[n + o] = (double)tsf;
         }
-        if (lane == 0) atomicAdd(&s_cnt, cnt);
+        if (sub == 0) atomicAdd(&s_cnt, cnt);
     }
     __syncthreads();
     if (threadIdx.x == 0 && s_cnt) atomicAdd(valid_slots, (unsigned long long)s_cnt);
@@ -330,7 +358,7 @@ int tgat_embed_ids(flid_tgat* m, const flid_graph* g, const float* node_feat, co
         // top-down sampling
         for (int l = L; l >= 1; --l) {
             ProfScope prof(m, PROF_SAMPLE, st);
-            level_sample_kernel<<<(unsigned)ceil_div(c[l] * 32, 256), 256, 0, st>>>(
+            level_sample_kernel<<<(unsigned)ceil_div(c[l] * LS_W, 256), 256, 0, st>>>(
                 g->indptr, g->adj, g->ts, w_ids + o[l], w_times + o[l], c[l], nf, k, w_nbr + o[l] * k,
                 w_eid + o[l] * k, w_dt + o[l] * k, l > 1 ? w_ids + o[l - 1] : nullptr,
                 l > 1 ? w_times + o[l - 1] : nullptr, nullptr, 0, nullptr, nullptr, d_valid);
@@ -490,7 +518,7 @@ int tgat_memo_build(flid_tgat* m, const flid_graph* g, const float* node_feat, c
             memo_targets_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(g->adj, g->ts, M, c0, n, w_ids, w_times,
                                                                          owner_major ? g->mirror : nullptr, w_rows);
             FLID_LAUNCH_CHECK();
-            level_sample_kernel<<<(unsigned)ceil_div(n * 32, 256), 256, 0, st>>>(
+            level_sample_kernel<<<(unsigned)ceil_div(n * LS_W, 256), 256, 0, st>>>(
                 g->indptr, g->adj, g->ts, w_ids, w_times, n, 0, k, m->ws_nbr.as<int32_t>(), m->ws_eid.as<int32_t>(),
                 m->ws_dt.as<float>(), nullptr, nullptr, level > 1 ? m->ws_pos.as<int32_t>() : nullptr, (int32_t)M,
                 nullptr, nullptr, d_valid);
@@ -546,7 +574,7 @@ int tgat_embed_memo(flid_tgat* m, const flid_graph* g, const float* node_feat, c
         const int64_t nf = std::max<int64_t>(0, std::min(nc, n_f64 - r0));
         {
             ProfScope prof(m, PROF_SAMPLE, st);
-            level_sample_kernel<<<(unsigned)ceil_div(nc * 32, 256), 256, 0, st>>>(
+            level_sample_kernel<<<(unsigned)ceil_div(nc * LS_W, 256), 256, 0, st>>>(
                 g->indptr, g->adj, g->ts, ids + r0, times + r0, nc, nf, k, m->ws_nbr.as<int32_t>(),
                 m->ws_eid.as<int32_t>(), m->ws_dt.as<float>(), nullptr, nullptr,
                 L > 1 ? m->ws_pos.as<int32_t>() : nullptr, (int32_t)M, try_self ? g->mirror : nullptr,
