@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(TAIL_ROWS) pseudo_tail_kernel(flid_mlp_weights
     labels[i] = arg;
 }
 
-static TcWeight g_fc1;
+static TcWeight g_fc1_dev[32];   // tiled fc1 image, one per device ordinal
 static DevBuf g_h1;
 
 }  // namespace flid
@@ -232,6 +232,10 @@ int flid_pseudo_label(const flid_mlp_weights* w, const float* emb, int64_t n, fl
         return FLID_OK;
     }
     // weights may have changed since the last call: re-tile fc1 (a few KB) every time
+    int dev = 0;
+    FLID_CUDA(cudaGetDevice(&dev));
+    FLID_REQUIRE(dev >= 0 && dev < 32, "flid_pseudo_label: device ordinal %d not supported", dev);
+    TcWeight& g_fc1 = g_fc1_dev[dev];
     FLID_TRY(tc_prepare_weight(w->fc1_w, w->input_dim, w->hidden1, w->input_dim, &g_fc1, st));
     const int64_t chunk = 262144;
     FLID_TRY(g_h1.reserve(sizeof(float) * (size_t)std::min<int64_t>(chunk, n) * w->hidden1));

@@ -437,7 +437,14 @@ int gemm(const float* A0, int64_t lda0, int w0, const float* A1, int64_t lda1, i
 struct Images {
     TcWeight q, o, f1, f2;
 };
-Images g_fwd, g_bwd;
+// one set per device: the images live in that device's memory
+constexpr int MAX_DEVICES = 32;
+Images g_fwd_dev[MAX_DEVICES], g_bwd_dev[MAX_DEVICES];
+int current_device(int* dev) {
+    FLID_CUDA(cudaGetDevice(dev));
+    FLID_REQUIRE(*dev >= 0 && *dev < MAX_DEVICES, "train layer: device ordinal %d not supported", *dev);
+    return FLID_OK;
+}
 
 struct Dims {
     int64_t n;
@@ -495,6 +502,9 @@ static int layer_fwd(const flid_train_weights* w, const float* q, const float* m
                      float* pre_scratch, float* out, cudaStream_t st) {
     const int64_t n = d.n;
     const int k = d.k, num_heads = d.H;
+    int dev = 0;
+    FLID_TRY(current_device(&dev));
+    Images& g_fwd = g_fwd_dev[dev];
     FLID_TRY(tc_prepare_weight(w->fold_q, d.qd, d.zw, d.qd, &g_fwd.q, st));
     FLID_TRY(tc_prepare_weight(w->fold_o, d.zw, d.qd, d.zw, &g_fwd.o, st));
     FLID_TRY(tc_prepare_weight(w->fc1_w, d.qd + d.dn, d.dn, d.qd + d.dn, &g_fwd.f1, st));
@@ -522,6 +532,9 @@ static int layer_bwd(const flid_train_weights* w, const float* q, const float* m
                      float* scratch, cudaStream_t st) {
     const int64_t n = d.n;
     const int k = d.k, num_heads = d.H;
+    int dev = 0;
+    FLID_TRY(current_device(&dev));
+    Images& g_bwd = g_bwd_dev[dev];
     float* d_hid = scratch;
     float* d_pre = d_hid + n * d.dn;
     float* dz = d_pre + n * d.qd;

@@ -13,6 +13,9 @@
  *   - pointers are DEVICE pointers unless the parameter name ends in _host.
  *   - `stream` is a cudaStream_t passed as void*; work is enqueued, not synchronised,
  *     unless stated.  Handles are thread-compatible, not thread-safe.
+ *   - one CUDA device per process (the torchrun layout: one rank per GPU): handles and the
+ *     library's internal scratch buffers belong to the device that was current when they
+ *     were first used.
  *   - ids are int64 at the boundary (numpy's default, as the reference passes them)
  *     and int32 internally; node id 0 / edge id 0 are the padding rows.
  */
