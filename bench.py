@@ -356,7 +356,7 @@ def run_ours(args, rank, world, local_rank):
                      "+ ln_kernel", "achieved": useful_tf, "executed_tf32": 3.0 * useful_tf, "peak": tpeak, "unit": "TFLOP/s",
                      "frac": useful_tf / tpeak, "peak_source": tpeak_src,
                      "note": "fp32-equivalent useful FLOPs against the measured bf16 peak; the kernel is L2->SM bandwidth "
-                             "bound (DESIGN.md section 4), tensor pipe ~37 % busy"}
+                             "bound (DESIGN.md section 4), tensor pipe 29-65 % busy by shape (profiles/r1_final_kernels_chunk606k.txt)"}
         cores = os.cpu_count() or 1
         cpu_base = None
         if world == 1:     # reported on rank 0 at N = 1 only (torchrun pins OMP to one thread per rank)
