@@ -89,10 +89,10 @@ extern "C" int flid_neighbor_mean(const flid_graph* g, const float* node_feat, i
                                   const void* times, int times_are_f32, int64_t n, int time_gap, int add_self, float* out,
                                   flid_stream stream) {
     using namespace flid;
+    if (n <= 0) return FLID_OK;
     FLID_REQUIRE(g && node_feat && nodes && times && out, "flid_neighbor_mean: null argument");
     FLID_REQUIRE(node_dim > 0 && node_dim % 4 == 0 && node_dim <= 128 * MIX_C, "flid_neighbor_mean: node_dim must be a multiple of 4, <= %d", 128 * MIX_C);
     FLID_REQUIRE(time_gap > 0, "flid_neighbor_mean: time_gap must be positive");
-    if (n <= 0) return FLID_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned blocks = (unsigned)ceil_div(n * 32, 256);
     if (times_are_f32)

@@ -468,10 +468,10 @@ extern "C" int flid_train_sample_levels(const flid_graph* g, const int64_t* root
                                         double* const* t64_host, int64_t* const* nbr_host, int64_t* const* eid_host,
                                         float* const* dt_host, flid_stream stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    FLID_REQUIRE(g && roots && times && ids_host && t64_host && nbr_host && eid_host && dt_host, "flid_train_sample_levels: null argument");
     FLID_REQUIRE(k > 0, "Number of sampled neighbors for each node should be greater than 0!");
     FLID_REQUIRE(num_levels >= 1 && n >= 0, "flid_train_sample_levels: bad shape");
     if (n == 0) return FLID_OK;
+    FLID_REQUIRE(g && roots && times && ids_host && t64_host && nbr_host && eid_host && dt_host, "flid_train_sample_levels: null argument");
     const int top = num_levels - 1;
     FLID_CUDA(cudaMemcpyAsync(ids_host[top], roots, n * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
     FLID_CUDA(cudaMemcpyAsync(t64_host[top], times, n * sizeof(double), cudaMemcpyDeviceToDevice, st));

@@ -249,6 +249,8 @@ def autograd_forward(time_encoder, conv_layers, merge_layers, sampler, node_feat
     assert k > 0, 'Number of sampled neighbors for each node should be greater than 0!'
     if k > 32:
         raise ValueError("flid_b200 training path: num_neighbors must be <= 32")
+    if len(node_ids) == 0:                     # an empty batch: nothing to sample, nothing to differentiate
+        return node_feat.new_zeros((0, node_feat.shape[1]))
     levels = sample_levels(sampler, node_ids, node_interact_times, depth, k, device)
     w_t, b_t = time_encoder.w.weight.reshape(-1), time_encoder.w.bias
     dn, T = node_feat.shape[1], b_t.shape[0]

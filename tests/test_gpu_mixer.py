@@ -141,3 +141,20 @@ def test_tcl_golden_and_oracle(name, L, k, bias, zeros):
         m.compute_src_dst_node_temporal_embeddings(src[:4], dst[:4], ts[:4], k + 1)     # num_depths mismatch (TCL.py:184)
     with pytest.raises(IndexError):
         m.compute_src_dst_node_temporal_embeddings(np.array([10 ** 6]), np.array([1]), np.array([5.0]), k)
+
+
+def test_empty_batches():
+    """Zero-length batches return empty tensors through every drop-in (the reference's loops can end on one)."""
+    src, dst, eid, ts, nf, ef = cases.small_stream()
+    s = flid_b200.NeighborSampler(None, "recent", seed=1, device=DEV, _events=(src, dst, eid, ts, nf.shape[0] - 1))
+    e = np.zeros(0, dtype=np.int64)
+    et = np.zeros(0, dtype=np.float64)
+    gm = flid_b200.GraphMixer(nf, ef, s, 100, 5, 1, device=DEV).to(DEV)
+    tcl = flid_b200.TCL(nf, ef, s, 100, 1, 2, 6, 0.1, DEV).to(DEV)
+    tg = flid_b200.TGAT(nf, ef, s, 100, 2, 2, 0.1, DEV).to(DEV)
+    for m, args in ((gm, (e, e, et, 5)), (tcl, (e, e, et, 5)), (tg, (e, e, et, 5))):
+        for train in (False, True):
+            m.train(train)
+            with torch.set_grad_enabled(train):
+                a, b = m.compute_src_dst_node_temporal_embeddings(*args)
+            assert a.shape == (0, 172) and b.shape == (0, 172), type(m).__name__
