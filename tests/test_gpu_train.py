@@ -154,7 +154,7 @@ def test_training_forward_backward_with_dropout_vs_reference_op_order(L, k, p):
     (a * w).sum().backward()
     (b * w).sum().backward()
     scale = max(1.0, float(b.detach().abs().max()))
-    assert float((a - b).abs().max()) <= 1e-4 * scale
+    assert float((a - b).detach().abs().max()) <= 1e-4 * scale
     for (name, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
         assert pa.grad is not None and pb.grad is not None, name
         rel = float((pa.grad - pb.grad).norm()) / max(float(pb.grad.norm()), 1e-6)
