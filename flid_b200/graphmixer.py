@@ -58,8 +58,8 @@ class GraphMixer(nn.Module):
                  time_feat_dim: int, num_tokens: int, num_layers: int = 2, token_dim_expansion_factor: float = 0.5,
                  channel_dim_expansion_factor: float = 4.0, dropout: float = 0.1, device: str = 'cpu'):
         super().__init__()
-        self.device = _lib.require_cuda(device)
-        self.node_raw_features = torch.from_numpy(np.ascontiguousarray(node_raw_features, dtype=np.float32)).to(self.device)
+        self.device = device                  # compute calls require CUDA (no CPU fallback); construction does not
+        self.node_raw_features = torch.from_numpy(np.ascontiguousarray(node_raw_features, dtype=np.float32)).to(device)
         self.neighbor_sampler = neighbor_sampler
         self.node_feat_dim = self.node_raw_features.shape[1]
         self.time_feat_dim = time_feat_dim
@@ -100,7 +100,7 @@ class GraphMixer(nn.Module):
         n = ids.shape[0]
         if n and (int(ids.min()) < 0 or int(ids.max()) > sampler.num_nodes):
             raise IndexError("flid_b200.GraphMixer: node id outside the graph")
-        dev = self.device
+        dev = _lib.require_cuda(self.node_raw_features.device)
         w_t, b_t = self.time_encoder.w.weight.reshape(-1), self.time_encoder.w.bias
         outs = []
         with torch.cuda.device(dev):

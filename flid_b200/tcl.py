@@ -52,9 +52,9 @@ class TCL(nn.Module):
                  time_feat_dim: int, num_layers: int = 2, num_heads: int = 2, num_depths: int = 20, dropout: float = 0.1,
                  device: str = 'cpu'):
         super().__init__()
-        self.device = _lib.require_cuda(device)
-        self.node_raw_features = torch.from_numpy(np.ascontiguousarray(node_raw_features, dtype=np.float32)).to(self.device)
-        self.edge_raw_features = torch.from_numpy(np.ascontiguousarray(edge_raw_features, dtype=np.float32)).to(self.device)
+        self.device = device                  # compute calls require CUDA (no CPU fallback); construction does not
+        self.node_raw_features = torch.from_numpy(np.ascontiguousarray(node_raw_features, dtype=np.float32)).to(device)
+        self.edge_raw_features = torch.from_numpy(np.ascontiguousarray(edge_raw_features, dtype=np.float32)).to(device)
         self.neighbor_sampler = neighbor_sampler
         self.node_feat_dim = self.node_raw_features.shape[1]
         self.edge_feat_dim = self.edge_raw_features.shape[1]
@@ -111,7 +111,7 @@ class TCL(nn.Module):
         for a in (src, dst):
             if b and (int(a.min()) < 0 or int(a.max()) > sampler.num_nodes):
                 raise IndexError("flid_b200.TCL: node id outside the graph")
-        dev, f32 = self.device, t_np.dtype == np.float32
+        dev, f32 = _lib.require_cuda(self.node_raw_features.device), t_np.dtype == np.float32
         outs_s, outs_d = [], []
         with torch.cuda.device(dev):
             d_src = _lib.to_device(src, np.int64, dev, "tcl_src")

@@ -65,6 +65,14 @@ def test_no_cpu_fallback():
             m.compute_src_dst_node_temporal_embeddings(np.array([1]), np.array([2]), np.array([1.0]), 20)
 
 
+def test_sampler_consumers_have_no_cpu_fallback_either():
+    nf, ef = np.zeros((4, 172), np.float32), np.zeros((4, 172), np.float32)
+    for m in (flid_b200.GraphMixer(nf, ef, None, 100, 5, 1), flid_b200.TCL(nf, ef, None, 100, 1, 2, 6)):
+        assert not m.time_encoder.w.weight.is_cuda
+        with pytest.raises((RuntimeError, TypeError)):
+            m.compute_src_dst_node_temporal_embeddings(np.array([1]), np.array([2]), np.array([1.0]), 5)
+
+
 def test_state_dict_keys_match_reference_layout():
     m = flid_b200.TGAT(np.zeros((4, 172), np.float32), np.zeros((4, 172), np.float32), None, 100, 2, 2, 0.1, "cpu")
     sd = m.state_dict()
@@ -105,6 +113,12 @@ def test_state_dict_keys_equal_live_reference():
     assert {k: tuple(v.shape) for k, v in ours.items()} == {k: tuple(v.shape) for k, v in theirs.items()}
     assert {k: tuple(v.shape) for k, v in flid_b200.MLPClassifier(172).state_dict().items()} == \
            {k: tuple(v.shape) for k, v in ref.MLPClassifier(172).state_dict().items()}
+    ours = flid_b200.GraphMixer(nf, ef, None, 100, 20, 2).state_dict()
+    theirs = ref.GraphMixer(nf, ef, None, 100, 20, 2).state_dict()
+    assert {k: tuple(v.shape) for k, v in ours.items()} == {k: tuple(v.shape) for k, v in theirs.items()}
+    ours = flid_b200.TCL(nf, ef, None, 100, 2, 2, 21).state_dict()
+    theirs = ref.TCL(nf, ef, None, 100, 2, 2, 21).state_dict()
+    assert {k: tuple(v.shape) for k, v in ours.items()} == {k: tuple(v.shape) for k, v in theirs.items()}
 
 
 def test_shard_bounds_cover_everything_in_order():
