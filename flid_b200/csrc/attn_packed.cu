@@ -127,24 +127,21 @@ __global__ void __launch_bounds__(128, (H * NV <= 6 && NV <= 3) ? 4 : 2) attn_pk
     const int k = a.k, dn = a.dn, de = a.de, T = a.T;
     const int nv4 = dn >> 2, ev4 = de >> 2, tot4 = nv4 + ev4, kd = dn + de + T;
 
+    // k > 32: the slots are taken in blocks of 32 (lane j owns slot base + j of the current block); the online
+    // softmax state carries over.  Whether the target has any valid neighbour at all (the reference's all-masked
+    // case: uniform weights over the padded rows) must be known before the first block is processed.
+    bool all_masked = false;
+    if (k > 32) {
+        int any = 0;
+        for (int base = 0; base < k; base += 32)
+            any |= __any_sync(FULL, base + lane < k && __ldg(a.nbr + i * k + base + lane) != 0);
+        all_masked = !any;
+    }
     int nb_l = 0, e_l = 0;
     float dt_l = 0.f;
     int64_t hrow_l = 0;
-    if (lane < k) {
-        nb_l = __ldg(a.nbr + i * k + lane);
-        e_l = __ldg(a.eid + i * k + lane);
-        dt_l = __ldg(a.dt + i * k + lane);
-        hrow_l = a.hrow_idx ? (int64_t)__ldg(a.hrow_idx + i * k + lane)
-                            : (a.hrow_by_id ? (int64_t)nb_l : a.hrow_offset + i * k + lane);
-    }
-    const unsigned valid = __ballot_sync(FULL, lane < k && nb_l != 0);
-    const bool all_masked = (valid == 0u);
-    unsigned todo = all_masked ? (k >= 32 ? FULL : ((1u << k) - 1u)) : valid;
-    // byte addresses of this lane's slot rows (lane j owns slot j); the edge base is shifted so
-    // that chunk index f >= nv4 addresses the edge row directly
-    const u64 haddr = (u64)(reinterpret_cast<const char*>(a.hrow_base) + hrow_l * (int64_t)dn * 4);
-    const u64 eaddr = (u64)(reinterpret_cast<const char*>(a.edge_feat) + ((int64_t)e_l * ev4 - nv4) * 16);
-
+    unsigned todo = 0u;
+    u64 haddr = 0ull, eaddr = 0ull;
     const float wmax = __ldg(a.time_bound), bmax = __ldg(a.time_bound + 1);
     const float* u = a.u_base + (a.u_index ? (int64_t)__ldg(a.u_index + i) : i) * (int64_t)(H * kd);
     // this warp's slice of shared memory: [H][NV][32] Row4 (row part of u) then [H][TP][32] packed pairs (time part)
@@ -292,19 +289,37 @@ __global__ void __launch_bounds__(128, (H * NV <= 6 && NV <= 3) ? 4 : 2) attn_pk
         }
     };
 
-    int ja[G], jb[G];
-    Row4 xa[G][NV], xb[G][NV];
-    next_group(ja);
-    load_group(ja, xa);
-    while (true) {
-        next_group(jb);
-        load_group(jb, xb);
-        process(ja, xa);
-        if (jb[0] < 0) break;
+    for (int base = 0; base < k; base += 32) {
+        const int kb = min(32, k - base);
+        if (lane < kb) {
+            nb_l = __ldg(a.nbr + i * k + base + lane);
+            e_l = __ldg(a.eid + i * k + base + lane);
+            dt_l = __ldg(a.dt + i * k + base + lane);
+            hrow_l = a.hrow_idx ? (int64_t)__ldg(a.hrow_idx + i * k + base + lane)
+                                : (a.hrow_by_id ? (int64_t)nb_l : a.hrow_offset + i * k + base + lane);
+        }
+        const unsigned valid = __ballot_sync(FULL, lane < kb && nb_l != 0);
+        if (k <= 32) all_masked = (valid == 0u);
+        todo = all_masked ? (kb >= 32 ? FULL : ((1u << kb) - 1u)) : valid;
+        if (todo == 0u) continue;  // warp-uniform
+        // byte addresses of this lane's slot rows; the edge base is shifted so that chunk index f >= nv4
+        // addresses the edge row directly
+        haddr = (u64)(reinterpret_cast<const char*>(a.hrow_base) + hrow_l * (int64_t)dn * 4);
+        eaddr = (u64)(reinterpret_cast<const char*>(a.edge_feat) + ((int64_t)e_l * ev4 - nv4) * 16);
+        int ja[G], jb[G];
+        Row4 xa[G][NV], xb[G][NV];
         next_group(ja);
         load_group(ja, xa);
-        process(jb, xb);
-        if (ja[0] < 0) break;
+        while (true) {
+            next_group(jb);
+            load_group(jb, xb);
+            process(ja, xa);
+            if (jb[0] < 0) break;
+            next_group(ja);
+            load_group(ja, xa);
+            process(jb, xb);
+            if (ja[0] < 0) break;
+        }
     }
 
     float* z = a.z + i * (int64_t)(H * kd);

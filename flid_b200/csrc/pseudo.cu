@@ -130,7 +130,15 @@ __global__ void prob_filter_kernel(const float* __restrict__ probs, int64_t n, i
     if (mx < thr) labels[i] = -1.f;
 }
 
-static DevBuf g_ptrs;
+// scratch is keyed by device ordinal (a process may drive an E-model and an M-model on two GPUs); calls on one
+// device are expected on one stream at a time
+constexpr int MAX_DEV = 32;
+static DevBuf g_ptrs_dev[MAX_DEV];
+static int cur_device(int* dev) {
+    FLID_CUDA(cudaGetDevice(dev));
+    FLID_REQUIRE(*dev >= 0 && *dev < MAX_DEV, "device ordinal %d not supported", *dev);
+    return FLID_OK;
+}
 
 // Bulk path: fc1 (in -> hidden1, ReLU) runs on the tcgen05 GEMM, this kernel finishes the row:
 // fc2 (ReLU) -> fc3 -> softmax / argmax.  128 rows per block, the h1 tile and the two small
@@ -206,8 +214,8 @@ __global__ void __launch_bounds__(TAIL_ROWS) pseudo_tail_kernel(flid_mlp_weights
     labels[i] = arg;
 }
 
-static TcWeight g_fc1_dev[32];   // tiled fc1 image, one per device ordinal
-static DevBuf g_h1;
+static TcWeight g_fc1_dev[MAX_DEV];   // tiled fc1 image, one per device ordinal
+static DevBuf g_h1_dev[MAX_DEV];
 
 }  // namespace flid
 
@@ -233,9 +241,9 @@ int flid_pseudo_label(const flid_mlp_weights* w, const float* emb, int64_t n, fl
     }
     // weights may have changed since the last call: re-tile fc1 (a few KB) every time
     int dev = 0;
-    FLID_CUDA(cudaGetDevice(&dev));
-    FLID_REQUIRE(dev >= 0 && dev < 32, "flid_pseudo_label: device ordinal %d not supported", dev);
+    FLID_TRY(cur_device(&dev));
     TcWeight& g_fc1 = g_fc1_dev[dev];
+    DevBuf& g_h1 = g_h1_dev[dev];
     FLID_TRY(tc_prepare_weight(w->fc1_w, w->input_dim, w->hidden1, w->input_dim, &g_fc1, st));
     const int64_t chunk = 262144;
     FLID_TRY(g_h1.reserve(sizeof(float) * (size_t)std::min<int64_t>(chunk, n) * w->hidden1));
@@ -260,6 +268,9 @@ int flid_entropy_filter(const float* const* probs_store_host, int num_iters, int
     FLID_REQUIRE(num_classes > 0 && num_classes <= MAXC, "flid_entropy_filter: classes must be in 1..16");
     if (n <= 0) return FLID_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0;
+    FLID_TRY(cur_device(&dev));
+    DevBuf& g_ptrs = g_ptrs_dev[dev];
     FLID_TRY(g_ptrs.reserve(sizeof(void*) * num_iters));
     FLID_CUDA(cudaMemcpyAsync(g_ptrs.p, probs_store_host, sizeof(void*) * num_iters, cudaMemcpyHostToDevice, st));
     entropy_filter_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(g_ptrs.as<const float*>(), num_iters, n,

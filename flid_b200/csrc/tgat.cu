@@ -662,7 +662,8 @@ void flid_tgat_free(flid_tgat* m) {
     for (auto e : m->prof_ev) cudaEventDestroy(e);
     flid::DevBuf* bufs[] = {&m->raw_q, &m->raw_k, &m->raw_v, &m->raw_r, &m->table, &m->ws_ids, &m->ws_times,
                             &m->ws_nbr, &m->ws_eid, &m->ws_dt, &m->ws_h, &m->ws_u, &m->ws_z, &m->ws_o,
-                            &m->ws_a, &m->ws_hd, &m->ws_misc, &m->ws_rid, &m->ws_rt, &m->ws_bad, &m->ws_pos, &m->ws_self, &m->ws_sort};
+                            &m->ws_a, &m->ws_hd, &m->ws_misc, &m->ws_rid, &m->ws_rt, &m->ws_bad, &m->ws_pos, &m->ws_self, &m->ws_sort,
+                            &m->tgn_ids, &m->tgn_times, &m->tgn_eids, &m->tgn_gi, &m->tgn_gh};
     for (auto* b : bufs) b->release();
     delete m;
 }
@@ -754,7 +755,6 @@ int flid_tgat_embed(flid_tgat* m, const flid_graph* g, const float* node_feat, c
     FLID_REQUIRE(m && g && node_feat && edge_feat, "flid_tgat_embed: null argument");
     FLID_REQUIRE(m->have_weights, "flid_tgat_embed: weights not set");
     FLID_REQUIRE(k > 0, "Number of sampled neighbors for each node should be greater than 0!");
-    FLID_REQUIRE(k <= 32, "flid_tgat_embed: num_neighbors above 32 is not supported by the attention kernel");
     if (n <= 0) return FLID_OK;
     FLID_REQUIRE(nodes && times && out, "flid_tgat_embed: null argument");
     cudaStream_t st = (cudaStream_t)stream;
@@ -784,7 +784,7 @@ int flid_tgat_memo_build(flid_tgat* m, const flid_graph* g, const float* node_fe
     using namespace flid;
     FLID_REQUIRE(m && g && node_feat && edge_feat && memo_out, "flid_tgat_memo_build: null argument");
     FLID_REQUIRE(m->have_weights, "flid_tgat_memo_build: weights not set");
-    FLID_REQUIRE(k > 0 && k <= 32, "flid_tgat_memo_build: num_neighbors must be in 1..32");
+    FLID_REQUIRE(k > 0, "Number of sampled neighbors for each node should be greater than 0!");
     FLID_REQUIRE(level >= 1 && level <= m->L, "flid_tgat_memo_build: level %d outside 1..%d", level, m->L);
     FLID_REQUIRE(level == 1 || memo_prev != nullptr, "flid_tgat_memo_build: level %d needs the level-%d table", level,
                  level - 1);
@@ -803,7 +803,6 @@ int flid_tgat_embed_memo(flid_tgat* m, const flid_graph* g, const float* node_fe
     FLID_REQUIRE(m && g && node_feat && edge_feat, "flid_tgat_embed_memo: null argument");
     FLID_REQUIRE(m->have_weights, "flid_tgat_embed_memo: weights not set");
     FLID_REQUIRE(k > 0, "Number of sampled neighbors for each node should be greater than 0!");
-    FLID_REQUIRE(k <= 32, "flid_tgat_embed_memo: num_neighbors above 32 is not supported by the attention kernel");
     FLID_REQUIRE(m->L == 1 || memo_tables_host != nullptr, "flid_tgat_embed_memo: memo tables missing");
     for (int l = 0; l + 1 < m->L; ++l)
         FLID_REQUIRE(memo_tables_host[l] != nullptr, "flid_tgat_embed_memo: memo table of layer %d is null", l + 1);

@@ -38,6 +38,7 @@ struct flid_tgat {
     bool self_from_memo = true;  // roots that are graph events read their own lower layers from the memo (FLID_SELF_MEMO=0 disables)
     flid::DevBuf ws_ids, ws_times, ws_nbr, ws_eid, ws_dt, ws_h, ws_u, ws_z, ws_o, ws_a, ws_hd, ws_misc, ws_pos, ws_self, ws_sort;
     flid::DevBuf ws_rid, ws_rt, ws_bad;  // root conversion staging
+    flid::DevBuf tgn_ids, tgn_times, tgn_eids, tgn_gi, tgn_gh;  // TGN step scratch (tgn.cu): per handle, hence per device
     int64_t stats[4] = {0, 0, 0, 0};
     int64_t valid_mult = 1;  // attention evaluations that consume each sampled neighbour list
     // optional per-kernel-class CUDA-event timing (bench.py's roofline numbers)

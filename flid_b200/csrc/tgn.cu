@@ -17,20 +17,18 @@
 
 namespace flid {
 
-struct TgnScratch {
-    DevBuf ids, times, eids, out, gi, gh;
-};
-static TgnScratch g_tgn;
 
 __global__ void tgn_prep_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
                                 const double* __restrict__ times, const int64_t* __restrict__ eids, int64_t B,
-                                int64_t num_rows, int32_t* __restrict__ ids, double* __restrict__ t2,
+                                int64_t id_limit, int32_t* __restrict__ ids, double* __restrict__ t2,
                                 int32_t* __restrict__ e32, int32_t* __restrict__ err) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= B) return;
+    // id_limit = min(bank rows, sampler nodes + 1): an id the sampler has no list for is the reference's
+    // IndexError in nodes_neighbor_times[node_id] (utils/utils.py:141), one beyond the bank its index error there
     int64_t s = src[i], d = dst[i], e = eids ? eids[i] : 0;
-    if (s < 0 || s >= num_rows) s = 0, atomicMax(err, 2);
-    if (d < 0 || d >= num_rows) d = 0, atomicMax(err, 2);
+    if (s < 0 || s >= id_limit) s = 0, atomicMax(err, 2);
+    if (d < 0 || d >= id_limit) d = 0, atomicMax(err, 2);
     if (e < 0 || e > 0x7fffffffLL) e = 0, atomicMax(err, 2);
     ids[i] = (int32_t)s, ids[B + i] = (int32_t)d;
     t2[i] = times[i], t2[B + i] = times[i];
@@ -136,9 +134,9 @@ __global__ void tgn_reset_kernel(flid_tgn_state s, const float* __restrict__ nod
 static int gru_rows(flid_tgat* m, const flid_tgn_state* s, const flid_gru_weights* gru, const int32_t* ids,
                     int64_t rows, const float* node_raw, int reset_scratch, cudaStream_t st) {
     const int dn = m->dn, msg = 2 * m->dn + m->T + m->de;
-    FLID_TRY(g_tgn.gi.reserve(sizeof(float) * rows * 3 * dn));
-    FLID_TRY(g_tgn.gh.reserve(sizeof(float) * rows * 3 * dn));
-    float *gi = g_tgn.gi.as<float>(), *gh = g_tgn.gh.as<float>();
+    FLID_TRY(m->tgn_gi.reserve(sizeof(float) * rows * 3 * dn));
+    FLID_TRY(m->tgn_gh.reserve(sizeof(float) * rows * 3 * dn));
+    float *gi = m->tgn_gi.as<float>(), *gh = m->tgn_gh.as<float>();
     GemmArgs a{s->pending_msg, msg, ids, gru->weight_ih, msg, gi, 3 * dn, gru->bias_ih, rows, 3 * dn, msg, 0, 0};
     FLID_TRY(launch_gemm(a, st));
     GemmArgs b{s->memories, dn, ids, gru->weight_hh, dn, gh, 3 * dn, gru->bias_hh, rows, 3 * dn, dn, 0, 0};
@@ -181,20 +179,25 @@ int flid_tgn_step(flid_tgat* m, const flid_graph* g, const flid_tgn_state* s, co
                  "flid_tgn_step: null argument");
     FLID_REQUIRE(out != nullptr || positive, "flid_tgn_step: nothing to do (no output buffer and no state update)");
     FLID_REQUIRE(m->have_weights, "flid_tgn_step: weights not set");
-    FLID_REQUIRE(k > 0 && k <= 32, "flid_tgn_step: num_neighbors must be in 1..32");
+    FLID_REQUIRE(k > 0, "Number of sampled neighbors for each node should be greater than 0!");
     FLID_REQUIRE(!positive || eids, "flid_tgn_step: edge_ids are required for positive edges");
-    FLID_REQUIRE(s->num_rows == g->num_nodes + 1, "flid_tgn_step: state rows != graph nodes + 1");
+    // A sampler built from a prefix of the stream (train_neighbor_sampler, PTCL/EM_warmup.py:71) may know fewer
+    // nodes than the bank has rows (one per node of the full graph); the other way round the bank could not
+    // hold the memories of sampled neighbours.
+    FLID_REQUIRE(s->num_rows >= g->num_nodes + 1, "flid_tgn_step: memory bank has %lld rows but the sampler knows %lld nodes",
+                 (long long)s->num_rows, (long long)g->num_nodes + 1);
     if (batch <= 0) return FLID_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t B = batch, n2 = 2 * batch;
-    FLID_TRY(g_tgn.ids.reserve(sizeof(int32_t) * n2));
-    FLID_TRY(g_tgn.times.reserve(sizeof(double) * n2));
-    FLID_TRY(g_tgn.eids.reserve(sizeof(int32_t) * B));
-    int32_t* ids = g_tgn.ids.as<int32_t>();
-    double* t2 = g_tgn.times.as<double>();
-    int32_t* e32 = g_tgn.eids.as<int32_t>();
-    tgn_prep_kernel<<<(unsigned)ceil_div(B, 256), 256, 0, st>>>(src, dst, times, eids, B, s->num_rows, ids, t2, e32,
-                                                               err_flag);
+    FLID_TRY(m->tgn_ids.reserve(sizeof(int32_t) * n2));
+    FLID_TRY(m->tgn_times.reserve(sizeof(double) * n2));
+    FLID_TRY(m->tgn_eids.reserve(sizeof(int32_t) * B));
+    int32_t* ids = m->tgn_ids.as<int32_t>();
+    double* t2 = m->tgn_times.as<double>();
+    int32_t* e32 = m->tgn_eids.as<int32_t>();
+    tgn_prep_kernel<<<(unsigned)ceil_div(B, 256), 256, 0, st>>>(src, dst, times, eids, B,
+                                                               std::min<int64_t>(s->num_rows, g->num_nodes + 1), ids, t2,
+                                                               e32, err_flag);
     FLID_LAUNCH_CHECK();
     // (1)+(2): embeddings on memory' + raw   (models/MemoryModel.py:117-146)
     // out == nullptr: state update only (the training-mode host path computes the embeddings itself)

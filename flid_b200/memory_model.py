@@ -233,6 +233,13 @@ class MemoryModel(nn.Module):
         if eng is not None:
             eng.close()
 
+    def invalidate_caches(self):
+        """Drop every derived device cache (uploaded weights, query table, incremental GRU state); needed after
+        ``.data`` writes that autograd's version counters do not see."""
+        self._engine.invalidate()
+        self.memory_bank._dirty = True
+        self._synced = None
+
     # ---- internals
     def _gru(self):
         cell = self.memory_updater.memory_updater

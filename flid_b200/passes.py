@@ -37,6 +37,15 @@ def all_gather_rows(local: torch.Tensor, num_items: int, per: int, dist_mod=None
     return out[:num_items]
 
 
+def _require_eval(*modules):
+    """The reference's pass loops run after ``model.eval()`` (PTCL/E_step.py:300, PTCL/M_step.py:456); a module
+    left in training mode would silently take the dropout / autograd path for the whole pass."""
+    for m in modules:
+        if m is not None and m.training:
+            raise RuntimeError(f"flid_b200.passes: {type(m).__name__} is in training mode; call .eval() first "
+                               "(bulk passes are inference passes)")
+
+
 def prepare_layer_memo(model, num_roots: int, num_neighbors: int, sharded: bool):
     """Build the layer memo (flid_tgat_memo_build) ahead of a bulk pass when it pays off:
     a pass over ``num_roots`` root queries costs sum_l (1+k)^(L-l) attention evaluations per
@@ -44,7 +53,7 @@ def prepare_layer_memo(model, num_roots: int, num_neighbors: int, sharded: bool)
     builds a contiguous slice of the table rows and the slices are all-gathered (NCCL)."""
     build = getattr(model, "build_layer_memo", None)
     depth = getattr(model, "num_layers", 1)
-    if build is None or depth < 2 or not model._engine.memo_mode or not (0 < num_neighbors <= 32):
+    if build is None or depth < 2 or not model._engine.memo_mode or num_neighbors <= 0:
         return False
     plain = sum((1 + num_neighbors) ** (depth - l) for l in range(1, depth + 1))
     cost = (depth - 1) * (model.neighbor_sampler.num_entries + 1)
@@ -54,27 +63,50 @@ def prepare_layer_memo(model, num_roots: int, num_neighbors: int, sharded: bool)
     return True
 
 
+def _is_tensor(x):
+    return isinstance(x, torch.Tensor)
+
+
+def _slice_events(src, dst, t, lo, hi):
+    return src[lo:hi], dst[lo:hi], t[lo:hi]
+
+
+def _embed_src_dst(model, src, dst, t, num_neighbors):
+    """Both endpoints of every event through one launch chain.  Host numpy arrays take the drop-in call
+    (``compute_src_dst_node_temporal_embeddings``: pinned staging + H2D inside); device tensors (int64 ids,
+    float64 / float32 times already resident in HBM) skip the copies."""
+    if _is_tensor(src):
+        b = src.shape[0]
+        both = model.compute_node_temporal_embeddings(torch.cat([src, dst]), torch.cat([t, t]), model.num_layers,
+                                                      num_neighbors)
+        return both[:b], both[b:]
+    return model.compute_src_dst_node_temporal_embeddings(src, dst, t, num_neighbors)
+
+
 def embed_events(model, src_node_ids, dst_node_ids, node_interact_times, num_neighbors: int = 20, sharded=None):
     """Embeddings of every event's source and destination node at the event time:
     two float32 [E, dn] device tensors, rows in event order (what the reference's full pass
     accumulates batch by batch and copies into ``src_node_embeddings`` / ``dst_node_embeddings``).
+    Inputs are host numpy arrays (the reference's types) or device tensors.
     With torch.distributed initialised (or ``sharded=True``) each rank embeds a contiguous
     event range and the halves are all-gathered."""
+    _require_eval(model)
     dist, rank, world = _dist()
     if sharded is None:
         sharded = world > 1
-    src = np.asarray(src_node_ids)
-    dst = np.asarray(dst_node_ids)
-    t = np.asarray(node_interact_times)
+    if _is_tensor(src_node_ids):
+        src, dst, t = src_node_ids, dst_node_ids, node_interact_times
+    else:
+        src, dst, t = np.asarray(src_node_ids), np.asarray(dst_node_ids), np.asarray(node_interact_times)
     e = len(src)
     if not sharded or world == 1:
         with torch.no_grad():
             prepare_layer_memo(model, 2 * e, num_neighbors, False)
-            return model.compute_src_dst_node_temporal_embeddings(src, dst, t, num_neighbors)
+            return _embed_src_dst(model, src, dst, t, num_neighbors)
     lo, hi, per = shard_bounds(e, rank, world)
     with torch.no_grad():
         prepare_layer_memo(model, 2 * e, num_neighbors, True)
-        a, b = model.compute_src_dst_node_temporal_embeddings(src[lo:hi], dst[lo:hi], t[lo:hi], num_neighbors)
+        a, b = _embed_src_dst(model, *_slice_events(src, dst, t, lo, hi), num_neighbors)
     both = torch.stack([a, b], dim=1)                       # [n_local, 2, dn]: one collective for both halves
     full = all_gather_rows(both, e, per, dist)
     return full[:, 0].contiguous(), full[:, 1].contiguous()
@@ -82,41 +114,56 @@ def embed_events(model, src_node_ids, dst_node_ids, node_interact_times, num_nei
 
 def e_step_pass(model, decoder: MLPClassifier, src_node_ids, dst_node_ids, node_interact_times,
                 num_neighbors: int = 20, pseudo_labels_store=None, ps_filter: str = 'entropy', threshold: float = 0.9,
-                sharded=None, return_embeddings: bool = False):
-    """Embedding pass + pseudo-label emission + EST/CST filter for a single-way dataset.
+                sharded=None, return_embeddings: bool = False, double_way: bool = False):
+    """Embedding pass + pseudo-label emission + EST/CST filter.
 
-    Returns (pseudo_labels float32 [1, E] with -1 marks, probabilities float32 [E, C],
-    (src_emb, dst_emb) or None).  ``pseudo_labels_store`` is the reference's list of earlier
-    iterations' probabilities; this pass's probabilities are appended to it before filtering
-    (PTCL/E_step.py:351 then PTCL/utils.py:80-83).  When sharded, only (label, probs) rows are
-    all-gathered (16 B/event for C=2) unless the embeddings are requested."""
+    Single-way datasets (``double_way=False``): returns (pseudo_labels float32 [1, E] with -1 marks,
+    probabilities float32 [E, C], (src_emb, dst_emb) or None).  Double-way datasets (PTCL/E_step.py:318-343:
+    labels for both endpoints): pseudo_labels [2, E], probabilities [2, E, C] (row 0 = sources).
+    ``pseudo_labels_store`` is the reference's list of earlier iterations' probabilities; this pass's
+    probabilities are appended to it before filtering (PTCL/E_step.py:351 then PTCL/utils.py:80-83).
+    When sharded, only (label, probs) rows are all-gathered (12 B/event/endpoint for C=2) unless the
+    embeddings are requested."""
+    _require_eval(model, decoder)
     dist, rank, world = _dist()
     if sharded is None:
         sharded = world > 1
-    src = np.asarray(src_node_ids)
+    if _is_tensor(src_node_ids):
+        src, dst, t = src_node_ids, dst_node_ids, node_interact_times
+    else:
+        src, dst, t = np.asarray(src_node_ids), np.asarray(dst_node_ids), np.asarray(node_interact_times)
     e = len(src)
     store = pseudo_labels_store if pseudo_labels_store is not None else []
+
+    def score(a, b):
+        """(labels float32 [ways, n], probs [ways, n, C]) of one event range"""
+        if double_way:
+            l2, p2 = emit_pseudo_labels(decoder, torch.cat([a, b]))
+            return l2.to(torch.float32).reshape(2, -1), p2.reshape(2, a.shape[0], -1)
+        l1, p1 = emit_pseudo_labels(decoder, a)
+        return l1.to(torch.float32).reshape(1, -1), p1.unsqueeze(0)
+
     if not sharded or world == 1:
-        src_emb, dst_emb = embed_events(model, src, dst_node_ids, node_interact_times, num_neighbors, sharded=False)
-        labels, probs = emit_pseudo_labels(decoder, src_emb)
+        src_emb, dst_emb = embed_events(model, src, dst, t, num_neighbors, sharded=False)
+        labels, probs = score(src_emb, dst_emb)
         emb = (src_emb, dst_emb)
     else:
         lo, hi, per = shard_bounds(e, rank, world)
-        dst = np.asarray(dst_node_ids)
-        t = np.asarray(node_interact_times)
         with torch.no_grad():
             prepare_layer_memo(model, 2 * e, num_neighbors, True)
-            a, b = model.compute_src_dst_node_temporal_embeddings(src[lo:hi], dst[lo:hi], t[lo:hi], num_neighbors)
-        l_loc, p_loc = emit_pseudo_labels(decoder, a)
-        packed = torch.cat([l_loc.to(torch.float32).unsqueeze(1), p_loc], dim=1)     # [n_local, 1 + C]
-        full = all_gather_rows(packed, e, per, dist)
-        labels, probs = full[:, 0].to(torch.int64), full[:, 1:].contiguous()
+            a, b = _embed_src_dst(model, *_slice_events(src, dst, t, lo, hi), num_neighbors)
+        l_loc, p_loc = score(a, b)                                            # [ways, n_loc], [ways, n_loc, C]
+        packed = torch.cat([l_loc.unsqueeze(2), p_loc], dim=2).transpose(0, 1)  # [n_loc, ways, 1 + C]
+        full = all_gather_rows(packed.contiguous(), e, per, dist).transpose(0, 1)
+        labels, probs = full[:, :, 0].contiguous(), full[:, :, 1:].contiguous()
         emb = None
         if return_embeddings:
             both = all_gather_rows(torch.stack([a, b], dim=1), e, per, dist)
             emb = (both[:, 0].contiguous(), both[:, 1].contiguous())
+    if not double_way:
+        probs = probs[0]
     store.append(probs)
-    pseudo = labels.to(torch.float32).reshape(1, -1).contiguous()
+    pseudo = labels.contiguous()
     if ps_filter == 'entropy':
         pseudo = entropy_filter(pseudo, store, threshold)
     elif ps_filter == 'probability':
@@ -135,6 +182,7 @@ def tgn_pass(model, src_node_ids, dst_node_ids, node_interact_times, edge_ids, b
     dev = model.node_raw_features.device
     out_s = torch.empty((e, model.node_feat_dim), dtype=torch.float32, device=dev)
     out_d = torch.empty_like(out_s)
+    _require_eval(model)
     model.memory_bank.__init_memory_bank__()
     with torch.no_grad():
         for lo in range(0, e, batch_size):

@@ -51,8 +51,11 @@ class MLPClassifier(nn.Module):
         return probs, labels, logits
 
     def forward(self, x: torch.Tensor):
-        """models/modules.py:86-97.  Eval / no-grad calls return the fused kernel's logits."""
-        if torch.is_grad_enabled() and self.training:
+        """models/modules.py:86-97.  The fused kernel (forward-only, no dropout) serves eval-mode calls that
+        need no graph; training mode (dropout, also under no_grad as in the reference) and any call whose
+        input or parameters require grad take the torch path."""
+        needs_graph = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if self.training or needs_graph or x.device.type != "cuda":
             # decoder training on cached embeddings (PTCL/E_step.py) is plain torch autograd, as in the reference
             x = self.dropout(self.act(self.fc1(x)))
             x = self.dropout(self.act(self.fc2(x)))

@@ -15,6 +15,11 @@ import torch
 from . import _lib
 
 
+import itertools
+
+_generation = itertools.count(1)
+
+
 class NeighborSampler:
     def __init__(self, adj_list=None, sample_neighbor_strategy: str = 'uniform', time_scaling_factor: float = 0.0,
                  seed: int = None, device=None, _events=None):
@@ -32,6 +37,9 @@ class NeighborSampler:
         self.device = _lib.require_cuda(device)
         self._handle = C.c_void_p(None)
         self._host = None
+        # process-unique id of this CSR: caches keyed on it (the layer memo) cannot be served to a later sampler
+        # whose C handle happens to be allocated at the same address
+        self.generation = next(_generation)
         lib = _lib.lib()
         with torch.cuda.device(self.device):
             if _events is not None:

@@ -84,6 +84,17 @@ class _Engine:
         self.memo_builds = 0      # how many times a memo was (re)built (diagnostics)
         self.build_stats = None   # set to [0, 0, 0] to accumulate (evaluations, valid slots, queries) over memo builds
         self.served = {}     # depth -> (key, root queries answered without a memo)
+        self.epoch = 0       # bumped by invalidate(): part of every cache key
+
+    def invalidate(self):
+        """Forget the uploaded weights, the cached node table and the layer memo.  Needed after writes that
+        autograd's version counter does not see (``param.data.copy_()``, ``.data`` mutation, feature tables
+        edited in place through ``.data``); ``load_state_dict`` / ``.to()`` / optimizer steps are detected."""
+        self.epoch += 1
+        self.versions.clear()
+        self.tables.clear()
+        self.memo.clear()
+        self.served.clear()
 
     def close(self):
         for h in self.handles.values():
@@ -147,7 +158,7 @@ class _Engine:
 
 
 def _memo_key(engine, depth, sampler, node_feat, edge_feat, k):
-    return (engine.versions.get(depth), int(sampler.handle.value or 0), node_feat.data_ptr(), node_feat._version,
+    return (engine.versions.get(depth), engine.epoch, sampler.generation, node_feat.data_ptr(), node_feat._version,
             edge_feat.data_ptr(), edge_feat._version, int(k))
 
 
@@ -275,7 +286,7 @@ def embed_roots(engine, depth, time_encoder, conv_layers, merge_layers, sampler,
         n = d_nodes.shape[0]
         out = torch.empty((n, node_feat.shape[1]), dtype=torch.float32, device=device)
         memo = None
-        if use_memo and 0 < int(num_neighbors) <= 32:
+        if use_memo and int(num_neighbors) > 0:
             memo = _memo_for_call(engine, depth, time_encoder, conv_layers, merge_layers, sampler, node_feat,
                                   edge_feat, int(num_neighbors), n)
         if memo is not None:
@@ -318,6 +329,22 @@ class TGAT(nn.Module):
         eng = getattr(self, "_engine", None)
         if eng is not None:
             eng.close()
+
+    def invalidate_caches(self):
+        """Drop every derived device cache (see ``_Engine.invalidate``)."""
+        self._engine.invalidate()
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        eng = getattr(self, "_engine", None)
+        if eng is not None:
+            eng.invalidate()
+        return out
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self._engine.invalidate()
+        return out
 
     def _needs_autograd(self):
         """Training-mode calls need dropout and a backward pass; eval-mode calls with grad enabled need the

@@ -222,13 +222,14 @@ def sample_levels(sampler, node_ids, node_interact_times, depth, k, device):
     with torch.cuda.device(device):
         d_ids = _lib.to_device(ids, np.int64, device, "tr_ids")
         d_t = _lib.to_device(t_np, np.float64, device, "tr_times")        # float32 -> float64 is exact
-        levels, ptrs, nl = {}, [[], [], [], [], []], n
+        levels, ptrs, nl, keep_alive = {}, [[], [], [], [], []], n, []
         for l in range(depth, 0, -1):
             tens = (torch.empty((nl,), dtype=torch.int64, device=device),
                     torch.empty((nl,), dtype=torch.float64, device=device),
                     torch.empty((nl, k), dtype=torch.int64, device=device),
                     torch.empty((nl, k), dtype=torch.int64, device=device),
                     torch.empty((nl, k), dtype=torch.float32, device=device))
+            keep_alive.append(tens)      # the C call below reads and writes every level's tensors through raw pointers
             for lst, t in zip(ptrs, tens):
                 lst.insert(0, t.data_ptr())
             levels[l] = (tens[0], tens[2], tens[3], tens[4])
@@ -237,6 +238,7 @@ def sample_levels(sampler, node_ids, node_interact_times, depth, k, device):
         _lib.check(_lib.lib().flid_train_sample_levels(sampler.handle, _lib.ptr(d_ids), _lib.ptr(d_t),
                                                        1 if t_np.dtype == np.float32 else 0, n, int(k), depth, *arrs,
                                                        _lib.stream()))
+        del keep_alive               # stream-ordered free: safe after the launches were queued
     return levels
 
 

@@ -8,8 +8,8 @@ the tree.  The hot-path modules only need
 ``utils.DataLoader`` that holds a 7-field record with the field names of
 ``utils/DataLoader.py:46-65``.
 
-The reference tree only exists in the build container (``/root/reference``); it
-never travels to the GPU box.  This shim is used by ``tests/golden/make_golden.py``
+The reference tree lives in the build container (``/root/reference``); on another
+machine a copy is looked for under ``baseline/_ref/`` and ``oracle/_ref/`` (never committed).  This shim is used by ``tests/golden/make_golden.py``
 (to mint golden vectors) and by the ``not gpu`` tests that pin the oracle against
 the reference when the tree is present.  Nothing in ``flid_b200/`` imports it.
 """
@@ -17,13 +17,20 @@ import os
 import sys
 import types
 
-REFERENCE_ROOTS = ("/root/reference",)
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# the build container's read-only tree, then the places a copy may have been put for the GPU box
+# (both git-ignored, neither gpurun-ignored); nested one level deep as a pip --target / unpacked archive would be
+REFERENCE_ROOTS = ("/root/reference", os.path.join(_REPO, "baseline", "_ref"), os.path.join(_REPO, "oracle", "_ref"))
 
 
 def reference_root():
     for root in REFERENCE_ROOTS:
-        if os.path.isfile(os.path.join(root, "models", "TGAT.py")):
-            return root
+        cands = [root]
+        if os.path.isdir(root):
+            cands += [os.path.join(root, d) for d in sorted(os.listdir(root)) if os.path.isdir(os.path.join(root, d))]
+        for c in cands:
+            if os.path.isfile(os.path.join(c, "models", "TGAT.py")) and os.path.isfile(os.path.join(c, "utils", "utils.py")):
+                return c
     return None
 
 

@@ -2,9 +2,10 @@
 (via the ctypes host layer) and compares against the CPU oracle (oracle/) on the same
 seeded inputs and against the golden vectors minted from the real FLiD reference.
 
-Tolerances (BASELINE.json north_star): sampler bit-exact; fp32 embeddings rel 1e-4
-(stated here as |got - want| <= 1e-4 * max(1, max|want|) elementwise, i.e. 1e-4 of the
-tensor's scale, plus a tight mean-error check); pseudo-label masks identical."""
+Tolerances (BASELINE.json north_star): sampler bit-exact; fp32 embeddings rel 1e-4, stated
+here as three checks: every element within 2e-5 of the tensor's scale (max(1, max|want|)),
+every significant element (|want| >= 0.1 * scale) within 1e-4 relative, and a mean absolute
+error below 2e-6 of the scale; pseudo-label masks identical."""
 import os
 
 import numpy as np
@@ -29,10 +30,16 @@ def assert_fp32_close(got, want, what=""):
     got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
     assert got.shape == want.shape, (got.shape, want.shape)
     assert np.isfinite(got).all(), f"{what}: non-finite values"
+    if want.size == 0:
+        return
     scale = max(1.0, float(np.abs(want).max()))
     err = np.abs(got - want)
-    assert err.max() <= 1e-4 * scale, f"{what}: max abs err {err.max():.3e} (scale {scale:.3g})"
-    assert err.mean() <= 1e-5 * scale, f"{what}: mean abs err {err.mean():.3e}"
+    assert err.max() <= 2e-5 * scale, f"{what}: max abs err {err.max():.3e} (scale {scale:.3g})"
+    big = np.abs(want) >= 0.1 * scale
+    if big.any():
+        rel = (err[big] / np.abs(want[big])).max()
+        assert rel <= 1e-4, f"{what}: max relative err {rel:.3e} on elements >= 0.1 * scale"
+    assert err.mean() <= 2e-6 * scale, f"{what}: mean abs err {err.mean():.3e}"
 
 
 def make_sampler(src, dst, eid, ts, n):
@@ -827,3 +834,136 @@ def test_full_size_dsub_shape_properties():
                                  g.src_node_ids[few], g.dst_node_ids[few], g.node_interact_times[few], 2, 30)
     assert_fp32_close(a[few].cpu().numpy(), wa.numpy(), "Dsub full-size src vs oracle")
     assert_fp32_close(b[few].cpu().numpy(), wb.numpy(), "Dsub full-size dst vs oracle")
+
+
+# ===================================================================== round-2 hardening
+@pytest.mark.parametrize("memo", [False, True])
+def test_tgat_more_than_32_neighbors(memo):
+    """num_neighbors above one warp's 32 slots (the reference takes any k, utils/load_configs.py:114):
+    hubs fill all 40 slots, most nodes are partly or fully padded."""
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    g = synth.wikipedia_shape(seed=3, scale=0.05)
+    p = otgat.default_params(172, 172, 100, 2, 2, seed=8, time_bias_scale=0.2)
+    m, s = tgat_pair(g.node_raw_features, g.edge_raw_features, g.src_node_ids, g.dst_node_ids, g.edge_ids,
+                     g.node_interact_times, 2, 2, p, memo)
+    o = osamp.OracleSampler.from_events(g.src_node_ids, g.dst_node_ids, g.edge_ids, g.node_interact_times, g.num_nodes)
+    sel = np.arange(g.num_interactions - 40, g.num_interactions)
+    src, dst, ts = g.src_node_ids[sel], g.dst_node_ids[sel], g.node_interact_times[sel]
+    got = s.get_historical_neighbors(src, ts, 40)
+    want = o.get_historical_neighbors(src, ts, 40)
+    assert all(np.array_equal(x, y) for x, y in zip(got, want))
+    assert (got[0] != 0).all(axis=1).any() and (got[0] == 0).any(), "case must mix full and padded neighbourhoods"
+    with torch.no_grad():
+        a, b = m.compute_src_dst_node_temporal_embeddings(src, dst, ts, 40)
+    wa, wb = otgat.embed_src_dst(p, torch.from_numpy(g.node_raw_features), torch.from_numpy(g.edge_raw_features), o,
+                                 src, dst, ts, 2, 40)
+    assert_fp32_close(a.cpu().numpy(), wa.numpy(), "k=40 src")
+    assert_fp32_close(b.cpu().numpy(), wb.numpy(), "k=40 dst")
+
+
+def test_training_path_rejects_more_than_32_neighbors():
+    """The training-mode kernels keep one slot per lane; the limit is an explicit error, not a wrong result."""
+    src, dst, eid, ts, nf, ef = cases.small_stream()
+    p = otgat.default_params(172, 172, 100, 1, 2, seed=3)
+    m, _ = tgat_pair(nf, ef, src, dst, eid, ts, 1, 2, p)
+    m.train()
+    with pytest.raises(ValueError, match="num_neighbors must be <= 32"):
+        m.compute_src_dst_node_temporal_embeddings(src[:4], dst[:4], ts[:4], 33)
+
+
+def test_tgn_wikipedia_shape_60_batches_vs_oracle():
+    """configs[1] at the Wikipedia shape (9 227 nodes, hubs with thousands of interactions): 60 consecutive
+    batches of 200 events taken from the middle of the stream (rich histories, many pending messages,
+    nodes in both roles within a batch), every batch and the final bank against the oracle."""
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    g = synth.wikipedia_shape(seed=0, scale=1.0)
+    p = otgn.default_params(172, 172, 100, 1, 2, seed=9, time_bias_scale=0.1)
+    m = tgn_model(g.node_raw_features, g.edge_raw_features, g.src_node_ids, g.dst_node_ids, g.edge_ids,
+                  g.node_interact_times, 1, p)
+    o = otgn.OracleTGN(p, torch.from_numpy(g.node_raw_features), torch.from_numpy(g.edge_raw_features),
+                       osamp.OracleSampler.from_events(g.src_node_ids, g.dst_node_ids, g.edge_ids,
+                                                       g.node_interact_times, g.num_nodes), 1, 20)
+    lo0, bs, nb = 100000, 200, 60
+    deg = np.bincount(np.concatenate([g.src_node_ids[:lo0], g.dst_node_ids[:lo0]]))
+    assert deg.max() > 5000, "the shape is meant to have hub nodes"
+    with torch.no_grad():
+        for b in range(nb):
+            sl = slice(lo0 + b * bs, lo0 + (b + 1) * bs)
+            a, c = m.compute_src_dst_node_temporal_embeddings(g.src_node_ids[sl], g.dst_node_ids[sl],
+                                                              g.node_interact_times[sl], g.edge_ids[sl], True, 20)
+            wa, wc = o.step(g.src_node_ids[sl], g.dst_node_ids[sl], g.node_interact_times[sl], g.edge_ids[sl], True)
+            assert_fp32_close(a.cpu().numpy(), wa.numpy(), f"wikipedia-shape TGN src batch {b}")
+            assert_fp32_close(c.cpu().numpy(), wc.numpy(), f"wikipedia-shape TGN dst batch {b}")
+    assert_fp32_close(m.memory_bank.node_memories.cpu().numpy(), o.mem.numpy(), "bank after 60 batches")
+    assert np.array_equal(m.memory_bank.node_last_updated_times.cpu().numpy(), o.last_upd.numpy())
+    pend = sorted(v for v, l in m.memory_bank.node_raw_messages.items() if len(l) > 0)
+    assert pend == sorted(v for v, l in o.msgs.items() if len(l) > 0) and len(pend) > 1000
+
+
+def test_tgn_train_prefix_sampler_with_full_size_bank():
+    """PTCL/EM_warmup.py:71: the train sampler is built from train_data only, so it may know fewer nodes than
+    the bank (one row per node of the full graph) has rows.  Batches inside the prefix work and match the
+    oracle; a node the sampler has no list for is the reference's IndexError."""
+    src, dst, eid, ts, nf, ef = cases.small_stream(num_nodes=60, num_edges=1200, seed=13, t_max=3.0e6)
+    cut = 600
+    keep = np.maximum(src[:cut], dst[:cut]) < 50
+    ps, pd, pe, pt = src[:cut][keep], dst[:cut][keep], eid[:cut][keep], ts[:cut][keep]
+    n_prefix = int(max(ps.max(), pd.max()))
+    assert n_prefix < nf.shape[0] - 1
+    p = otgn.default_params(172, 172, 100, 1, 2, seed=6, time_bias_scale=0.1)
+    s = make_sampler(ps, pd, pe, pt, n_prefix)
+    m = flid_b200.MemoryModel(nf, ef, s, 100, "TGN", 1, 2, 0.1, device=DEV).to(DEV)
+    m.load_state_dict({k: v for k, v in p.items() if not k.startswith("_")}, strict=False)
+    m.eval()
+    m.memory_bank.__init_memory_bank__()
+    o = otgn.OracleTGN(p, torch.from_numpy(nf), torch.from_numpy(ef),
+                       osamp.OracleSampler.from_events(ps, pd, pe, pt, n_prefix), 1, 10)
+    with torch.no_grad():
+        for lo in range(0, len(ps) - 40, 40):
+            sl = slice(lo, lo + 40)
+            a, c = m.compute_src_dst_node_temporal_embeddings(ps[sl], pd[sl], pt[sl], pe[sl], True, 10)
+            wa, wc = o.step(ps[sl], pd[sl], pt[sl], pe[sl], True)
+            assert_fp32_close(torch.cat([a, c]).cpu().numpy(), torch.cat([wa, wc]).numpy(), f"prefix batch {lo // 40}")
+        bad = np.array([nf.shape[0] - 1], dtype=np.int64)
+        with pytest.raises(IndexError):
+            m.compute_src_dst_node_temporal_embeddings(bad, ps[:1], pt[-1:], pe[:1], True, 10)
+
+
+def test_invalidate_caches_after_data_writes():
+    """``param.data`` writes do not bump autograd's version counter: an explicit invalidate picks them up,
+    and a rebuilt sampler never inherits the previous sampler's layer memo."""
+    src, dst, eid, ts, nf, ef = cases.small_stream()
+    p = otgat.default_params(172, 172, 100, 2, 2, seed=3)
+    m, s = tgat_pair(nf, ef, src, dst, eid, ts, 2, 2, p, True)
+    sel = np.arange(300, 340)
+    with torch.no_grad():
+        a0, _ = m.compute_src_dst_node_temporal_embeddings(src[sel], dst[sel], ts[sel], 5)
+        m.merge_layers[1].fc2.bias.data.add_(1.0)
+        m.invalidate_caches()
+        a1, _ = m.compute_src_dst_node_temporal_embeddings(src[sel], dst[sel], ts[sel], 5)
+        assert_fp32_close((a1 - a0).cpu().numpy(), np.ones_like(a0.cpu().numpy()), "bias shift after invalidate")
+        gens = {s.generation}
+        for _ in range(3):
+            s2 = make_sampler(src[:200], dst[:200], eid[:200], ts[:200], nf.shape[0] - 1)
+            assert s2.generation not in gens
+            gens.add(s2.generation)
+            m.set_neighbor_sampler(s2)
+            b1, _ = m.compute_src_dst_node_temporal_embeddings(src[sel], dst[sel], ts[sel], 5)
+            m.set_layer_memo(False)
+            b2, _ = m.compute_src_dst_node_temporal_embeddings(src[sel], dst[sel], ts[sel], 5)
+            m.set_layer_memo(True)
+            assert_fp32_close(b1.cpu().numpy(), b2.cpu().numpy(), "memo of a rebuilt sampler")
+            del s2
+
+
+def test_decoder_eval_mode_with_grad_keeps_the_graph():
+    dec = flid_b200.MLPClassifier(172, 0.1, 2).to(DEV)
+    dec.eval()
+    x = torch.randn(8, 172, device=DEV, requires_grad=True)
+    out = dec(x)
+    assert out.requires_grad
+    out.sum().backward()
+    assert x.grad is not None and float(x.grad.abs().sum()) > 0
+    with torch.no_grad():
+        fused = dec(x)
+    assert_fp32_close(fused.cpu().numpy(), out.detach().cpu().numpy(), "fused decoder vs torch path")
