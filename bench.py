@@ -382,13 +382,14 @@ class Bench:
         (host-side staging counts for the end-to-end number)."""
         self.sync_all()
         t0 = time.perf_counter()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        marks[0].record()
+        for i in range(steps):
             fn()
-        e1.record()
+            marks[i + 1].record()
         self.sync_all()
-        return e0.elapsed_time(e1), 1000.0 * (time.perf_counter() - t0)
+        self.last_step_ms = [marks[i].elapsed_time(marks[i + 1]) for i in range(steps)]
+        return marks[0].elapsed_time(marks[-1]), 1000.0 * (time.perf_counter() - t0)
 
     def max_over_ranks(self, *vals):
         t = torch.tensor(list(vals), dtype=torch.float64, device=self.dev)
@@ -507,7 +508,8 @@ def run_tgat(b, ci, cfg):
         clocks.start()
     _lib.check(lib.flid_tgat_profile(handle, 1))
     launches0 = lib.flid_launch_count()
-    ms_total, _ = b.timed(lambda: step_device(store), args.steps)
+    ms_total, wall_dev = b.timed(lambda: step_device(store), args.steps)
+    step_ms = list(b.last_step_ms)
     launches = lib.flid_launch_count() - launches0
     prof_ms = (ctypes.c_double * 4)()
     prof_n = (ctypes.c_int64 * 4)()
@@ -580,7 +582,7 @@ def run_tgat(b, ci, cfg):
                                   "each timed step), %d attention evaluations per step on rank 0 instead of %d"
                                   % (evals_l1 + evals_up, roots_loc * sum((1 + K_NBR) ** i for i in range(L))))
                    if use_memo else "off",
-                   "est_kept_fraction": kept,
+                   "est_kept_fraction": kept, "step_ms": step_ms, "wall_ms_per_step": wall_dev / args.steps,
                    "l2_policy": "inputs larger than L2 (edge feature table %.0f MB, %.0f MB of embeddings written "
                                 "per step; L2 is 126 MB)" % (g.edge_raw_features.nbytes / 1e6,
                                                                roots_per_step * DN * 4 / 1e6)},

@@ -4,7 +4,7 @@ Python API: ``NeighborSampler`` / ``get_neighbor_sampler``, ``TGAT``, ``MemoryMo
 ``libflid_b200.so`` (include/flid_b200.h); there is no CPU fallback.
 """
 from .sampler import NeighborSampler, get_neighbor_sampler  # noqa: F401
-from .tgat import TGAT, TimeEncoder, MultiHeadAttention, MergeLayer  # noqa: F401
+from .tgat import TGAT, TimeEncoder, MultiHeadAttention, MergeLayer, set_numeric_mode, get_numeric_mode  # noqa: F401
 from .memory_model import MemoryModel, MemoryBank  # noqa: F401
 from .graphmixer import GraphMixer  # noqa: F401
 from .tcl import TCL  # noqa: F401
@@ -12,4 +12,5 @@ from .pseudo_label import (MLPClassifier, emit_pseudo_labels, entropy_filter, pr
                            update_pseudo_labels)
 
 __all__ = ["NeighborSampler", "get_neighbor_sampler", "TGAT", "MemoryModel", "MemoryBank", "GraphMixer", "TCL", "MLPClassifier",
-           "emit_pseudo_labels", "entropy_filter", "prob_filter", "update_pseudo_labels"]
+           "emit_pseudo_labels", "entropy_filter", "prob_filter", "update_pseudo_labels", "set_numeric_mode",
+           "get_numeric_mode"]

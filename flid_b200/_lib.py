@@ -81,6 +81,9 @@ _SIGNATURES = {
                                        C.c_int64, C.c_int, c_void, c_void]),
     "flid_tgat_set_self_from_memo": (C.c_int, [c_void, C.c_int]),
     "flid_tgat_set_chunk_targets": (C.c_int, [c_void, C.c_int64]),
+    "flid_tgat_set_numeric_mode": (C.c_int, [c_void, C.c_int]),
+    "flid_tgat_bulk_invalidate": (C.c_int, [c_void]),
+    "flid_tgat_set_bulk_projection": (C.c_int, [c_void, C.c_int]),
     "flid_tgat_profile": (C.c_int, [c_void, C.c_int]),
     "flid_tgat_profile_read": (C.c_int, [c_void, C.POINTER(C.c_double), c_i64p]),
     "flid_tgat_last_stats": (C.c_int, [c_void, c_i64p]),

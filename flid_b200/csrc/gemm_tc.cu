@@ -41,7 +41,7 @@ namespace flid {
 // image layout: [n_block][k_chunk][half][c4][n_tile] float4
 // element (n, k) of the logical weight is W[n * sn + k * sk]: (ldw, 1) for W[N, K], (1, ldw) for a stored W^T[K, N]
 __global__ void tc_prep_kernel(const float* __restrict__ W, int64_t sn, int64_t sk, int N, int K, int n_tile,
-                               int n_blocks, int k_chunks, float4* __restrict__ out) {
+                               int n_blocks, int k_chunks, int single, float4* __restrict__ out) {
     const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t total = (int64_t)n_blocks * k_chunks * 2 * C4 * n_tile;
     if (idx >= total) return;
@@ -59,8 +59,8 @@ __global__ void tc_prep_kernel(const float* __restrict__ W, int64_t sn, int64_t 
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         const float x = (n < N && k + e < K) ? W[(int64_t)n * sn + (int64_t)(k + e) * sk] : 0.f;
-        const float hi = tf32_hi(x);
-        v[e] = half ? (x - hi) : hi;
+        const float hi = single ? bf16_round(x) : tf32_hi(x);
+        v[e] = half ? (single ? 0.f : x - hi) : hi;
     }
     out[idx] = make_float4(v[0], v[1], v[2], v[3]);
 }
@@ -71,6 +71,7 @@ struct TcShape {
     int acc_bufs;          // 2 when two accumulator sets fit in TMEM (epilogue overlaps the next group)
     uint32_t acc_stride;   // TMEM columns per accumulator set (MS * n_tile)
     int64_t m_groups;      // groups of MS * 128 rows
+    int single;            // TcWeight::single: one MMA per product on bf16-rounded operands
     int staged_epilogue;   // stage C through shared memory (pays off for long K loops and scattered rows)
     long long* trace;      // FLID_GEMM_TRACE (development): per-stage clock64 stamps of CTA 0, [6][TRACE_Q]
 };
@@ -177,8 +178,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(TcGemmArgs g, cons
 #pragma unroll
             for (int i = 0; i < NL; ++i) {
                 const float4 x = v[i];
-                const float4 hi = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
                 uint8_t* dst = st + (i >> 2) * A_SUB + (i & 3) * (32 * 16);  // sub-tile i / 4, rows (i % 4) * 32 + ...
+                if (sh.single) {
+                    *reinterpret_cast<float4*>(dst) = make_float4(bf16_round(x.x), bf16_round(x.y), bf16_round(x.z), bf16_round(x.w));
+                    continue;
+                }
+                const float4 hi = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
                 *reinterpret_cast<float4*>(dst) = hi;
                 *reinterpret_cast<float4*>(dst + A_HALF) = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
             }
@@ -330,11 +335,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(TcGemmArgs g, cons
                         const uint64_t d_ahi = umma_desc(a0, A_CSTRIDE, 128);
                         const uint64_t d_alo = umma_desc(a0 + A_HALF, A_CSTRIDE, 128);
                         const uint32_t d = d0 + ms * sh.n_tile;
+                        const uint64_t row_off = (uint64_t)((n_a * 16u) >> 4);  // start-address field is in 16 B units
+                        if (sh.single) {
+                            umma_tf32(d, d_ahi, d_bhi, idesc, (kc | j) ? 1u : 0u);
+                            if (n_b) umma_tf32(d + n_a, d_ahi, d_bhi + row_off, idesc_b, (kc | j) ? 1u : 0u);
+                            continue;
+                        }
                         umma_tf32(d, d_alo, d_bhi, idesc, (kc | j) ? 1u : 0u);  // small terms first
                         umma_tf32(d, d_ahi, d_blo, idesc, 1u);
                         umma_tf32(d, d_ahi, d_bhi, idesc, 1u);
                         if (n_b) {  // second column group: weight rows n_a.. of the same chunk (16 B per row)
-                            const uint64_t row_off = (uint64_t)((n_a * 16u) >> 4);  // start-address field is in 16 B units
                             umma_tf32(d + n_a, d_alo, d_bhi + row_off, idesc_b, (kc | j) ? 1u : 0u);
                             umma_tf32(d + n_a, d_ahi, d_blo + row_off, idesc_b, 1u);
                             umma_tf32(d + n_a, d_ahi, d_bhi + row_off, idesc_b, 1u);
@@ -360,8 +370,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(TcGemmArgs g, cons
                 TRACE(5, tq);
                 ++tq;
                 uint8_t* st = smem + (size_t)s * stage_bytes + MS * A_SUB;
-                mbar_arrive_expect_tx(&bar_full[s], 2 * b_half);
-                bulk_g2s(st, wsrc + kc * chunk4, 2 * b_half, &bar_full[s]);
+                const uint32_t wbytes = sh.single ? b_half : 2 * b_half;  // the lo half is not used by a single-MMA product
+                mbar_arrive_expect_tx(&bar_full[s], wbytes);
+                bulk_g2s(st, wsrc + kc * chunk4, wbytes, &bar_full[s]);
                 if (++s == (uint32_t)sh.stages) s = 0, ph ^= 1;
             }
         }
@@ -384,7 +395,8 @@ static int pick_n_tile(int N) {
     return t < 16 ? 16 : t;
 }
 
-static int prepare_weight(const float* W, int64_t sn, int64_t sk, int N, int K, TcWeight* w, cudaStream_t st) {
+static int prepare_weight(const float* W, int64_t sn, int64_t sk, int N, int K, TcWeight* w, cudaStream_t st,
+                          int single = 0) {
     FLID_REQUIRE(W && w && N > 0 && K > 0, "tc_prepare_weight: bad argument");
     const int n_tile = pick_n_tile(N);
     const int n_blocks = (N + n_tile - 1) / n_tile;
@@ -394,17 +406,17 @@ static int prepare_weight(const float* W, int64_t sn, int64_t sk, int N, int K, 
         FLID_CUDA(cudaFree(w->buf));
         w->buf = nullptr;
     }
-    w->N = N, w->K = K, w->n_tile = n_tile, w->n_blocks = n_blocks, w->k_chunks = k_chunks;
+    w->N = N, w->K = K, w->n_tile = n_tile, w->n_blocks = n_blocks, w->k_chunks = k_chunks, w->single = single;
     if (!w->buf) FLID_CUDA(cudaMalloc((void**)&w->buf, w->bytes()));
     const int64_t total = (int64_t)n_blocks * k_chunks * 2 * C4 * n_tile;
-    tc_prep_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(W, sn, sk, N, K, n_tile, n_blocks, k_chunks,
+    tc_prep_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(W, sn, sk, N, K, n_tile, n_blocks, k_chunks, single,
                                                                   reinterpret_cast<float4*>(w->buf));
     FLID_LAUNCH_CHECK();
     return FLID_OK;
 }
 
-int tc_prepare_weight(const float* W, int64_t ldw, int N, int K, TcWeight* w, cudaStream_t st) {
-    return prepare_weight(W, ldw, 1, N, K, w, st);
+int tc_prepare_weight(const float* W, int64_t ldw, int N, int K, TcWeight* w, cudaStream_t st, int single) {
+    return prepare_weight(W, ldw, 1, N, K, w, st, single);
 }
 
 int tc_prepare_weight_t(const float* Wt, int64_t ldw, int N, int K, TcWeight* w, cudaStream_t st) {
@@ -477,7 +489,7 @@ int tc_gemm(const TcGemmArgs& g, const TcWeight& w, cudaStream_t st) {
         cudaMemsetAsync(d_trace, 0, sizeof(long long) * 6 * TRACE_Q, st);
         sh.trace = d_trace;
     }
-    sh.N = w.N, sh.n_tile = w.n_tile, sh.n_blocks = w.n_blocks, sh.k_chunks = w.k_chunks;
+    sh.N = w.N, sh.n_tile = w.n_tile, sh.n_blocks = w.n_blocks, sh.k_chunks = w.k_chunks, sh.single = w.single;
     // Sub-tiles per work item.  Measured on the B200 (tools/gemm_probe.py, M = 65 536): sharing a
     // weight stage between two sub-tiles halves the weight traffic but was 10-25 % slower on every
     // shape (accumulators can no longer be double-buffered, so the epilogue is exposed, and the

@@ -16,6 +16,11 @@ constexpr int TC_KC = 16;  // K floats per pipeline stage (2 UMMA k-steps of 8)
 struct TcWeight {
     float* buf = nullptr;
     int N = 0, K = 0, n_tile = 0, n_blocks = 0, k_chunks = 0;
+    // 0: fp32-grade product (3xTF32: hi/lo split of both operands, three MMAs per product)
+    // 1: "bf16 projections" numeric mode: both operands rounded to bfloat16 (round-to-nearest-even; a bf16 value is
+    //    exactly representable in tf32), one MMA per product, fp32 accumulation -- the arithmetic of a bf16-in /
+    //    fp32-acc GEMM on the same tensor pipe, with a third of the MMAs and half of the operand traffic
+    int single = 0;
     size_t bytes() const { return (size_t)n_blocks * k_chunks * 2 * (TC_KC / 4) * n_tile * 16; }
 };
 
@@ -37,7 +42,7 @@ struct TcGemmArgs {
 };
 
 // (re)build the tiled hi/lo image of W[N, K] (row stride ldw); allocates w->buf on first use
-int tc_prepare_weight(const float* W, int64_t ldw, int N, int K, TcWeight* w, cudaStream_t st);
+int tc_prepare_weight(const float* W, int64_t ldw, int N, int K, TcWeight* w, cudaStream_t st, int single = 0);
 // same for a weight stored transposed, Wt[K, N] (row stride ldw): the data-gradient GEMMs of train_layer.cu
 int tc_prepare_weight_t(const float* Wt, int64_t ldw, int N, int K, TcWeight* w, cudaStream_t st);
 void tc_free_weight(TcWeight* w);

@@ -48,6 +48,7 @@ struct TsShape {
     int acc_bufs;          // accumulator sets in TMEM (the A ring takes the remaining columns)
     uint32_t acc_stride;   // TMEM columns per accumulator set (= n_tile)
     int staged_epilogue;
+    int single;            // TcWeight::single: one MMA per product on bf16-rounded operands
     int64_t m_groups;      // 128-row tiles
     long long* trace;      // unused (kept so that the shared code compiles unchanged)
 };
@@ -141,11 +142,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_ts_kernel(TcGemmArgs g, c
             for (int i = 0; i < 4; ++i) {
                 const float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
 #pragma unroll
-                for (int e = 0; e < 4; ++e) hi[4 * i + e] = tf32_hi(x[e]), lo[4 * i + e] = x[e] - hi[4 * i + e];
+                for (int e = 0; e < 4; ++e) {
+                    hi[4 * i + e] = sh.single ? bf16_round(x[e]) : tf32_hi(x[e]);
+                    lo[4 * i + e] = x[e] - hi[4 * i + e];
+                }
             }
             const uint32_t taddr = tmem + a_cols + stage * 32u + ((uint32_t)(pw * 32) << 16);
             tmem_st16(taddr, hi);
-            tmem_st16(taddr + 16u, lo);
+            if (!sh.single) tmem_st16(taddr + 16u, lo);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
             mbar_arrive(&bar_full[stage]);
@@ -288,6 +292,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_ts_kernel(TcGemmArgs g, c
                     const uint64_t d_bhi = umma_desc(sb + (2 * j) * b_lbo, b_lbo, 128);
                     const uint64_t d_blo = umma_desc(sb + b_half + (2 * j) * b_lbo, b_lbo, 128);
                     const uint32_t a_hi = ta + 8u * j, a_lo = a_hi + 16u;
+                    if (sh.single) {
+                        umma_tf32_ts(d0, a_hi, d_bhi, idesc, (kc | j) ? 1u : 0u);
+                        if (n_b) umma_tf32_ts(d0 + n_a, a_hi, d_bhi + (uint64_t)((n_a * 16u) >> 4), idesc_b, (kc | j) ? 1u : 0u);
+                        continue;
+                    }
                     umma_tf32_ts(d0, a_lo, d_bhi, idesc, (kc | j) ? 1u : 0u);  // small terms first
                     umma_tf32_ts(d0, a_hi, d_blo, idesc, 1u);
                     umma_tf32_ts(d0, a_hi, d_bhi, idesc, 1u);
@@ -313,8 +322,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_ts_kernel(TcGemmArgs g, c
             for (int kc = 0; kc < sh.k_chunks; ++kc) {
                 mbar_wait(&bar_empty[s], ph ^ 1);
                 uint8_t* st = smem + (size_t)s * stage_bytes;
-                mbar_arrive_expect_tx(&bar_full[s], 2 * b_half);
-                bulk_g2s(st, wsrc + kc * chunk4, 2 * b_half, &bar_full[s]);
+                const uint32_t wbytes = sh.single ? b_half : 2 * b_half;  // the lo half is not used by a single-MMA product
+                mbar_arrive_expect_tx(&bar_full[s], wbytes);
+                bulk_g2s(st, wsrc + kc * chunk4, wbytes, &bar_full[s]);
                 if (++s == (uint32_t)sh.stages) s = 0, ph ^= 1;
             }
         }
@@ -333,7 +343,7 @@ int tc_gemm_ts(const TcGemmArgs& g, const TcWeight& w, int sm_count, int smem_ma
     }
     TsShape sh;
     sh.trace = nullptr;
-    sh.N = w.N, sh.n_tile = w.n_tile, sh.n_blocks = w.n_blocks, sh.k_chunks = w.k_chunks;
+    sh.N = w.N, sh.n_tile = w.n_tile, sh.n_blocks = w.n_blocks, sh.k_chunks = w.k_chunks, sh.single = w.single;
     sh.m_groups = ceil_div(g.M, 128);
     sh.acc_stride = (uint32_t)w.n_tile;
     // two accumulator sets when that still leaves >= 4 stages of A columns, else one

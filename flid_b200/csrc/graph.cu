@@ -316,7 +316,7 @@ int flid_graph_build_entries(const int64_t* owner, const int64_t* nbr, const int
 
 void flid_graph_free(flid_graph* g) {
     if (!g) return;
-    cudaFree(g->indptr), cudaFree(g->adj), cudaFree(g->ts), cudaFree(g->mirror), cudaFree(g->bad_flag);
+    cudaFree(g->indptr), cudaFree(g->adj), cudaFree(g->ts), cudaFree(g->mirror), cudaFree(g->bad_flag), cudaFree(g->owner), cudaFree(g->ent_eid);
     delete g;
 }
 

@@ -12,6 +12,10 @@ struct flid_graph {
     int32_t* mirror = nullptr;  // [M] position of the same event's entry in the other endpoint's list
                                 // (graphs built from events with M < 2^31 only, else null)
     int* bad_flag = nullptr;    // device int, zero between calls: out-of-range query ids of the sampler entry points
+    // derived arrays of the projected bulk path (bulk_kv.cu), built on first use
+    int32_t* owner = nullptr;   // [M] node whose list holds the entry
+    int32_t* ent_eid = nullptr; // [M + 1] edge id of the entry (row M: the padded slot, edge 0)
+    int64_t max_eid = -1;       // largest edge id in the adjacency (rows of the per-edge tables)
 };
 
 namespace flid {

@@ -1,4 +1,4 @@
-// Constants and PTX wrappers shared by the tcgen05 GEMM kernels (gemm_tc.cu, gemm_tc_pair.cu).
+// Constants and PTX wrappers shared by the tcgen05 GEMM kernels (gemm_tc.cu, gemm_tc_ts.cu).
 #pragma once
 #include "gemm_tc.cuh"
 
@@ -90,5 +90,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 }
 
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+// float32 -> bfloat16 (round to nearest even) -> float32; finite inputs
+__device__ __forceinline__ float bf16_round(float x) {
+    uint32_t u = __float_as_uint(x);
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return __uint_as_float(u & 0xffff0000u);
+}
 
 }  // namespace flid

@@ -267,12 +267,14 @@ static int query_fold(flid_tgat* m, int layer, const float* feat, const int32_t*
 // +residual -> LayerNorm -> MergeLayer.  self rows: layer-(l-1) features of the targets.
 static int output_chain(flid_tgat* m, int layer, int64_t n, const float* Z, const float* self_base,
                         const int32_t* self_idx, const float* merge_feat, const int32_t* ids, float* O, float* A,
-                        float* Hd, float* out, const int32_t* out_idx, cudaStream_t st) {
+                        float* Hd, float* out, const int32_t* out_idx, cudaStream_t st, bool kv = false) {
     const LayerDev& ld = m->layers[layer];
     if (m->use_tc) {
         TcGemmArgs t1;
-        t1.A0 = Z, t1.lda0 = m->zw, t1.w0 = m->zw, t1.C = O, t1.ldc = m->qd, t1.bias = ld.res_b, t1.M = n;
-        FLID_TRY(tc_gemm(t1, ld.tc_o, st));
+        // kv: Z is the projected stream's output [sum a V | sum a te per head] (bulk_kv.cu), qd + H T wide
+        const int zw = kv ? m->qd + m->H * m->T : m->zw;
+        t1.A0 = Z, t1.lda0 = zw, t1.w0 = zw, t1.C = O, t1.ldc = m->qd, t1.bias = ld.res_b, t1.M = n;
+        FLID_TRY(tc_gemm(t1, kv ? ld.tc_o2 : ld.tc_o, st));
         FLID_TRY(launch_ln(O, self_base, self_idx, m->te0, ld.ln_w, ld.ln_b, A, n, m->dn, m->T, st));
         TcGemmArgs t2;   // fc1 on [attention output | layer-0 row of the target], ReLU fused
         t2.A0 = A, t2.lda0 = m->qd, t2.w0 = m->qd, t2.A1 = merge_feat, t2.lda1 = m->dn, t2.idx1 = ids, t2.w1 = m->dn;
@@ -450,6 +452,7 @@ struct LayerCall {
     bool u_from_table = false;         // layer 1 with the cached per-node query fold
     float* out = nullptr;              // [n, dn]
     const int32_t* out_idx = nullptr;  // nullable: row i is written to out + out_idx[i] * dn
+    bool kv = false;                   // projected bulk path (bulk_kv.cu); needs pos, eid and the level's tables
 };
 
 // one attention layer (1-based `layer`) for n targets: query fold -> stream -> out chain
@@ -457,12 +460,22 @@ static int layer_eval(flid_tgat* m, int layer, const LayerCall& c, const float* 
                       int k, cudaStream_t st) {
     float *U = m->ws_u.as<float>(), *Z = m->ws_z.as<float>(), *O = m->ws_o.as<float>(), *A = m->ws_a.as<float>(),
           *Hd = m->ws_hd.as<float>();
+    if (c.kv) {
+        KvCall kc;
+        kc.level = layer, kc.n = c.n, kc.ids = c.ids, kc.self_base = c.self_base, kc.self_idx = c.self_idx;
+        kc.nbr = c.nbr, kc.eid = c.eid, kc.pos = c.pos, kc.dt = c.dt, kc.U = U, kc.Y = Z;
+        FLID_TRY(kv_attention(m, kc, k, st));
+        ProfScope prof(m, PROF_OUT, st);
+        return output_chain(m, layer - 1, c.n, Z, c.self_base, c.self_idx, node_feat, c.ids, O, A, Hd, c.out, c.out_idx, st,
+                            true);
+    }
     AttnArgs a;
     a.edge_feat = edge_feat;
     a.nbr = c.nbr, a.eid = c.eid, a.dt = c.dt;
     a.time_w = m->time_w, a.time_b = m->time_b, a.time_bound = m->time_bound;
     a.z = Z, a.n = c.n, a.k = k, a.dn = m->dn, a.de = m->de, a.T = m->T;
-    a.hrow_base = c.hrow_base, a.hrow_by_id = c.pos ? 0 : 1, a.hrow_offset = 0, a.hrow_idx = c.pos;
+    const bool by_pos = c.pos != nullptr && layer > 1;  // level 1 rows are node-table rows even when positions were sampled
+    a.hrow_base = c.hrow_base, a.hrow_by_id = by_pos ? 0 : 1, a.hrow_offset = 0, a.hrow_idx = by_pos ? c.pos : nullptr;
     if (c.u_from_table) {
         a.u_base = m->table.as<float>(), a.u_index = c.ids;
     } else {
@@ -494,6 +507,26 @@ static int reserve_layer_ws(flid_tgat* m, int64_t n, int k, bool need_u) {
     return FLID_OK;
 }
 
+// enough free device memory for the projected tables of `level` (already allocated ones count as fitting)?
+static bool kv_tables_fit(flid_tgat* m, const flid_graph* g, int level) {
+    size_t need = 0;
+    const size_t M1 = (size_t)g->num_entries + 1;
+    if (level == 1) {
+        // per-node V, per-edge V (at most one row per entry), per-entry scores
+        const size_t want = sizeof(float) * ((size_t)(m->table_rows > 0 ? m->table_rows : 1) * m->qd + M1 * m->qd + M1 * m->H);
+        const size_t have = m->kv_vn1.cap + m->kv_ve1.cap + m->kv_s1.cap;
+        need = want > have ? want - have : 0;
+    } else {
+        const size_t want = sizeof(float) * M1 * 2 * m->qd;
+        const size_t have = (int)m->kv_tab.size() > level - 2 ? m->kv_tab[level - 2].cap : 0;
+        need = want > have ? want + want / 8 : 0;
+    }
+    if (need == 0) return true;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return false;
+    return need + (size_t(2) << 30) < free_b;   // keep 2 GiB of headroom for the caller's own tensors
+}
+
 int tgat_memo_build(flid_tgat* m, const flid_graph* g, const float* node_feat, const float* edge_feat, int k, int level,
                     const float* memo_prev, int64_t row_lo, int64_t row_hi, float* memo_out, cudaStream_t st) {
     const int64_t M = g->num_entries;
@@ -509,6 +542,15 @@ int tgat_memo_build(flid_tgat* m, const flid_graph* g, const float* node_feat, c
     // sharded build) keeps table order so that its output stays one contiguous block.
     const bool owner_major = g->mirror != nullptr && row_lo == 0 && row_hi == M + 1;
     if (owner_major) FLID_TRY(m->ws_self.reserve(sizeof(int32_t) * std::min(chunk, row_hi - row_lo)));
+    // projected bulk path (bulk_kv.cu): every entry is a slot of up to k targets of this build, so the per-entry
+    // projections pay off; level 1 needs the cached per-node query table
+    bool kv = kv_supported(m) && (level > 1 || use_table) && kv_tables_fit(m, g, level);
+    if (kv) {
+        if (level == 1)
+            FLID_TRY(kv_ensure_level1(m, g, node_feat, edge_feat, st));
+        else
+            FLID_TRY(kv_ensure_level(m, g, level, memo_prev, node_feat, edge_feat, st));
+    }
     int32_t* w_rows = owner_major ? m->ws_self.as<int32_t>() : nullptr;
     int64_t evals = 0;
     for (int64_t c0 = row_lo; c0 < row_hi; c0 += chunk) {
@@ -520,15 +562,17 @@ int tgat_memo_build(flid_tgat* m, const flid_graph* g, const float* node_feat, c
             FLID_LAUNCH_CHECK();
             level_sample_kernel<<<(unsigned)ceil_div(n * LS_W, 256), 256, 0, st>>>(
                 g->indptr, g->adj, g->ts, w_ids, w_times, n, 0, k, m->ws_nbr.as<int32_t>(), m->ws_eid.as<int32_t>(),
-                m->ws_dt.as<float>(), nullptr, nullptr, level > 1 ? m->ws_pos.as<int32_t>() : nullptr, (int32_t)M,
+                m->ws_dt.as<float>(), nullptr, nullptr, (level > 1 || kv) ? m->ws_pos.as<int32_t>() : nullptr, (int32_t)M,
                 nullptr, nullptr, d_valid);
             FLID_LAUNCH_CHECK();
         }
         LayerCall c;
+        c.kv = kv;
         c.n = n, c.ids = w_ids;
         c.nbr = m->ws_nbr.as<int32_t>(), c.eid = m->ws_eid.as<int32_t>(), c.dt = m->ws_dt.as<float>();
         if (level == 1) {
             c.hrow_base = node_feat, c.self_base = node_feat, c.self_idx = w_ids, c.u_from_table = use_table;
+            if (kv) c.pos = m->ws_pos.as<int32_t>();
         } else {
             c.pos = m->ws_pos.as<int32_t>();
             c.hrow_base = memo_prev;
@@ -560,6 +604,14 @@ int tgat_embed_memo(flid_tgat* m, const flid_graph* g, const float* node_feat, c
     const bool try_self = L > 1 && g->mirror != nullptr && m->self_from_memo;
     const int64_t chunk = std::max<int64_t>(1, m->max_l1_targets);
     const int64_t nmax = std::min(chunk, n);
+    // projected bulk path: worth building the per-entry tables when the call's slots outnumber the entries
+    // (a bulk pass); per-batch calls keep the x-space stream
+    bool kv = kv_supported(m) && use_table && n * (int64_t)k >= M && M > 0;
+    for (int l = 2; l <= L && kv; ++l) kv = kv_tables_fit(m, g, l);
+    if (kv) {
+        for (int l = 2; l <= L; ++l) FLID_TRY(kv_ensure_level(m, g, l, memo[l - 2], node_feat, edge_feat, st));
+    }
+    bool kv_l1_ready = false;
     FLID_TRY(reserve_layer_ws(m, nmax, k, L > 1 || !use_table));
     if (L > 1) FLID_TRY(m->ws_h.reserve(sizeof(float) * 2 * nmax * m->dn));
     if (try_self) FLID_TRY(m->ws_self.reserve(sizeof(int32_t) * nmax));
@@ -577,7 +629,7 @@ int tgat_embed_memo(flid_tgat* m, const flid_graph* g, const float* node_feat, c
             level_sample_kernel<<<(unsigned)ceil_div(nc * LS_W, 256), 256, 0, st>>>(
                 g->indptr, g->adj, g->ts, ids + r0, times + r0, nc, nf, k, m->ws_nbr.as<int32_t>(),
                 m->ws_eid.as<int32_t>(), m->ws_dt.as<float>(), nullptr, nullptr,
-                L > 1 ? m->ws_pos.as<int32_t>() : nullptr, (int32_t)M, try_self ? g->mirror : nullptr,
+                (L > 1 || kv) ? m->ws_pos.as<int32_t>() : nullptr, (int32_t)M, try_self ? g->mirror : nullptr,
                 try_self ? m->ws_self.as<int32_t>() : nullptr, d_cnt);
             FLID_LAUNCH_CHECK();
         }
@@ -590,12 +642,18 @@ int tgat_embed_memo(flid_tgat* m, const flid_graph* g, const float* node_feat, c
         const bool all_in_memo = try_self && h_cnt[1] == h_prev[1];
         h_prev[0] = h_cnt[0], h_prev[1] = h_cnt[1];
         float* hbuf[2] = {m->ws_h.as<float>(), L > 1 ? m->ws_h.as<float>() + nmax * m->dn : nullptr};
+        if (kv && !all_in_memo && !kv_l1_ready) {
+            FLID_TRY(kv_ensure_level1(m, g, node_feat, edge_feat, st));
+            kv_l1_ready = true;
+        }
         for (int l = all_in_memo ? L : 1; l <= L; ++l) {
             LayerCall c;
+            c.kv = kv;
             c.n = nc, c.ids = ids + r0;
             c.nbr = m->ws_nbr.as<int32_t>(), c.eid = m->ws_eid.as<int32_t>(), c.dt = m->ws_dt.as<float>();
             if (l == 1) {
                 c.hrow_base = node_feat, c.self_base = node_feat, c.self_idx = ids + r0, c.u_from_table = use_table;
+                if (kv) c.pos = m->ws_pos.as<int32_t>();
             } else {
                 c.pos = m->ws_pos.as<int32_t>();
                 c.hrow_base = memo[l - 2];
@@ -642,6 +700,8 @@ int flid_tgat_create(int node_dim, int edge_dim, int time_dim, int num_layers, i
     m->use_tc = !(mode && strcmp(mode, "simt") == 0);
     const char* sm = getenv("FLID_SELF_MEMO");
     m->self_from_memo = !(sm && sm[0] == '0');
+    const char* kvv = getenv("FLID_BULK_KV");
+    m->kv_enabled = !(kvv && kvv[0] == '0');
     const char* so = getenv("FLID_SORT_QUERIES");
     m->sort_bulk_queries = !(so && so[0] == '0');
     if (const char* ct = getenv("FLID_CHUNK_TARGETS"))   // development knob, same as flid_tgat_set_chunk_targets
@@ -658,7 +718,10 @@ void flid_tgat_free(flid_tgat* m) {
         cudaFree(l.fc1_w), cudaFree(l.fc1_b), cudaFree(l.fc2_w), cudaFree(l.fc2_b);
         flid::tc_free_weight(&l.tc_q), flid::tc_free_weight(&l.tc_o), flid::tc_free_weight(&l.tc_f1);
         flid::tc_free_weight(&l.tc_f2);
+        flid::kv_free_layer(l);
     }
+    m->kv_vn1.release(), m->kv_ve1.release(), m->kv_s1.release();
+    for (auto& t : m->kv_tab) t.release();
     for (auto e : m->prof_ev) cudaEventDestroy(e);
     flid::DevBuf* bufs[] = {&m->raw_q, &m->raw_k, &m->raw_v, &m->raw_r, &m->table, &m->ws_ids, &m->ws_times,
                             &m->ws_nbr, &m->ws_eid, &m->ws_dt, &m->ws_h, &m->ws_u, &m->ws_z, &m->ws_o,
@@ -706,11 +769,13 @@ int flid_tgat_set_weights(flid_tgat* m, const float* time_w, const float* time_b
         FLID_TRY(dev_copy(&d.fc1_b, w.fc1_b, dn, st));
         FLID_TRY(dev_copy(&d.fc2_w, w.fc2_w, (size_t)dn * dn, st));
         FLID_TRY(dev_copy(&d.fc2_b, w.fc2_b, dn, st));
-        FLID_TRY(tc_prepare_weight(d.mfoldT, qd, zw, dn, &d.tc_q, st));
-        FLID_TRY(tc_prepare_weight(d.wvoT, zw, qd, zw, &d.tc_o, st));
-        FLID_TRY(tc_prepare_weight(d.fc1_w, qd + dn, dn, qd + dn, &d.tc_f1, st));
-        FLID_TRY(tc_prepare_weight(d.fc2_w, dn, dn, dn, &d.tc_f2, st));
+        FLID_TRY(tc_prepare_weight(d.mfoldT, qd, zw, dn, &d.tc_q, st, m->numeric));
+        FLID_TRY(tc_prepare_weight(d.wvoT, zw, qd, zw, &d.tc_o, st, m->numeric));
+        FLID_TRY(tc_prepare_weight(d.fc1_w, qd + dn, dn, qd + dn, &d.tc_f1, st, m->numeric));
+        FLID_TRY(tc_prepare_weight(d.fc2_w, dn, dn, dn, &d.tc_f2, st, m->numeric));
+        FLID_TRY(kv_fold_layer(m, l, w.query_w, w.key_w, w.value_w, w.res_w, st));
     }
+    m->weights_version += 1;
     m->have_weights = true;
     m->table_src = nullptr;  // cached query folds are stale now
     m->table_rows = 0;
@@ -844,6 +909,16 @@ int flid_tgat_set_self_from_memo(flid_tgat* m, int enable) {
     using namespace flid;
     FLID_REQUIRE(m != nullptr, "flid_tgat_set_self_from_memo: null handle");
     m->self_from_memo = enable != 0;
+    return FLID_OK;
+}
+
+int flid_tgat_set_numeric_mode(flid_tgat* m, int mode) {
+    using namespace flid;
+    FLID_REQUIRE(m != nullptr, "flid_tgat_set_numeric_mode: null handle");
+    FLID_REQUIRE(mode == 0 || mode == 1, "flid_tgat_set_numeric_mode: mode must be 0 (f32) or 1 (bf16 projections)");
+    FLID_REQUIRE(mode == 0 || m->use_tc, "flid_tgat_set_numeric_mode: the bf16 mode needs the tcgen05 GEMMs (FLID_GEMM=simt is set)");
+    if (m->numeric != mode) m->have_weights = false;  // the tiled weight images are per mode
+    m->numeric = mode;
     return FLID_OK;
 }
 

@@ -14,6 +14,15 @@ struct LayerDev {
     float *res_b = nullptr, *ln_w = nullptr, *ln_b = nullptr;              // [qd]
     float *fc1_w = nullptr, *fc1_b = nullptr, *fc2_w = nullptr, *fc2_b = nullptr;  // merge layer, reference layout
     TcWeight tc_q, tc_o, tc_f1, tc_f2;  // hi/lo-split, tiled images for the tcgen05 GEMM
+    // projected bulk path (bulk_kv.cu): per-entry K/V rows instead of per-slot raw rows.  Row layouts are
+    // head-interleaved (kv_perm) so that a lane of the stream kernel only ever touches its own head.
+    float* kvw = nullptr;     // one allocation holding the small fp32 matrices below
+    float *wqs = nullptr, *cqs = nullptr;  // [qd, dn], [qd]   qs = scale * Wq [h | te0]      (level >= 2 targets)
+    float *wut = nullptr, *cut = nullptr;  // [H*T, dn], [H*T] time part of the folded query
+    float *wk2 = nullptr, *wv2 = nullptr;  // [qd, dn+de]      K / V of [h_{l-1} | e]          (level >= 2 entries)
+    float *wvn = nullptr, *wve = nullptr;  // [qd, dn], [qd, de]  V of node / edge rows          (level 1)
+    float* wo2 = nullptr;                  // [qd, qd + H*T]   residual_fc on [sum a V | Wv_t sum a te]
+    TcWeight tc_qs, tc_ut, tc_k2, tc_v2, tc_vn, tc_ve, tc_o2;
 };
 }  // namespace flid
 
@@ -21,6 +30,7 @@ struct flid_tgat {
     int dn = 0, de = 0, T = 0, L = 0, H = 0;
     int qd = 0, kd = 0, hd = 0, zw = 0;  // zw = H * kd
     bool have_weights = false;
+    int numeric = 0;     // flid_tgat_set_numeric_mode: 0 fp32-grade (3xTF32), 1 bf16-rounded operands / one MMA per product
     bool use_tc = true;  // projection GEMMs on tcgen05 (3xTF32); false = fp32 SIMT (FLID_GEMM=simt)
     float *time_w = nullptr, *time_b = nullptr, *te0 = nullptr, *time_bound = nullptr;
     std::vector<flid::LayerDev> layers;
@@ -38,6 +48,22 @@ struct flid_tgat {
     bool self_from_memo = true;  // roots that are graph events read their own lower layers from the memo (FLID_SELF_MEMO=0 disables)
     flid::DevBuf ws_ids, ws_times, ws_nbr, ws_eid, ws_dt, ws_h, ws_u, ws_z, ws_o, ws_a, ws_hd, ws_misc, ws_pos, ws_self, ws_sort;
     flid::DevBuf ws_rid, ws_rt, ws_bad;  // root conversion staging
+    // projected bulk path: tables derived from (weights, graph, feature tables[, memo of the level below])
+    bool kv_enabled = true;             // FLID_BULK_KV=0 disables (A/B timing)
+    uint64_t weights_version = 0;       // bumped by flid_tgat_set_weights
+    uint64_t bulk_epoch = 0;            // bumped by flid_tgat_bulk_invalidate (the caller rebuilt a memo table)
+    struct KvKey {
+        uint64_t wv = 0, epoch = 0;
+        const void *g = nullptr, *nf = nullptr, *ef = nullptr, *memo = nullptr;
+        int64_t entries = -1;
+        bool operator==(const KvKey& o) const {
+            return wv == o.wv && epoch == o.epoch && g == o.g && nf == o.nf && ef == o.ef && memo == o.memo && entries == o.entries;
+        }
+    };
+    KvKey kv_l1_key;
+    flid::DevBuf kv_vn1, kv_ve1, kv_s1;             // level 1: V of node rows [N+1, qd], V of edge rows [max_eid+1, qd], scores [M+1, H]
+    std::vector<flid::DevBuf> kv_tab;               // level l >= 2 (index l-2): [M+1, 2*qd] = [K | V] of entry p
+    std::vector<KvKey> kv_tab_key;
     flid::DevBuf tgn_ids, tgn_times, tgn_eids, tgn_gi, tgn_gh;  // TGN step scratch (tgn.cu): per handle, hence per device
     int64_t stats[4] = {0, 0, 0, 0};
     int64_t valid_mult = 1;  // attention evaluations that consume each sampled neighbour list
@@ -54,6 +80,28 @@ namespace flid {
 int tgat_embed_ids(flid_tgat* m, const flid_graph* g, const float* node_feat, const float* edge_feat,
                    const int32_t* ids, const double* times, int64_t n_f64, int64_t n, int k, float* out,
                    cudaStream_t st);
+
+// ---- projected bulk path (bulk_kv.cu)
+bool kv_supported(const flid_tgat* m);
+int kv_fold_layer(flid_tgat* m, int l, const float* wq, const float* wk, const float* wv, const float* wr, cudaStream_t st);
+void kv_free_layer(LayerDev& d);
+// level-1 tables (V of node / edge rows, per-entry scores against the owner's folded query); needs the cached node table
+int kv_ensure_level1(flid_tgat* m, const flid_graph* g, const float* node_feat, const float* edge_feat, cudaStream_t st);
+// level >= 2: K/V rows of every adjacency entry from the memo of the level below
+int kv_ensure_level(flid_tgat* m, const flid_graph* g, int level, const float* memo_prev, const float* node_feat,
+                    const float* edge_feat, cudaStream_t st);
+struct KvCall {
+    int level = 1;
+    int64_t n = 0;
+    const int32_t* ids = nullptr;       // level 1: node ids of the targets (rows of the cached query table)
+    const float* self_base = nullptr;   // level >= 2: layer-(l-1) rows of the targets
+    const int32_t* self_idx = nullptr;
+    const int32_t *nbr = nullptr, *eid = nullptr, *pos = nullptr;
+    const float* dt = nullptr;
+    float *U = nullptr, *Y = nullptr;   // workspaces: [n, qd + H*T] each
+};
+// query side (level >= 2: two GEMMs) + stream kernel; Y = [sum a V (interleaved) | sum a te per head]
+int kv_attention(flid_tgat* m, const KvCall& c, int k, cudaStream_t st);
 
 // classes for the event timer
 enum { PROF_SAMPLE = 0, PROF_QFOLD = 1, PROF_ATTN = 2, PROF_OUT = 3, PROF_CLASSES = 4 };

@@ -12,6 +12,7 @@ neighbourhoods (the same bit-exact kernel), the attention stream as a CUDA kerne
 hand-written backward kernel, and torch matmuls for the dense projections.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -20,6 +21,27 @@ import torch.nn as nn
 from . import _lib
 from .sampler import NeighborSampler
 from .train import autograd_forward
+
+
+NUMERIC_MODES = {"f32": 0, "bf16": 1}
+_numeric_mode = os.environ.get("FLID_NUMERIC", "f32")
+if _numeric_mode not in NUMERIC_MODES:
+    raise ValueError(f"FLID_NUMERIC must be one of {sorted(NUMERIC_MODES)}, got {_numeric_mode!r}")
+
+
+def set_numeric_mode(mode: str = "f32"):
+    """Numeric mode of the projection GEMMs of every flid_b200 model in this process (BASELINE.json north_star):
+    "f32" (default): fp32-grade products, embeddings within fp32 rel 1e-4 of the reference;
+    "bf16": operands rounded to bfloat16, fp32 accumulation (rel 2e-2, identical argmax on >= 99.9 % of nodes).
+    Models pick the change up at their next call (weights are re-tiled, derived caches dropped)."""
+    global _numeric_mode
+    if mode not in NUMERIC_MODES:
+        raise ValueError(f"numeric mode must be one of {sorted(NUMERIC_MODES)}, got {mode!r}")
+    _numeric_mode = mode
+
+
+def get_numeric_mode() -> str:
+    return _numeric_mode
 
 
 class TimeEncoder(nn.Module):
@@ -85,6 +107,7 @@ class _Engine:
         self.build_stats = None   # set to [0, 0, 0] to accumulate (evaluations, valid slots, queries) over memo builds
         self.served = {}     # depth -> (key, root queries answered without a memo)
         self.epoch = 0       # bumped by invalidate(): part of every cache key
+        self.bulk_projection = True   # projected (per-entry K/V) formulation of bulk calls, flid_tgat_set_bulk_projection
 
     def invalidate(self):
         """Forget the uploaded weights, the cached node table and the layer memo.  Needed after writes that
@@ -119,7 +142,7 @@ class _Engine:
             cached = [(mod._parameters, k, mod._parameters[k]) for mod, keys in mods for k in keys]
             self.param_cache[depth] = cached
         params = [p for _, _, p in cached]
-        fp = tuple([(p.data_ptr(), p._version) for p in params])
+        fp = tuple([(p.data_ptr(), p._version) for p in params]) + (_numeric_mode, self.bulk_projection)
         if self.versions.get(depth) != fp:
             for p in params:
                 if p.device != device:
@@ -142,6 +165,8 @@ class _Engine:
                 for name, t in zip([f[0] for f in _lib.LayerWeights._fields_], chunk):
                     setattr(layers[l], name, t.data_ptr())
             tw, tb = params[0].detach().contiguous(), params[1].detach().contiguous()
+            _lib.check(lib.flid_tgat_set_numeric_mode(h, NUMERIC_MODES[_numeric_mode]))
+            _lib.check(lib.flid_tgat_set_bulk_projection(h, 1 if self.bulk_projection else 0))
             _lib.check(lib.flid_tgat_set_weights(h, _lib.ptr(tw), _lib.ptr(tb), layers, _lib.stream()))
             self.versions[depth] = fp
             self.tables.pop(depth, None)
@@ -192,6 +217,7 @@ def build_layer_memo(engine, depth, time_encoder, conv_layers, merge_layers, sam
         if have is not None and have[0] == key:
             return have[1]
         engine.memo.pop(depth, None)
+        _lib.check(lib.flid_tgat_bulk_invalidate(h))     # new memo contents: the projected per-entry tables follow
         rows = sampler.num_entries + 1
         rank, world, dist = 0, 1, None
         if sharded:
@@ -399,6 +425,13 @@ class TGAT(nn.Module):
         self._engine.memo_mode = mode
         if not mode:
             self._engine.memo.clear()
+
+    def set_bulk_projection(self, enable: bool = True):
+        """Bulk calls (memo build, whole-pass embedding) project every adjacency entry once per pass and stream the
+        projected rows (csrc/bulk_kv.cu); results agree with the per-slot path to fp32 rounding.  ``False`` keeps
+        the per-slot stream everywhere: memoised results then equal the recursion bit for bit."""
+        self._engine.bulk_projection = bool(enable)
+        self._engine.memo.clear()
 
     def build_layer_memo(self, num_neighbors: int = 20, sharded: bool = False):
         """Explicitly (re)build the memo for full-depth calls; collective when ``sharded``."""

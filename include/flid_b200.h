@@ -147,16 +147,36 @@ int flid_tgat_memo_build(flid_tgat* m, const flid_graph* g, const float* node_fe
 /* flid_tgat_embed with the lower num_layers-1 levels read from memo tables
  * (memo_tables_host = host array of num_layers-1 device pointers, level 1 first): one
  * sampling pass and num_layers attention evaluations per root instead of
- * sum_l (1+k)^(L-l).  Same results, bit for bit.                                         */
+ * sum_l (1+k)^(L-l).  Per-batch calls give the same results as flid_tgat_embed bit for bit; bulk calls
+ * (see flid_tgat_bulk_invalidate) use the projected formulation and agree to fp32 rounding.        */
 int flid_tgat_embed_memo(flid_tgat* m, const flid_graph* g, const float* node_feat, const float* edge_feat,
                          const float* const* memo_tables_host, const int64_t* nodes, const double* times,
                          int times_are_f32, int64_t n, int k, float* out, flid_stream stream);
+/* Bulk calls (flid_tgat_memo_build; flid_tgat_embed_memo with at least entries / k roots) project every
+ * adjacency entry once per pass -- the reference's key / value projections (models/modules.py:191-197) hoisted
+ * from "per neighbour slot" to "per entry" -- and keep those tables inside the handle, keyed on the weights, the
+ * graph and the table pointers.  Call this after rebuilding a memo table in place (same pointer, new contents)
+ * or after editing a feature table in place, so that the projected tables are rebuilt too.                  */
+int flid_tgat_bulk_invalidate(flid_tgat* m);
+/* Switch the projected formulation of bulk calls off (0) or on (1, default): off, every call uses the per-slot
+ * stream and memoised results equal flid_tgat_embed's bit for bit.  Takes effect at the next
+ * flid_tgat_set_weights.  For tests and A/B timing.                                                        */
+int flid_tgat_set_bulk_projection(flid_tgat* m, int enable);
 /* A root query (v, t) that is itself an event of the graph (built with flid_graph_build_events)
  * at a float32-exact time finds its own lower-layer embeddings in the memo too (the table row
  * of the event's entry in the other endpoint's list), so flid_tgat_embed_memo evaluates only
  * the top layer for it; other roots take the full chain.  Same bits either way; on by default,
  * this switch exists for tests and A/B timing.                                            */
 int flid_tgat_set_self_from_memo(flid_tgat* m, int enable);
+/* Numeric mode of the projection GEMMs (BASELINE.json north_star; reference: the Q/K/V/out projections of
+ * models/modules.py:186-197,227-241 and the MergeLayer of :66-68).
+ *   0 (default): fp32-grade -- every product as three tf32 MMAs on hi/lo-split operands (rel. error ~2^-21),
+ *                embeddings within fp32 rel 1e-4 of the reference;
+ *   1: "bf16 projections" -- operands rounded to bfloat16 (RNE), one MMA per product, fp32 accumulation;
+ *                tolerance rel 2e-2 with identical argmax on >= 99.9 % of nodes.
+ * Takes effect at the next flid_tgat_set_weights (the weight images are tiled per mode).  The gather /
+ * time-encode / softmax stream and the decoder stay fp32 in both modes.                              */
+int flid_tgat_set_numeric_mode(flid_tgat* m, int mode);
 /* upper bound on layer-1 targets processed per internal chunk (workspace ~7 KB per target;
  * default 606208 = 148 x 4096).  Results do not depend on it.                                   */
 int flid_tgat_set_chunk_targets(flid_tgat* m, int64_t max_layer1_targets);

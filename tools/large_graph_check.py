@@ -64,8 +64,9 @@ def main():
         m.set_layer_memo(False)
         plain = m.compute_node_temporal_embeddings(nodes[sub], times[sub], 2, 20)
         m.set_layer_memo("auto")
-    same = torch.equal(plain, out[sub])
-    print("memoised pass == recursion, bit for bit:", same, flush=True)
+    diff = float((plain - out[sub]).abs().max())
+    same = diff <= 2e-5 * max(1.0, float(plain.abs().max()))
+    print(f"memoised (projected) pass vs recursion: max |diff| = {diff:.2e}", flush=True)
     # independent arithmetic: the differentiable torch-op path (64-bit safe indexing)
     few = sub[:256]
     m.train()
