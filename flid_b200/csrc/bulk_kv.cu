@@ -130,12 +130,20 @@ __global__ void kv_owner_kernel(const int64_t* __restrict__ indptr, int64_t num_
     owner[p] = (int32_t)lo;
 }
 
+// out[0] = largest edge id, out[1] = 1 if some entry's neighbour is node 0 (the reference masks such a slot as
+// padding, utils/utils.py:204 + models/modules.py:210: only the slot-mask kernels reproduce that)
 __global__ void kv_max_eid_kernel(const int2* __restrict__ adj, int64_t M, int* __restrict__ out) {
-    int m = 0;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < M; i += (int64_t)gridDim.x * blockDim.x)
-        m = max(m, __ldg(adj + i).y);
+    int m = 0, z = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < M; i += (int64_t)gridDim.x * blockDim.x) {
+        const int2 ne = __ldg(adj + i);
+        m = max(m, ne.y), z |= (ne.x == 0);
+    }
     for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(FULL, m, o));
-    if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+    z = __any_sync(FULL, z);
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(out, m);
+        if (z) atomicMax(out + 1, 1);
+    }
 }
 
 __global__ void kv_entry_eid_kernel(const int2* __restrict__ adj, int64_t M, int32_t* __restrict__ eid) {
@@ -284,6 +292,10 @@ struct KvArgs {
     float* y;                // [n, qd + H T]
     int64_t n;
     int k, qd, T, tpw;       // tpw: targets per warp (a block walks 4 * tpw consecutive targets)
+    // windowed kernel: the valid slots of a target are the `cnt` consecutive CSR positions before `cut`
+    const int2* win;         // [n] (cut, cnt)
+    const int2* adj;         // [M] (neighbour, edge) by position (MODE 1 row ids)
+    int pad_pos;             // position standing for a padded slot (row of the projected tables)
 };
 
 // MODE 1: level 1 (scores precomputed per entry, V = Vn[nbr] + Ve[eid]); MODE 2: level >= 2 ([K | V] per entry).
@@ -557,12 +569,274 @@ __global__ void __launch_bounds__(128, 4) attn_kv_kernel(KvArgs a) {
     }
 }
 
+
+// ------------------------------------------------------------------ windowed stream kernel
+// Same arithmetic as attn_kv_kernel, organised around the fact that the valid slots of a target are CONSECUTIVE
+// adjacency positions [cut - cnt, cut) (the 'recent' sampler takes the last cnt <= k entries before the cut,
+// utils/utils.py:188-206): no slot bit mask, no per-slot address shuffles, rows of level >= 2 at a constant
+// stride from a running pointer.  ncu on the mask-driven kernel showed ~140 warp instructions per slot of which
+// a third was slot bookkeeping and 64-bit address traffic; the kernel is bound by instruction issue and dependent
+// latencies (issue slots 51-57 % busy, L1 hit 73-82 %, DRAM 9-17 %), so instructions are what to remove.
+template <int H, int MODE, int NVF, int TP>
+__global__ void __launch_bounds__(128, 4) attn_win_kernel(KvArgs a) {
+    extern __shared__ __align__(16) unsigned char q_smem[];
+    constexpr int G = 2, V = G * H;
+    constexpr int WARP_BYTES = NVF * 32 * 16 + 32 * 4 + H * TP * 32 * 8;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, hl = lane & (H - 1);
+    const int k = a.k, qd = a.qd, T = a.T;
+    const int full = NVF * 128, tail = qd - full;
+    unsigned char* ws = q_smem + wib * WARP_BYTES;
+    Row4* qf_s = reinterpret_cast<Row4*>(ws) + lane;                            // [NVF][32]
+    float* qt_s = reinterpret_cast<float*>(ws + NVF * 32 * 16) + lane;          // [32]
+    u64* ut_s = reinterpret_cast<u64*>(ws + NVF * 32 * 16 + 32 * 4) + lane;     // [H][TP][32]
+    const float wmax = __ldg(a.time_bound), bmax = __ldg(a.time_bound + 1);
+    u64 tw[TP], tb[TP];
+#pragma unroll
+    for (int r = 0; r < TP; ++r) {
+        const int c0 = lane + 64 * r, c1 = c0 + 32;
+        tw[r] = pk(c0 < T ? __ldg(a.time_w + c0) : 0.f, c1 < T ? __ldg(a.time_w + c1) : 0.f);
+        tb[r] = pk(c0 < T ? __ldg(a.time_b + c0) : 0.f, c1 < T ? __ldg(a.time_b + c1) : 0.f);
+    }
+    const int tl = tail > 0 ? min(lane, tail - 1) : 0;  // lanes beyond the tail read a valid float; never stored
+    const int64_t rowf = MODE == 2 ? 2 * (int64_t)qd : (int64_t)qd;  // floats per table row
+    // this lane's view of the tables: chunk `lane` of row 0
+    const float* kv_l = (MODE == 2 ? a.kv : a.vn) + 4 * lane;
+    const float* ve_l = (MODE == 1 ? a.ve : a.kv) + 4 * lane;
+
+    struct Rows {
+        Row4 x0[NVF], x1[NVF];  // MODE 1: Vn, Ve chunks; MODE 2: K, V chunks
+        float t0, t1;           // tails
+        float sv[MODE == 1 ? H : 1];  // MODE 1: precomputed [h | e] score of the slot per head (same in every lane)
+    };
+
+    for (int jt = 0; jt < a.tpw; ++jt) {
+        const int64_t i = (int64_t)blockIdx.x * (4 * a.tpw) + jt * 4 + wib;
+        if (i >= a.n) break;  // warp-uniform
+        const float* qrow = a.q_base + (a.q_index ? (int64_t)__ldg(a.q_index + i) : i) * a.q_stride;
+        if (MODE == 2) {
+#pragma unroll
+            for (int r = 0; r < NVF; ++r) qf_s[r * 32] = ldg_row4(qrow + 4 * (lane + 32 * r));
+            qt_s[0] = (lane < tail) ? __ldg(qrow + full + lane) : 0.f;
+        }
+#pragma unroll
+        for (int h = 0; h < H; ++h)
+#pragma unroll
+            for (int r = 0; r < TP; ++r) {
+                const int c0 = lane + 64 * r, c1 = c0 + 32;
+                const float* ut = qrow + a.ut_off + h * a.ut_hstride;
+                ut_s[(h * TP + r) * 32] = pk(c0 < T ? __ldg(ut + c0) : 0.f, c1 < T ? __ldg(ut + c1) : 0.f);
+            }
+        const int2 wn = __ldg(a.win + i);
+        // a target without neighbours: the reference's uniform weights over k identical padded rows == that row once
+        const bool empty = wn.y == 0;
+        const int cnt = empty ? 1 : wn.y;
+        const int first = empty ? a.pad_pos : wn.x - wn.y;   // position of slot 0
+        const int64_t dt0 = i * k + (empty ? k - 1 : k - wn.y);  // index of slot 0's dt
+
+        Row4 acc[NVF];
+        float acc_t = 0.f;
+        u64 acct[H][TP];
+        float mx[H], den[H];
+#pragma unroll
+        for (int r = 0; r < NVF; ++r) acc[r] = Row4{0ull, 0ull};
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            mx[h] = -INFINITY, den[h] = 0.f;
+#pragma unroll
+            for (int r = 0; r < TP; ++r) acct[h][r] = 0ull;
+        }
+
+        for (int j0 = 0; j0 < cnt; j0 += 32) {
+            const int nb = min(32, cnt - j0);
+            // lane-held per-slot scalars of this block of <= 32 slots
+            float dt_l = 0.f;
+            int nbr_l = 0, eid_l = 0;
+            if (lane < nb) {
+                dt_l = __ldg(a.dt + dt0 + j0 + lane);
+                if (MODE == 1 && !empty) {
+                    const int2 ne = __ldg(a.adj + first + j0 + lane);
+                    nbr_l = ne.x, eid_l = ne.y;
+                }
+            }
+            auto load = [&](int g, Rows(&x)[G]) {
+#pragma unroll
+                for (int s = 0; s < G; ++s) {
+                    const int js = min(g + s, nb - 1);  // a missing second slot re-reads the first (weight 0)
+                    const float *p0, *p1;
+                    if (MODE == 2) {
+                        p0 = kv_l + (int64_t)(first + j0 + js) * rowf;
+                        p1 = p0 + qd;
+                    } else {
+                        p0 = kv_l + (int64_t)__shfl_sync(FULL, nbr_l, js) * rowf;
+                        p1 = ve_l + (int64_t)__shfl_sync(FULL, eid_l, js) * rowf;
+                    }
+#pragma unroll
+                    for (int r = 0; r < NVF; ++r) {
+                        x[s].x0[r] = ldg_row4(p0 + 128 * r);
+                        x[s].x1[r] = ldg_row4(p1 + 128 * r);
+                    }
+                    x[s].t0 = __ldg(p0 - 4 * lane + full + tl);
+                    x[s].t1 = __ldg(p1 - 4 * lane + full + tl);
+                    if (MODE == 1) {
+                        const float* sp = a.s1 + (int64_t)(first + j0 + js) * H;  // uniform address: one wavefront
+#pragma unroll
+                        for (int h = 0; h < H; ++h) x[s].sv[h] = __ldg(sp + h);
+                    }
+                }
+            };
+            auto process = [&](int g, const Rows(&x)[G]) {
+                const bool two = g + 1 < nb;
+                float d[G];
+                d[0] = __shfl_sync(FULL, dt_l, g);
+                d[1] = __shfl_sync(FULL, dt_l, two ? g + 1 : g);
+                u64 xt[G][TP];
+                const float amax = fmaf(fmaxf(fabsf(d[0]), fabsf(d[1])), wmax, bmax);
+                if (amax < COS_FAST_LIMIT) {
+#pragma unroll
+                    for (int s = 0; s < G; ++s)
+#pragma unroll
+                        for (int r = 0; r < TP; ++r) xt[s][r] = cos2_fast(fma2(pk1(d[s]), tw[r], tb[r]));
+                } else {
+#pragma unroll
+                    for (int s = 0; s < G; ++s)
+#pragma unroll
+                        for (int r = 0; r < TP; ++r) xt[s][r] = cos2_accurate(fma2(pk1(d[s]), tw[r], tb[r]));
+                }
+                float part[V];
+                if (!empty) {
+#pragma unroll
+                    for (int s = 0; s < G; ++s) {
+                        float own = 0.f;
+                        if (MODE == 2) {
+                            u64 p0 = 0ull, p1 = 0ull;
+#pragma unroll
+                            for (int r = 0; r < NVF; ++r) {
+                                const Row4 q = qf_s[r * 32];
+                                p0 = fma2(x[s].x0[r].a, q.a, p0);
+                                p1 = fma2(x[s].x0[r].b, q.b, p1);
+                            }
+                            own = fmaf(x[s].t0, qt_s[0], hsum(add2(p0, p1)));
+                        }
+#pragma unroll
+                        for (int h = 0; h < H; ++h) {
+                            u64 p0 = 0ull;
+#pragma unroll
+                            for (int r = 0; r < TP; ++r) p0 = fma2(xt[s][r], ut_s[(h * TP + r) * 32], p0);
+                            part[s * H + h] = (MODE == 2 && h == hl) ? hsum(p0) + own : hsum(p0);
+                        }
+                    }
+                    reduce_bcast<V>(part, lane);
+                    if (MODE == 1) {  // + the precomputed [h | e] scores of the two slots
+#pragma unroll
+                        for (int h = 0; h < H; ++h) part[h] += x[0].sv[h], part[H + h] += x[1].sv[h];
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < V; ++q) part[q] = 0.f;
+                }
+                if (!two) {
+#pragma unroll
+                    for (int h = 0; h < H; ++h) part[H + h] = -INFINITY;  // weight ex2(-inf) = 0 on the re-read row
+                }
+                float w0[H], w1[H], corr_own = 1.f;
+                bool raised = false;
+#pragma unroll
+                for (int h = 0; h < H; ++h) {
+                    const float gmax = fmaxf(part[h], part[H + h]);
+                    if (gmax > mx[h]) {  // warp-uniform: raise the running max, rescale what was accumulated
+                        const float corr = ex2(mx[h] - gmax);
+                        const u64 c2 = pk1(corr);
+                        mx[h] = gmax;
+                        den[h] *= corr;
+#pragma unroll
+                        for (int r = 0; r < TP; ++r) acct[h][r] = mul2(acct[h][r], c2);
+                        if (h == hl) corr_own = corr;
+                        raised = true;
+                    }
+                    w0[h] = ex2(part[h] - mx[h]), w1[h] = ex2(part[H + h] - mx[h]);
+                    den[h] += w0[h] + w1[h];
+                    const u64 W0 = pk1(w0[h]), W1 = pk1(w1[h]);
+#pragma unroll
+                    for (int r = 0; r < TP; ++r) acct[h][r] = fma2(W1, xt[1][r], fma2(W0, xt[0][r], acct[h][r]));
+                }
+                if (raised) {
+                    const u64 c2 = pk1(corr_own);
+#pragma unroll
+                    for (int r = 0; r < NVF; ++r) acc[r].a = mul2(acc[r].a, c2), acc[r].b = mul2(acc[r].b, c2);
+                    acc_t *= corr_own;
+                }
+                float wo0 = w0[0], wo1 = w1[0];
+#pragma unroll
+                for (int h = 1; h < H; ++h)
+                    if (hl == h) wo0 = w0[h], wo1 = w1[h];
+                const u64 W0 = pk1(wo0), W1 = pk1(wo1);
+                if (MODE == 2) {
+#pragma unroll
+                    for (int r = 0; r < NVF; ++r) {
+                        acc[r].a = fma2(W1, x[1].x1[r].a, fma2(W0, x[0].x1[r].a, acc[r].a));
+                        acc[r].b = fma2(W1, x[1].x1[r].b, fma2(W0, x[0].x1[r].b, acc[r].b));
+                    }
+                    acc_t = fmaf(wo1, x[1].t1, fmaf(wo0, x[0].t1, acc_t));
+                } else {
+#pragma unroll
+                    for (int r = 0; r < NVF; ++r) {
+                        acc[r].a = fma2(W1, add2(x[1].x0[r].a, x[1].x1[r].a), fma2(W0, add2(x[0].x0[r].a, x[0].x1[r].a), acc[r].a));
+                        acc[r].b = fma2(W1, add2(x[1].x0[r].b, x[1].x1[r].b), fma2(W0, add2(x[0].x0[r].b, x[0].x1[r].b), acc[r].b));
+                    }
+                    acc_t = fmaf(wo1, x[1].t0 + x[1].t1, fmaf(wo0, x[0].t0 + x[0].t1, acc_t));
+                }
+            };
+
+            Rows xa[G], xb[G];
+            int g = 0;
+            load(0, xa);
+            while (true) {
+                if (g + 2 < nb) load(g + 2, xb);
+                process(g, xa);
+                g += 2;
+                if (g >= nb) break;
+                if (g + 2 < nb) load(g + 2, xa);
+                process(g, xb);
+                g += 2;
+                if (g >= nb) break;
+            }
+        }
+
+        const int P = qd + H * T;
+        float* y = a.y + i * (int64_t)P;
+        float inv_own = 1.0f / den[0];
+#pragma unroll
+        for (int h = 1; h < H; ++h)
+            if (hl == h) inv_own = 1.0f / den[h];
+        const u64 io = pk1(inv_own);
+#pragma unroll
+        for (int r = 0; r < NVF; ++r)
+            reinterpret_cast<ulonglong2*>(y)[lane + 32 * r] = make_ulonglong2(mul2(acc[r].a, io), mul2(acc[r].b, io));
+        if (lane < tail) y[full + lane] = acc_t * inv_own;
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            const u64 inv = pk1(1.0f / den[h]);
+#pragma unroll
+            for (int r = 0; r < TP; ++r) {
+                const int c0 = lane + 64 * r, c1 = c0 + 32;
+                float lo, hi;
+                upk(mul2(acct[h][r], inv), lo, hi);
+                if (c0 < T) y[qd + h * T + c0] = lo;
+                if (c1 < T) y[qd + h * T + c1] = hi;
+            }
+        }
+    }
+}
+
 template <int H, int MODE, int NVF>
 int launch_kv(const KvArgs& a, cudaStream_t st) {
     constexpr int TP = 2;
     constexpr int WARP_BYTES = NVF * 32 * 16 + 32 * 4 + H * TP * 32 * 8;
     const unsigned blocks = (unsigned)ceil_div(a.n, 4 * (int64_t)a.tpw);
-    attn_kv_kernel<H, MODE, NVF, TP><<<blocks, 128, 4 * WARP_BYTES, st>>>(a);
+    if (a.win != nullptr)
+        attn_win_kernel<H, MODE, NVF, TP><<<blocks, 128, 4 * WARP_BYTES, st>>>(a);
+    else
+        attn_kv_kernel<H, MODE, NVF, TP><<<blocks, 128, 4 * WARP_BYTES, st>>>(a);
     FLID_LAUNCH_CHECK();
     return FLID_OK;
 }
@@ -646,17 +920,18 @@ static int graph_derived(const flid_graph* gc, cudaStream_t st) {
     }
     if (g->max_eid < 0) {
         int* d = nullptr;
-        int h = 0;
-        FLID_CUDA(cudaMalloc((void**)&d, sizeof(int)));
-        FLID_CUDA(cudaMemsetAsync(d, 0, sizeof(int), st));
+        int h[2] = {0, 0};
+        FLID_CUDA(cudaMalloc((void**)&d, 2 * sizeof(int)));
+        FLID_CUDA(cudaMemsetAsync(d, 0, 2 * sizeof(int), st));
         if (M > 0) {
             kv_max_eid_kernel<<<(unsigned)std::min<int64_t>(ceil_div(M, 256), 2048), 256, 0, st>>>(g->adj, M, d);
             FLID_LAUNCH_CHECK();
         }
-        FLID_CUDA(cudaMemcpyAsync(&h, d, sizeof(int), cudaMemcpyDeviceToHost, st));
+        FLID_CUDA(cudaMemcpyAsync(h, d, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
         FLID_CUDA(cudaStreamSynchronize(st));
         cudaFree(d);
-        g->max_eid = h;
+        g->max_eid = h[0];
+        g->zero_nbr = h[1];
     }
     return FLID_OK;
 }
@@ -735,6 +1010,7 @@ int kv_attention(flid_tgat* m, const KvCall& c, int k, cudaStream_t st) {
     a.time_w = m->time_w, a.time_b = m->time_b, a.time_bound = m->time_bound;
     a.y = c.Y, a.n = c.n, a.k = k, a.qd = qd, a.T = T;
     a.kv = nullptr, a.vn = nullptr, a.ve = nullptr, a.s1 = nullptr;
+    a.win = c.graph_zero_nbr ? nullptr : c.win, a.adj = c.adj, a.pad_pos = c.pad_pos;
     // a block walks 4 * tpw consecutive targets; keep every SM busy on small calls
     const int64_t per = c.n / (148 * 4 * 4);
     a.tpw = per >= 8 ? 8 : (per >= 4 ? 4 : (per >= 2 ? 2 : 1));

@@ -15,6 +15,7 @@ struct flid_graph {
     // derived arrays of the projected bulk path (bulk_kv.cu), built on first use
     int32_t* owner = nullptr;   // [M] node whose list holds the entry
     int32_t* ent_eid = nullptr; // [M + 1] edge id of the entry (row M: the padded slot, edge 0)
+    int zero_nbr = 0;           // some entry's neighbour is node 0 (masked like padding by the reference)
     int64_t max_eid = -1;       // largest edge id in the adjacency (rows of the per-edge tables)
 };
 

@@ -93,7 +93,8 @@ __global__ void __launch_bounds__(256) level_sample_kernel(
     const int32_t* __restrict__ ids, const double* __restrict__ times, int64_t n, int64_t n_f64, int k,
     int32_t* __restrict__ nbr, int32_t* __restrict__ eid, float* __restrict__ dt, int32_t* __restrict__ next_ids,
     double* __restrict__ next_times, int32_t* __restrict__ pos, int32_t pad_pos,
-    const int32_t* __restrict__ mirror, int32_t* __restrict__ self_pos, unsigned long long* __restrict__ valid_slots) {
+    const int32_t* __restrict__ mirror, int32_t* __restrict__ self_pos, unsigned long long* __restrict__ valid_slots,
+    int2* __restrict__ win = nullptr) {
     __shared__ int s_cnt;
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
@@ -132,6 +133,7 @@ __global__ void __launch_bounds__(256) level_sample_kernel(
         const int64_t have = cut - start;
         const int cnt = have < (int64_t)k ? (int)have : k;
         if (next_ids && sub == 0) next_ids[q] = v, next_times[q] = t;
+        if (win && sub == 0) win[q] = make_int2((int)cut, cnt);  // the valid slots are positions [cut - cnt, cut)
         if (self_pos && sub == 0) {
             // Is (v, t) itself an event of the graph at a float32-exact time?  Then the lower-layer
             // embeddings of this root are already in the layer memo: the row of the event's entry in
@@ -453,6 +455,10 @@ struct LayerCall {
     float* out = nullptr;              // [n, dn]
     const int32_t* out_idx = nullptr;  // nullable: row i is written to out + out_idx[i] * dn
     bool kv = false;                   // projected bulk path (bulk_kv.cu); needs pos, eid and the level's tables
+    const int2* win = nullptr;         // kv: (cut, cnt) per target
+    const int2* adj = nullptr;
+    int pad_pos = 0;
+    bool zero_nbr = false;
 };
 
 // one attention layer (1-based `layer`) for n targets: query fold -> stream -> out chain
@@ -464,6 +470,7 @@ static int layer_eval(flid_tgat* m, int layer, const LayerCall& c, const float* 
         KvCall kc;
         kc.level = layer, kc.n = c.n, kc.ids = c.ids, kc.self_base = c.self_base, kc.self_idx = c.self_idx;
         kc.nbr = c.nbr, kc.eid = c.eid, kc.pos = c.pos, kc.dt = c.dt, kc.U = U, kc.Y = Z;
+        kc.win = m->kv_windowed ? c.win : nullptr, kc.adj = c.adj, kc.pad_pos = c.pad_pos, kc.graph_zero_nbr = c.zero_nbr;
         FLID_TRY(kv_attention(m, kc, k, st));
         ProfScope prof(m, PROF_OUT, st);
         return output_chain(m, layer - 1, c.n, Z, c.self_base, c.self_idx, node_feat, c.ids, O, A, Hd, c.out, c.out_idx, st,
@@ -498,6 +505,7 @@ static int reserve_layer_ws(flid_tgat* m, int64_t n, int k, bool need_u) {
     FLID_TRY(m->ws_eid.reserve(sizeof(int32_t) * n * k));
     FLID_TRY(m->ws_dt.reserve(sizeof(float) * n * k));
     FLID_TRY(m->ws_pos.reserve(sizeof(int32_t) * n * k));
+    FLID_TRY(m->ws_win.reserve(sizeof(int2) * n));
     if (need_u) FLID_TRY(m->ws_u.reserve(sizeof(float) * n * m->zw));
     FLID_TRY(m->ws_z.reserve(sizeof(float) * n * m->zw));
     FLID_TRY(m->ws_o.reserve(sizeof(float) * n * m->qd));
@@ -563,11 +571,11 @@ int tgat_memo_build(flid_tgat* m, const flid_graph* g, const float* node_feat, c
             level_sample_kernel<<<(unsigned)ceil_div(n * LS_W, 256), 256, 0, st>>>(
                 g->indptr, g->adj, g->ts, w_ids, w_times, n, 0, k, m->ws_nbr.as<int32_t>(), m->ws_eid.as<int32_t>(),
                 m->ws_dt.as<float>(), nullptr, nullptr, (level > 1 || kv) ? m->ws_pos.as<int32_t>() : nullptr, (int32_t)M,
-                nullptr, nullptr, d_valid);
+                nullptr, nullptr, d_valid, kv ? m->ws_win.as<int2>() : nullptr);
             FLID_LAUNCH_CHECK();
         }
         LayerCall c;
-        c.kv = kv;
+        c.kv = kv, c.win = m->ws_win.as<int2>(), c.adj = g->adj, c.pad_pos = (int)M, c.zero_nbr = g->zero_nbr != 0;
         c.n = n, c.ids = w_ids;
         c.nbr = m->ws_nbr.as<int32_t>(), c.eid = m->ws_eid.as<int32_t>(), c.dt = m->ws_dt.as<float>();
         if (level == 1) {
@@ -630,7 +638,7 @@ int tgat_embed_memo(flid_tgat* m, const flid_graph* g, const float* node_feat, c
                 g->indptr, g->adj, g->ts, ids + r0, times + r0, nc, nf, k, m->ws_nbr.as<int32_t>(),
                 m->ws_eid.as<int32_t>(), m->ws_dt.as<float>(), nullptr, nullptr,
                 (L > 1 || kv) ? m->ws_pos.as<int32_t>() : nullptr, (int32_t)M, try_self ? g->mirror : nullptr,
-                try_self ? m->ws_self.as<int32_t>() : nullptr, d_cnt);
+                try_self ? m->ws_self.as<int32_t>() : nullptr, d_cnt, kv ? m->ws_win.as<int2>() : nullptr);
             FLID_LAUNCH_CHECK();
         }
         // counters of this chunk (one small synchronous read per chunk of up to 65 536 roots)
@@ -648,7 +656,7 @@ int tgat_embed_memo(flid_tgat* m, const flid_graph* g, const float* node_feat, c
         }
         for (int l = all_in_memo ? L : 1; l <= L; ++l) {
             LayerCall c;
-            c.kv = kv;
+            c.kv = kv, c.win = m->ws_win.as<int2>(), c.adj = g->adj, c.pad_pos = (int)M, c.zero_nbr = g->zero_nbr != 0;
             c.n = nc, c.ids = ids + r0;
             c.nbr = m->ws_nbr.as<int32_t>(), c.eid = m->ws_eid.as<int32_t>(), c.dt = m->ws_dt.as<float>();
             if (l == 1) {
@@ -702,6 +710,8 @@ int flid_tgat_create(int node_dim, int edge_dim, int time_dim, int num_layers, i
     m->self_from_memo = !(sm && sm[0] == '0');
     const char* kvv = getenv("FLID_BULK_KV");
     m->kv_enabled = !(kvv && kvv[0] == '0');
+    const char* kk = getenv("FLID_KV_KERNEL");
+    m->kv_windowed = !(kk && strcmp(kk, "mask") == 0);
     const char* so = getenv("FLID_SORT_QUERIES");
     m->sort_bulk_queries = !(so && so[0] == '0');
     if (const char* ct = getenv("FLID_CHUNK_TARGETS"))   // development knob, same as flid_tgat_set_chunk_targets
@@ -726,7 +736,7 @@ void flid_tgat_free(flid_tgat* m) {
     flid::DevBuf* bufs[] = {&m->raw_q, &m->raw_k, &m->raw_v, &m->raw_r, &m->table, &m->ws_ids, &m->ws_times,
                             &m->ws_nbr, &m->ws_eid, &m->ws_dt, &m->ws_h, &m->ws_u, &m->ws_z, &m->ws_o,
                             &m->ws_a, &m->ws_hd, &m->ws_misc, &m->ws_rid, &m->ws_rt, &m->ws_bad, &m->ws_pos, &m->ws_self, &m->ws_sort,
-                            &m->tgn_ids, &m->tgn_times, &m->tgn_eids, &m->tgn_gi, &m->tgn_gh};
+                            &m->tgn_ids, &m->tgn_times, &m->tgn_eids, &m->tgn_gi, &m->tgn_gh, &m->ws_win};
     for (auto* b : bufs) b->release();
     delete m;
 }

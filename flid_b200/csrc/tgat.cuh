@@ -48,6 +48,8 @@ struct flid_tgat {
     bool self_from_memo = true;  // roots that are graph events read their own lower layers from the memo (FLID_SELF_MEMO=0 disables)
     flid::DevBuf ws_ids, ws_times, ws_nbr, ws_eid, ws_dt, ws_h, ws_u, ws_z, ws_o, ws_a, ws_hd, ws_misc, ws_pos, ws_self, ws_sort;
     flid::DevBuf ws_rid, ws_rt, ws_bad;  // root conversion staging
+    flid::DevBuf ws_win;                 // (cut, cnt) per target of the current chunk (windowed stream kernel)
+    bool kv_windowed = true;             // FLID_KV_KERNEL=mask selects the slot-mask kernel (A/B timing)
     // projected bulk path: tables derived from (weights, graph, feature tables[, memo of the level below])
     bool kv_enabled = true;             // FLID_BULK_KV=0 disables (A/B timing)
     uint64_t weights_version = 0;       // bumped by flid_tgat_set_weights
@@ -98,6 +100,10 @@ struct KvCall {
     const int32_t* self_idx = nullptr;
     const int32_t *nbr = nullptr, *eid = nullptr, *pos = nullptr;
     const float* dt = nullptr;
+    const int2* win = nullptr;          // non-null: (cut, cnt) per target -> the windowed stream kernel
+    const int2* adj = nullptr;          // graph adjacency by position (windowed kernel, level 1)
+    int pad_pos = 0;                    // position of the padded slot's row in the projected tables
+    bool graph_zero_nbr = false;        // an entry with neighbour id 0 exists: only the slot-mask kernel handles it
     float *U = nullptr, *Y = nullptr;   // workspaces: [n, qd + H*T] each
 };
 // query side (level >= 2: two GEMMs) + stream kernel; Y = [sum a V (interleaved) | sum a te per head]
