@@ -543,7 +543,7 @@ def run_tgat(b, ci, cfg):
     value = roots_per_step * args.steps / (ms_total / 1000.0)
     e2e_value = roots_per_step * args.steps / (ms_e2e / 1000.0)
     lo, hi, _ = passes.shard_bounds(e, rank, world)
-    roots_loc = 2 * (hi - lo)
+    roots_loc = int(pass_stats["embed"][2])        # root queries answered by rank 0 (the roots of the nodes it owns)
     top_evals = pass_stats["embed"][0]
     build_evals = pass_stats["build"][0]
     if use_memo:
@@ -577,7 +577,8 @@ def run_tgat(b, ci, cfg):
         "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(ci, cfg, g), "layers": L, "num_neighbors": K_NBR, "heads": HEADS,
-                   "roots_per_step": roots_per_step, "parallelism": f"query-sharded x{world}, graph replicated",
+                   "roots_per_step": roots_per_step, "parallelism": (f"owner-partitioned x{world} (queries routed to the rank that owns their node, memo rows "
+                                   f"exchanged once per level), graph replicated") if world > 1 else "one GPU",
                    "layer_memo": ("on: lower layers of every adjacency entry evaluated once per pass (rebuilt inside "
                                   "each timed step), %d attention evaluations per step on rank 0 instead of %d"
                                   % (evals_l1 + evals_up, roots_loc * sum((1 + K_NBR) ** i for i in range(L))))

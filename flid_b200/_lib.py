@@ -83,6 +83,10 @@ _SIGNATURES = {
     "flid_tgat_set_chunk_targets": (C.c_int, [c_void, C.c_int64]),
     "flid_tgat_set_numeric_mode": (C.c_int, [c_void, C.c_int]),
     "flid_tgat_bulk_invalidate": (C.c_int, [c_void]),
+    "flid_tgat_memo_build_owner_range": (C.c_int, [c_void, c_void, c_void, c_void, C.c_int, C.c_int, c_void, C.c_int64,
+                                                   C.c_int64, C.c_int, c_void, c_void]),
+    "flid_tgat_set_bulk_range": (C.c_int, [c_void, C.c_int64, C.c_int64]),
+    "flid_graph_export_mirror": (C.c_int, [c_void, c_void, c_void]),
     "flid_tgat_set_bulk_projection": (C.c_int, [c_void, C.c_int]),
     "flid_tgat_profile": (C.c_int, [c_void, C.c_int]),
     "flid_tgat_profile_read": (C.c_int, [c_void, C.POINTER(C.c_double), c_i64p]),

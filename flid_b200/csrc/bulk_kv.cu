@@ -155,12 +155,13 @@ __global__ void kv_entry_eid_kernel(const int2* __restrict__ adj, int64_t M, int
 // (already in the log2 domain).  One warp per entry; consecutive entries share the owner, so the u rows hit L1.
 template <int H>
 __global__ void __launch_bounds__(256) kv_score1_kernel(const int32_t* __restrict__ owner, const int2* __restrict__ adj,
-                                                        int64_t M, const float* __restrict__ table,
+                                                        int64_t M, int64_t lo, int64_t hi, const float* __restrict__ table,
                                                         const float* __restrict__ nf, const float* __restrict__ ef, int dn,
                                                         int de, int kd, float* __restrict__ s1) {
     const int lane = threadIdx.x & 31;
-    const int64_t p = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    if (p > M) return;
+    int64_t p = lo + ((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+    if (p > hi) return;
+    if (p == hi) p = M;  // the work item after the range: the padded slot's row
     if (p == M) {  // padded slot: never read (padded slots are skipped unless every slot is padded, then scores are 0)
         if (lane < H) s1[p * H + lane] = 0.f;
         return;
@@ -296,6 +297,7 @@ struct KvArgs {
     const int2* win;         // [n] (cut, cnt)
     const int2* adj;         // [M] (neighbour, edge) by position (MODE 1 row ids)
     int pad_pos;             // position standing for a padded slot (row of the projected tables)
+    int ve_by_pos;           // MODE 1: rows of `ve` are indexed by CSR position instead of edge id
 };
 
 // MODE 1: level 1 (scores precomputed per entry, V = Vn[nbr] + Ve[eid]); MODE 2: level >= 2 ([K | V] per entry).
@@ -577,13 +579,16 @@ __global__ void __launch_bounds__(128, 4) attn_kv_kernel(KvArgs a) {
 // stride from a running pointer.  ncu on the mask-driven kernel showed ~140 warp instructions per slot of which
 // a third was slot bookkeeping and 64-bit address traffic; the kernel is bound by instruction issue and dependent
 // latencies (issue slots 51-57 % busy, L1 hit 73-82 %, DRAM 9-17 %), so instructions are what to remove.
-template <int H, int MODE, int NVF, int TP>
-__global__ void __launch_bounds__(128, 4) attn_win_kernel(KvArgs a) {
+// QDC / TC: compile-time row width and time dimension (0 = take them from the arguments).  With the reference's
+// shape (qd = 272, T = 100) every row offset becomes an immediate: the generic instance spent ~60 of its ~266
+// instructions per slot pair on 64-bit address arithmetic.
+template <int H, int MODE, int NVF, int TP, int QDC, int TC, int MINB>
+__global__ void __launch_bounds__(128, MINB) attn_win_kernel(KvArgs a) {
     extern __shared__ __align__(16) unsigned char q_smem[];
     constexpr int G = 2, V = G * H;
     constexpr int WARP_BYTES = NVF * 32 * 16 + 32 * 4 + H * TP * 32 * 8;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, hl = lane & (H - 1);
-    const int k = a.k, qd = a.qd, T = a.T;
+    const int k = a.k, qd = QDC ? QDC : a.qd, T = TC ? TC : a.T;
     const int full = NVF * 128, tail = qd - full;
     unsigned char* ws = q_smem + wib * WARP_BYTES;
     Row4* qf_s = reinterpret_cast<Row4*>(ws) + lane;                            // [NVF][32]
@@ -655,7 +660,9 @@ __global__ void __launch_bounds__(128, 4) attn_win_kernel(KvArgs a) {
                 dt_l = __ldg(a.dt + dt0 + j0 + lane);
                 if (MODE == 1 && !empty) {
                     const int2 ne = __ldg(a.adj + first + j0 + lane);
-                    nbr_l = ne.x, eid_l = ne.y;
+                    nbr_l = ne.x, eid_l = a.ve_by_pos ? first + j0 + lane : ne.y;
+                } else if (MODE == 1 && a.ve_by_pos) {
+                    eid_l = a.pad_pos;
                 }
             }
             auto load = [&](int g, Rows(&x)[G]) {
@@ -833,9 +840,20 @@ int launch_kv(const KvArgs& a, cudaStream_t st) {
     constexpr int TP = 2;
     constexpr int WARP_BYTES = NVF * 32 * 16 + 32 * 4 + H * TP * 32 * 8;
     const unsigned blocks = (unsigned)ceil_div(a.n, 4 * (int64_t)a.tpw);
-    if (a.win != nullptr)
-        attn_win_kernel<H, MODE, NVF, TP><<<blocks, 128, 4 * WARP_BYTES, st>>>(a);
-    else
+    static const int minb = [] {  // development knob: resident blocks per SM the windowed kernel is compiled for
+        const char* e = getenv("FLID_KV_MINB");
+        return (e && e[0] == '3') ? 3 : 4;
+    }();
+    if (a.win != nullptr) {
+        if (NVF == 2 && a.qd == 272 && a.T == 100) {
+            if (minb == 3)
+                attn_win_kernel<H, MODE, NVF, TP, 272, 100, 3><<<blocks, 128, 4 * WARP_BYTES, st>>>(a);
+            else
+                attn_win_kernel<H, MODE, NVF, TP, 272, 100, 4><<<blocks, 128, 4 * WARP_BYTES, st>>>(a);
+        } else {
+            attn_win_kernel<H, MODE, NVF, TP, 0, 0, 4><<<blocks, 128, 4 * WARP_BYTES, st>>>(a);
+        }
+    } else
         attn_kv_kernel<H, MODE, NVF, TP><<<blocks, 128, 4 * WARP_BYTES, st>>>(a);
     FLID_LAUNCH_CHECK();
     return FLID_OK;
@@ -936,34 +954,53 @@ static int graph_derived(const flid_graph* gc, cudaStream_t st) {
     return FLID_OK;
 }
 
+static void bulk_range(const flid_tgat* m, const flid_graph* g, int64_t* lo, int64_t* hi) {
+    *lo = m->bulk_hi < 0 ? 0 : m->bulk_lo;
+    *hi = m->bulk_hi < 0 ? g->num_entries : m->bulk_hi;
+}
+
 int kv_ensure_level1(flid_tgat* m, const flid_graph* g, const float* node_feat, const float* edge_feat, cudaStream_t st) {
     flid_tgat::KvKey key;
     key.wv = m->weights_version, key.epoch = m->bulk_epoch, key.g = g, key.nf = node_feat, key.ef = edge_feat;
     key.entries = g->num_entries;
+    bulk_range(m, g, &key.lo, &key.hi);
     if (m->kv_l1_key == key && m->kv_s1.p) return FLID_OK;
     FLID_REQUIRE(m->table_src == node_feat && m->table_rows > 0, "projected bulk path: node table not cached");
     FLID_TRY(graph_derived(g, st));
     const LayerDev& ld = m->layers[0];
-    const int64_t M = g->num_entries, rows_n = m->table_rows, rows_e = g->max_eid + 1;
+    const int64_t M = g->num_entries, rows_n = m->table_rows, lo = key.lo, hi = key.hi;
+    const bool whole = lo == 0 && hi == M;
+    // whole adjacency: one projected row per edge; a range (one rank's share): one per entry of the range, so that
+    // a rank projects E / W edge rows instead of all E
+    const int64_t rows_e = whole ? g->max_eid + 1 : M + 1;
     const int qd = m->qd;
     FLID_TRY(m->kv_vn1.reserve(sizeof(float) * (size_t)rows_n * qd));
     FLID_TRY(m->kv_ve1.reserve(sizeof(float) * (size_t)rows_e * qd));
     FLID_TRY(m->kv_s1.reserve(sizeof(float) * (size_t)(M + 1) * m->H));
+    m->kv_ve_by_pos = !whole;
     {
         ProfScope prof(m, PROF_QFOLD, st);
         TcGemmArgs t;
         t.A0 = node_feat, t.lda0 = m->dn, t.w0 = m->dn, t.C = m->kv_vn1.as<float>(), t.ldc = qd, t.M = rows_n;
         FLID_TRY(tc_gemm(t, ld.tc_vn, st));
         TcGemmArgs e;
-        e.A0 = edge_feat, e.lda0 = m->de, e.w0 = m->de, e.C = m->kv_ve1.as<float>(), e.ldc = qd, e.M = rows_e;
-        FLID_TRY(tc_gemm(e, ld.tc_ve, st));
-        const unsigned blocks = (unsigned)ceil_div((M + 1) * 32, 256);
+        e.A0 = edge_feat, e.lda0 = m->de, e.w0 = m->de, e.ldc = qd;
+        if (whole) {
+            e.C = m->kv_ve1.as<float>(), e.M = rows_e;
+            FLID_TRY(tc_gemm(e, ld.tc_ve, st));
+        } else {
+            e.idx0 = g->ent_eid + lo, e.C = m->kv_ve1.as<float>() + lo * qd, e.M = hi - lo;
+            FLID_TRY(tc_gemm(e, ld.tc_ve, st));
+            e.idx0 = g->ent_eid + M, e.C = m->kv_ve1.as<float>() + M * qd, e.M = 1;  // the padded slot's row
+            FLID_TRY(tc_gemm(e, ld.tc_ve, st));
+        }
+        const unsigned blocks = (unsigned)ceil_div((hi - lo + 1) * 32, 256);
         const float* table = m->table.as<float>();
         float* s1 = m->kv_s1.as<float>();
         switch (m->H) {
-            case 1: kv_score1_kernel<1><<<blocks, 256, 0, st>>>(g->owner, g->adj, M, table, node_feat, edge_feat, m->dn, m->de, m->kd, s1); break;
-            case 2: kv_score1_kernel<2><<<blocks, 256, 0, st>>>(g->owner, g->adj, M, table, node_feat, edge_feat, m->dn, m->de, m->kd, s1); break;
-            default: kv_score1_kernel<4><<<blocks, 256, 0, st>>>(g->owner, g->adj, M, table, node_feat, edge_feat, m->dn, m->de, m->kd, s1); break;
+            case 1: kv_score1_kernel<1><<<blocks, 256, 0, st>>>(g->owner, g->adj, M, lo, hi, table, node_feat, edge_feat, m->dn, m->de, m->kd, s1); break;
+            case 2: kv_score1_kernel<2><<<blocks, 256, 0, st>>>(g->owner, g->adj, M, lo, hi, table, node_feat, edge_feat, m->dn, m->de, m->kd, s1); break;
+            default: kv_score1_kernel<4><<<blocks, 256, 0, st>>>(g->owner, g->adj, M, lo, hi, table, node_feat, edge_feat, m->dn, m->de, m->kd, s1); break;
         }
         FLID_LAUNCH_CHECK();
     }
@@ -978,6 +1015,7 @@ int kv_ensure_level(flid_tgat* m, const flid_graph* g, int level, const float* m
     flid_tgat::KvKey key;
     key.wv = m->weights_version, key.epoch = m->bulk_epoch, key.g = g, key.nf = node_feat, key.ef = edge_feat;
     key.memo = memo_prev, key.entries = g->num_entries;
+    bulk_range(m, g, &key.lo, &key.hi);
     DevBuf& tab = m->kv_tab[level - 2];
     if (m->kv_tab_key[level - 2] == key && tab.p) return FLID_OK;
     FLID_TRY(graph_derived(g, st));
@@ -989,14 +1027,20 @@ int kv_ensure_level(flid_tgat* m, const flid_graph* g, int level, const float* m
     const LayerDev& ld = m->layers[level - 1];
     // rows in chunks of full tile rounds (the GEMM's work counter is 32-bit)
     const int64_t chunk = (int64_t)148 * 128 * 4096;
-    for (int64_t r0 = 0; r0 <= M; r0 += chunk) {
-        const int64_t nr = std::min(chunk, M + 1 - r0);
-        for (int half = 0; half < 2; ++half) {
-            TcGemmArgs t;
-            t.A0 = memo_prev + r0 * m->dn, t.lda0 = m->dn, t.w0 = m->dn;
-            t.A1 = edge_feat, t.lda1 = m->de, t.idx1 = ent_eid + r0, t.w1 = m->de;
-            t.C = tab.as<float>() + r0 * 2 * qd + half * qd, t.ldc = 2 * qd, t.M = nr;
-            FLID_TRY(tc_gemm(t, half ? ld.tc_v2 : ld.tc_k2, st));
+    // rows [lo, hi) of the range and the padded slot's row M (contiguous with the range when it reaches the end)
+    int64_t seg_lo[2] = {key.lo, M}, seg_n[2] = {key.hi - key.lo, 1};
+    int segs = 2;
+    if (key.hi == M) seg_n[0] += 1, segs = 1;
+    for (int sg = 0; sg < segs; ++sg) {
+        for (int64_t r0 = seg_lo[sg]; r0 < seg_lo[sg] + seg_n[sg]; r0 += chunk) {
+            const int64_t nr = std::min(chunk, seg_lo[sg] + seg_n[sg] - r0);
+            for (int half = 0; half < 2; ++half) {
+                TcGemmArgs t;
+                t.A0 = memo_prev + r0 * m->dn, t.lda0 = m->dn, t.w0 = m->dn;
+                t.A1 = edge_feat, t.lda1 = m->de, t.idx1 = ent_eid + r0, t.w1 = m->de;
+                t.C = tab.as<float>() + r0 * 2 * qd + half * qd, t.ldc = 2 * qd, t.M = nr;
+                FLID_TRY(tc_gemm(t, half ? ld.tc_v2 : ld.tc_k2, st));
+            }
         }
     }
     m->kv_tab_key[level - 2] = key;
@@ -1011,6 +1055,8 @@ int kv_attention(flid_tgat* m, const KvCall& c, int k, cudaStream_t st) {
     a.y = c.Y, a.n = c.n, a.k = k, a.qd = qd, a.T = T;
     a.kv = nullptr, a.vn = nullptr, a.ve = nullptr, a.s1 = nullptr;
     a.win = c.graph_zero_nbr ? nullptr : c.win, a.adj = c.adj, a.pad_pos = c.pad_pos;
+    a.ve_by_pos = m->kv_ve_by_pos ? 1 : 0;
+    if (c.level == 1 && m->kv_ve_by_pos) a.eid = c.pos;  // slot-mask kernel: edge rows by position as well
     // a block walks 4 * tpw consecutive targets; keep every SM busy on small calls
     const int64_t per = c.n / (148 * 4 * 4);
     a.tpw = per >= 8 ? 8 : (per >= 4 ? 4 : (per >= 2 ? 2 : 1));
@@ -1046,6 +1092,15 @@ extern "C" int flid_tgat_set_bulk_projection(flid_tgat* m, int enable) {
     FLID_REQUIRE(m != nullptr, "flid_tgat_set_bulk_projection: null handle");
     if (m->kv_enabled != (enable != 0)) m->have_weights = false;  // the projected weight images are built by set_weights
     m->kv_enabled = enable != 0;
+    return FLID_OK;
+}
+
+extern "C" int flid_tgat_set_bulk_range(flid_tgat* m, int64_t pos_lo, int64_t pos_hi) {
+    using namespace flid;
+    FLID_REQUIRE(m != nullptr, "flid_tgat_set_bulk_range: null handle");
+    FLID_REQUIRE(pos_hi < 0 || (pos_lo >= 0 && pos_lo <= pos_hi), "flid_tgat_set_bulk_range: bad range");
+    m->bulk_lo = pos_hi < 0 ? 0 : pos_lo;
+    m->bulk_hi = pos_hi;
     return FLID_OK;
 }
 

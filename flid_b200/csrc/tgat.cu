@@ -535,12 +535,17 @@ static bool kv_tables_fit(flid_tgat* m, const flid_graph* g, int level) {
     return need + (size_t(2) << 30) < free_b;   // keep 2 GiB of headroom for the caller's own tensors
 }
 
+// owner_range: [row_lo, row_hi) are WORK ITEMS in owner-major order -- item q evaluates the query (owner of q, time
+// of q) and its row is scattered to q's partner position (any row of the table); one rank's share of an
+// owner-partitioned pass.  Otherwise [row_lo, row_hi) are table rows.
 int tgat_memo_build(flid_tgat* m, const flid_graph* g, const float* node_feat, const float* edge_feat, int k, int level,
-                    const float* memo_prev, int64_t row_lo, int64_t row_hi, float* memo_out, cudaStream_t st) {
+                    const float* memo_prev, int64_t row_lo, int64_t row_hi, float* memo_out, cudaStream_t st,
+                    bool owner_range = false, bool with_padded_row = false) {
     const int64_t M = g->num_entries;
     const bool use_table = level == 1 && (m->table_src == node_feat && m->table_rows > 0);
     const int64_t chunk = std::max<int64_t>(1, m->max_l1_targets);
-    FLID_TRY(reserve_layer_ws(m, std::min(chunk, row_hi - row_lo), k, !use_table));
+    const int64_t ws_rows = std::max<int64_t>(1, std::min(chunk, row_hi - row_lo));
+    FLID_TRY(reserve_layer_ws(m, ws_rows, k, !use_table));
     unsigned long long* d_valid = m->ws_misc.as<unsigned long long>();
     FLID_CUDA(cudaMemsetAsync(d_valid, 0, sizeof(unsigned long long), st));
     int32_t* w_ids = m->ws_ids.as<int32_t>();
@@ -548,8 +553,8 @@ int tgat_memo_build(flid_tgat* m, const flid_graph* g, const float* node_feat, c
     // A build of the whole table walks it in owner-major order and scatters the rows (the mirror is a
     // permutation, so every row is written exactly once); a row-range build (one rank's slice of a
     // sharded build) keeps table order so that its output stays one contiguous block.
-    const bool owner_major = g->mirror != nullptr && row_lo == 0 && row_hi == M + 1;
-    if (owner_major) FLID_TRY(m->ws_self.reserve(sizeof(int32_t) * std::min(chunk, row_hi - row_lo)));
+    const bool owner_major = g->mirror != nullptr && (owner_range || (row_lo == 0 && row_hi == M + 1));
+    if (owner_major) FLID_TRY(m->ws_self.reserve(sizeof(int32_t) * ws_rows));
     // projected bulk path (bulk_kv.cu): every entry is a slot of up to k targets of this build, so the per-entry
     // projections pay off; level 1 needs the cached per-node query table
     bool kv = kv_supported(m) && (level > 1 || use_table) && kv_tables_fit(m, g, level);
@@ -561,8 +566,12 @@ int tgat_memo_build(flid_tgat* m, const flid_graph* g, const float* node_feat, c
     }
     int32_t* w_rows = owner_major ? m->ws_self.as<int32_t>() : nullptr;
     int64_t evals = 0;
-    for (int64_t c0 = row_lo; c0 < row_hi; c0 += chunk) {
-        const int64_t n = std::min(chunk, row_hi - c0);
+    // chunks of the range, then (owner-range builds) the padded slot's query as an item of its own
+    std::vector<std::pair<int64_t, int64_t>> chunks;
+    for (int64_t c0 = row_lo; c0 < row_hi; c0 += chunk) chunks.push_back({c0, std::min(chunk, row_hi - c0)});
+    if (with_padded_row && row_hi <= M) chunks.push_back({M, 1});
+    for (const auto& ch : chunks) {
+        const int64_t c0 = ch.first, n = ch.second;
         {
             ProfScope prof(m, PROF_SAMPLE, st);
             memo_targets_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(g->adj, g->ts, M, c0, n, w_ids, w_times,
@@ -614,7 +623,8 @@ int tgat_embed_memo(flid_tgat* m, const flid_graph* g, const float* node_feat, c
     const int64_t nmax = std::min(chunk, n);
     // projected bulk path: worth building the per-entry tables when the call's slots outnumber the entries
     // (a bulk pass); per-batch calls keep the x-space stream
-    bool kv = kv_supported(m) && use_table && n * (int64_t)k >= M && M > 0;
+    const int64_t range_entries = m->bulk_hi < 0 ? M : m->bulk_hi - m->bulk_lo;
+    bool kv = kv_supported(m) && use_table && n * (int64_t)k >= range_entries && M > 0;
     for (int l = 2; l <= L && kv; ++l) kv = kv_tables_fit(m, g, l);
     if (kv) {
         for (int l = 2; l <= L; ++l) FLID_TRY(kv_ensure_level(m, g, l, memo[l - 2], node_feat, edge_feat, st));
@@ -869,6 +879,33 @@ int flid_tgat_memo_build(flid_tgat* m, const flid_graph* g, const float* node_fe
     if (row_lo == row_hi) return FLID_OK;
     return tgat_memo_build(m, g, node_feat, edge_feat, k, level, memo_prev, row_lo, row_hi, memo_out,
                            (cudaStream_t)stream);
+}
+
+int flid_tgat_memo_build_owner_range(flid_tgat* m, const flid_graph* g, const float* node_feat, const float* edge_feat,
+                                     int k, int level, const float* memo_prev, int64_t item_lo, int64_t item_hi,
+                                     int with_padded_row, float* memo_out, flid_stream stream) {
+    using namespace flid;
+    FLID_REQUIRE(m && g && node_feat && edge_feat && memo_out, "flid_tgat_memo_build_owner_range: null argument");
+    FLID_REQUIRE(m->have_weights, "flid_tgat_memo_build_owner_range: weights not set");
+    FLID_REQUIRE(k > 0, "Number of sampled neighbors for each node should be greater than 0!");
+    FLID_REQUIRE(level >= 1 && level <= m->L, "flid_tgat_memo_build_owner_range: level %d outside 1..%d", level, m->L);
+    FLID_REQUIRE(level == 1 || memo_prev != nullptr, "flid_tgat_memo_build_owner_range: level %d needs the level-%d table",
+                 level, level - 1);
+    FLID_REQUIRE(g->mirror != nullptr, "flid_tgat_memo_build_owner_range: the graph has no partner index (build it from events)");
+    FLID_REQUIRE(item_lo >= 0 && item_lo <= item_hi && item_hi <= g->num_entries,
+                 "flid_tgat_memo_build_owner_range: item range outside [0, entries]");
+    if (item_hi == item_lo && !with_padded_row) return FLID_OK;
+    return tgat_memo_build(m, g, node_feat, edge_feat, k, level, memo_prev, item_lo, item_hi, memo_out,
+                           (cudaStream_t)stream, true, with_padded_row != 0);
+}
+
+int flid_graph_export_mirror(const flid_graph* g, int32_t* out_dev, flid_stream stream) {
+    using namespace flid;
+    FLID_REQUIRE(g && out_dev, "flid_graph_export_mirror: null argument");
+    FLID_REQUIRE(g->mirror != nullptr, "flid_graph_export_mirror: the graph has no partner index (build it from events)");
+    FLID_CUDA(cudaMemcpyAsync(out_dev, g->mirror, sizeof(int32_t) * g->num_entries, cudaMemcpyDeviceToDevice,
+                              (cudaStream_t)stream));
+    return FLID_OK;
 }
 
 int flid_tgat_embed_memo(flid_tgat* m, const flid_graph* g, const float* node_feat, const float* edge_feat,

@@ -57,11 +57,17 @@ struct flid_tgat {
     struct KvKey {
         uint64_t wv = 0, epoch = 0;
         const void *g = nullptr, *nf = nullptr, *ef = nullptr, *memo = nullptr;
-        int64_t entries = -1;
+        int64_t entries = -1, lo = 0, hi = -1;
         bool operator==(const KvKey& o) const {
-            return wv == o.wv && epoch == o.epoch && g == o.g && nf == o.nf && ef == o.ef && memo == o.memo && entries == o.entries;
+            return wv == o.wv && epoch == o.epoch && g == o.g && nf == o.nf && ef == o.ef && memo == o.memo &&
+                   entries == o.entries && lo == o.lo && hi == o.hi;
         }
     };
+    // owner-partitioned passes (one rank of a multi-GPU pass): every target this handle sees has its window inside
+    // the CSR position range [bulk_lo, bulk_hi), so the per-entry tables are only filled there (+ the padded row);
+    // bulk_hi < 0 = the whole adjacency
+    int64_t bulk_lo = 0, bulk_hi = -1;
+    bool kv_ve_by_pos = false;           // level-1 edge projections indexed by CSR position (range builds) instead of edge id
     KvKey kv_l1_key;
     flid::DevBuf kv_vn1, kv_ve1, kv_s1;             // level 1: V of node rows [N+1, qd], V of edge rows [max_eid+1, qd], scores [M+1, H]
     std::vector<flid::DevBuf> kv_tab;               // level l >= 2 (index l-2): [M+1, 2*qd] = [K | V] of entry p

@@ -67,10 +67,6 @@ def _is_tensor(x):
     return isinstance(x, torch.Tensor)
 
 
-def _slice_events(src, dst, t, lo, hi):
-    return src[lo:hi], dst[lo:hi], t[lo:hi]
-
-
 def _embed_src_dst(model, src, dst, t, num_neighbors):
     """Both endpoints of every event through one launch chain.  Host numpy arrays take the drop-in call
     (``compute_src_dst_node_temporal_embeddings``: pinned staging + H2D inside); device tensors (int64 ids,
@@ -83,13 +79,53 @@ def _embed_src_dst(model, src, dst, t, num_neighbors):
     return model.compute_src_dst_node_temporal_embeddings(src, dst, t, num_neighbors)
 
 
+def _scatter_all_reduce(rows: torch.Tensor, index: torch.Tensor, total: int, dist):
+    """Every row of the [total, w] result is produced by exactly one rank: write the local rows into a zeroed
+    table and sum the tables (x + 0 is exact)."""
+    full = rows.new_zeros((total,) + tuple(rows.shape[1:]))
+    full.index_copy_(0, index, rows)
+    dist.all_reduce(full)
+    return full
+
+
+def _owned_roots(model, src, dst, t, num_neighbors, dist, rank, world):
+    """Owner-partitioned pass, first half: build the sharded layer memo, route the root queries of this rank's
+    contiguous event slice to the ranks that own their nodes, embed the roots this rank owns.
+    Returns (embeddings [n_own, dn], global root index [n_own]: event i's source is i, its destination E + i)."""
+    from . import _lib
+    from .shard import route_roots
+    from .tgat import shard_plan
+    e = len(src)
+    dev = model.node_raw_features.device
+    lo, hi, _ = shard_bounds(e, rank, world)
+    with torch.no_grad(), torch.cuda.device(dev):
+        prepare_layer_memo(model, 2 * e, num_neighbors, True)
+        if _is_tensor(src):
+            s_loc, d_loc, t_loc = src[lo:hi], dst[lo:hi], t[lo:hi]
+            is32 = t.dtype == torch.float32
+        else:
+            is32 = np.asarray(t).dtype == np.float32
+            s_loc = _lib.to_device(src[lo:hi], np.int64, dev, "p_src")
+            d_loc = _lib.to_device(dst[lo:hi], np.int64, dev, "p_dst")
+            t_loc = _lib.to_device(t[lo:hi], np.float64, dev, "p_t")      # float32 -> float64 is exact
+        ev = torch.arange(lo, hi, device=dev, dtype=torch.int64)
+        t64 = t_loc.to(torch.float64)
+        plan = shard_plan(model._engine, model.neighbor_sampler, dev)
+        nodes, times, gidx = route_roots(torch.cat([s_loc.to(torch.int64), d_loc.to(torch.int64)]), torch.cat([t64, t64]),
+                                         torch.cat([ev, ev + e]), plan.node_inner, world, dist)
+        if is32:
+            times = times.to(torch.float32)       # the recursion's dtype rule follows the caller's dtype
+        emb = model.compute_node_temporal_embeddings(nodes, times, model.num_layers, num_neighbors)
+    return emb, gidx
+
+
 def embed_events(model, src_node_ids, dst_node_ids, node_interact_times, num_neighbors: int = 20, sharded=None):
     """Embeddings of every event's source and destination node at the event time:
     two float32 [E, dn] device tensors, rows in event order (what the reference's full pass
     accumulates batch by batch and copies into ``src_node_embeddings`` / ``dst_node_embeddings``).
     Inputs are host numpy arrays (the reference's types) or device tensors.
-    With torch.distributed initialised (or ``sharded=True``) each rank embeds a contiguous
-    event range and the halves are all-gathered."""
+    With torch.distributed initialised (or ``sharded=True``) the pass is owner-partitioned
+    (flid_b200/shard.py) and the rows are combined on every rank."""
     _require_eval(model)
     dist, rank, world = _dist()
     if sharded is None:
@@ -103,13 +139,12 @@ def embed_events(model, src_node_ids, dst_node_ids, node_interact_times, num_nei
         with torch.no_grad():
             prepare_layer_memo(model, 2 * e, num_neighbors, False)
             return _embed_src_dst(model, src, dst, t, num_neighbors)
-    lo, hi, per = shard_bounds(e, rank, world)
-    with torch.no_grad():
-        prepare_layer_memo(model, 2 * e, num_neighbors, True)
-        a, b = _embed_src_dst(model, *_slice_events(src, dst, t, lo, hi), num_neighbors)
-    both = torch.stack([a, b], dim=1)                       # [n_local, 2, dn]: one collective for both halves
-    full = all_gather_rows(both, e, per, dist)
-    return full[:, 0].contiguous(), full[:, 1].contiguous()
+    try:
+        emb, gidx = _owned_roots(model, src, dst, t, num_neighbors, dist, rank, world)
+        full = _scatter_all_reduce(emb, gidx, 2 * e, dist)
+    finally:
+        model._engine.shard_tag = None
+    return full[:e], full[e:]
 
 
 def e_step_pass(model, decoder: MLPClassifier, src_node_ids, dst_node_ids, node_interact_times,
@@ -122,8 +157,8 @@ def e_step_pass(model, decoder: MLPClassifier, src_node_ids, dst_node_ids, node_
     labels for both endpoints): pseudo_labels [2, E], probabilities [2, E, C] (row 0 = sources).
     ``pseudo_labels_store`` is the reference's list of earlier iterations' probabilities; this pass's
     probabilities are appended to it before filtering (PTCL/E_step.py:351 then PTCL/utils.py:80-83).
-    When sharded, only (label, probs) rows are all-gathered (12 B/event/endpoint for C=2) unless the
-    embeddings are requested."""
+    When sharded, only (label, probs) rows travel between the ranks (12 B/event/endpoint for C=2) unless
+    the embeddings are requested."""
     _require_eval(model, decoder)
     dist, rank, world = _dist()
     if sharded is None:
@@ -133,33 +168,32 @@ def e_step_pass(model, decoder: MLPClassifier, src_node_ids, dst_node_ids, node_
     else:
         src, dst, t = np.asarray(src_node_ids), np.asarray(dst_node_ids), np.asarray(node_interact_times)
     e = len(src)
+    ways = 2 if double_way else 1
     store = pseudo_labels_store if pseudo_labels_store is not None else []
-
-    def score(a, b):
-        """(labels float32 [ways, n], probs [ways, n, C]) of one event range"""
-        if double_way:
-            l2, p2 = emit_pseudo_labels(decoder, torch.cat([a, b]))
-            return l2.to(torch.float32).reshape(2, -1), p2.reshape(2, a.shape[0], -1)
-        l1, p1 = emit_pseudo_labels(decoder, a)
-        return l1.to(torch.float32).reshape(1, -1), p1.unsqueeze(0)
-
     if not sharded or world == 1:
         src_emb, dst_emb = embed_events(model, src, dst, t, num_neighbors, sharded=False)
-        labels, probs = score(src_emb, dst_emb)
+        l_all, p_all = emit_pseudo_labels(decoder, torch.cat([src_emb, dst_emb]) if double_way else src_emb)
+        labels = l_all.to(torch.float32).reshape(ways, e)
+        probs = p_all.reshape(ways, e, -1)
         emb = (src_emb, dst_emb)
     else:
-        lo, hi, per = shard_bounds(e, rank, world)
-        with torch.no_grad():
-            prepare_layer_memo(model, 2 * e, num_neighbors, True)
-            a, b = _embed_src_dst(model, *_slice_events(src, dst, t, lo, hi), num_neighbors)
-        l_loc, p_loc = score(a, b)                                            # [ways, n_loc], [ways, n_loc, C]
-        packed = torch.cat([l_loc.unsqueeze(2), p_loc], dim=2).transpose(0, 1)  # [n_loc, ways, 1 + C]
-        full = all_gather_rows(packed.contiguous(), e, per, dist).transpose(0, 1)
-        labels, probs = full[:, :, 0].contiguous(), full[:, :, 1:].contiguous()
-        emb = None
-        if return_embeddings:
-            both = all_gather_rows(torch.stack([a, b], dim=1), e, per, dist)
-            emb = (both[:, 0].contiguous(), both[:, 1].contiguous())
+        try:
+            own, gidx = _owned_roots(model, src, dst, t, num_neighbors, dist, rank, world)
+            if not double_way:                      # only the source endpoints are scored (PTCL/E_step.py:327-331)
+                keep = torch.nonzero(gidx < e).reshape(-1)
+                own_s, gidx_s = own.index_select(0, keep), gidx.index_select(0, keep)
+            else:
+                own_s, gidx_s = own, gidx
+            l_loc, p_loc = emit_pseudo_labels(decoder, own_s)
+            packed = torch.cat([l_loc.to(torch.float32).unsqueeze(1), p_loc], dim=1)      # [n_own, 1 + C]
+            full = _scatter_all_reduce(packed, gidx_s, ways * e, dist).reshape(ways, e, -1)
+            labels, probs = full[:, :, 0].contiguous(), full[:, :, 1:].contiguous()
+            emb = None
+            if return_embeddings:
+                both = _scatter_all_reduce(own, gidx, 2 * e, dist)
+                emb = (both[:e], both[e:])
+        finally:
+            model._engine.shard_tag = None
     if not double_way:
         probs = probs[0]
     store.append(probs)

@@ -107,13 +107,17 @@ class _Engine:
         self.build_stats = None   # set to [0, 0, 0] to accumulate (evaluations, valid slots, queries) over memo builds
         self.served = {}     # depth -> (key, root queries answered without a memo)
         self.epoch = 0       # bumped by invalidate(): part of every cache key
-        self.bulk_projection = True   # projected (per-entry K/V) formulation of bulk calls, flid_tgat_set_bulk_projection
+        # projected (per-entry K/V) formulation of bulk calls, flid_tgat_set_bulk_projection (FLID_BULK_KV=0: off)
+        self.bulk_projection = os.environ.get("FLID_BULK_KV", "1") != "0"
+        self.shard_tag = None         # (rank, world) while an owner-partitioned pass is running (flid_b200.passes)
+        self.shard_plans = {}         # (sampler generation, rank, world) -> shard.ShardPlan
 
     def invalidate(self):
         """Forget the uploaded weights, the cached node table and the layer memo.  Needed after writes that
         autograd's version counter does not see (``param.data.copy_()``, ``.data`` mutation, feature tables
         edited in place through ``.data``); ``load_state_dict`` / ``.to()`` / optimizer steps are detected."""
         self.epoch += 1
+        self.shard_tag = None
         self.versions.clear()
         self.tables.clear()
         self.memo.clear()
@@ -184,11 +188,12 @@ class _Engine:
 
 def _memo_key(engine, depth, sampler, node_feat, edge_feat, k):
     return (engine.versions.get(depth), engine.epoch, sampler.generation, node_feat.data_ptr(), node_feat._version,
-            edge_feat.data_ptr(), edge_feat._version, int(k))
+            edge_feat.data_ptr(), edge_feat._version, int(k), engine.shard_tag)
 
 
 def memo_piece_bounds(rows, rank, world, pieces):
-    """Row ranges of the sharded memo build.  The table (``per * world * pieces`` rows, ``per`` =
+    """Row ranges of a table-order sharded memo build (kept for callers that split a build by table rows, e.g. the
+    tests of flid_tgat_memo_build's row-range form).  The table (``per * world * pieces`` rows, ``per`` =
     ceil(rows / (world * pieces))) is cut into ``pieces`` super-blocks of ``world * per`` rows; inside
     super-block p rank r owns rows [p*world*per + r*per, ... + per), clipped to ``rows``.
     Returns (per, [(block_start, lo, hi), ...])."""
@@ -200,11 +205,27 @@ def memo_piece_bounds(rows, rank, world, pieces):
     return per, out
 
 
+def shard_plan(engine, sampler, device):
+    """The owner partition of this rank (flid_b200.shard.ShardPlan), cached per sampler."""
+    import torch.distributed as dist
+    from .shard import ShardPlan
+    rank, world = dist.get_rank(), dist.get_world_size()
+    key = (sampler.generation, rank, world)
+    plan = engine.shard_plans.get(key)
+    if plan is None:
+        engine.shard_plans.clear()
+        plan = ShardPlan(sampler, rank, world, device)
+        engine.shard_plans[key] = plan
+    return plan
+
+
 def build_layer_memo(engine, depth, time_encoder, conv_layers, merge_layers, sampler, node_feat, edge_feat,
                      num_neighbors, sharded=False):
     """Fill the layer memo (include/flid_b200.h, flid_tgat_memo_build) for levels 1..depth-1.
-    ``sharded`` (torch.distributed initialised, called by every rank): each rank builds a
-    contiguous range of table rows and the ranges are all-gathered in place over NCCL."""
+    ``sharded`` (torch.distributed initialised, called by every rank): owner-partitioned build -- each rank
+    evaluates the work items of its own position range in owner-major order and the rows that belong to other
+    ranks' ranges are exchanged once per level (flid_b200/shard.py); the resulting table is complete for this
+    rank's range only and is used through ``engine.shard_tag``."""
     if depth < 2:
         return None
     device = node_feat.device
@@ -212,6 +233,13 @@ def build_layer_memo(engine, depth, time_encoder, conv_layers, merge_layers, sam
     with torch.cuda.device(device):
         h = engine.handle(depth, time_encoder, conv_layers, merge_layers, device)
         engine.ensure_table(depth, h, node_feat)
+        plan = None
+        if sharded:
+            import torch.distributed as dist
+            if dist.get_world_size() > 1:
+                plan = shard_plan(engine, sampler, device)
+        engine.shard_tag = (plan.rank, plan.world) if plan is not None else None
+        _lib.check(lib.flid_tgat_set_bulk_range(h, plan.pos_lo if plan else 0, plan.pos_hi if plan else -1))
         key = _memo_key(engine, depth, sampler, node_feat, edge_feat, num_neighbors)
         have = engine.memo.get(depth)
         if have is not None and have[0] == key:
@@ -219,36 +247,26 @@ def build_layer_memo(engine, depth, time_encoder, conv_layers, merge_layers, sam
         engine.memo.pop(depth, None)
         _lib.check(lib.flid_tgat_bulk_invalidate(h))     # new memo contents: the projected per-entry tables follow
         rows = sampler.num_entries + 1
-        rank, world, dist = 0, 1, None
-        if sharded:
-            import torch.distributed as dist
-            rank, world = dist.get_rank(), dist.get_world_size()
-        # Sharded build, pipelined with its exchange: the table is cut into `pieces` super-blocks of world * per rows;
-        # inside each, rank r builds rows [r * per, (r + 1) * per) and the super-block is all-gathered in place
-        # (asynchronously, on NCCL's stream) while the next piece is being built.
-        pieces = 2 if world > 1 else 1
-        per, bounds = memo_piece_bounds(rows, rank, world, pieces)
         dn = node_feat.shape[1]
         tables = []
         prev = None
         for level in range(1, depth):
-            t = torch.empty((per * world * pieces, dn), dtype=torch.float32, device=device)
-            pending = []
-            for base, lo, hi in bounds:
-                if hi > lo:
-                    _lib.check(lib.flid_tgat_memo_build(h, sampler.handle, _lib.ptr(node_feat), _lib.ptr(edge_feat),
-                                                        int(num_neighbors), level, _lib.ptr(prev), lo, hi, _lib.ptr(t),
-                                                        _lib.stream()))
-                    if engine.build_stats is not None:      # measurement runs only: reading the counters synchronises
-                        st = (C.c_int64 * 4)()
-                        _lib.check(lib.flid_tgat_last_stats(h, st))
-                        engine.build_stats = [a + int(b) for a, b in zip(engine.build_stats, st[:3])]
-                if world > 1:
-                    block = t[base:base + per * world]
-                    pending.append(dist.all_gather_into_tensor(block, block[rank * per:(rank + 1) * per],
-                                                               async_op=True))     # in place
-            for work in pending:
-                work.wait()
+            t = torch.empty((rows, dn), dtype=torch.float32, device=device)
+            if plan is None:
+                _lib.check(lib.flid_tgat_memo_build(h, sampler.handle, _lib.ptr(node_feat), _lib.ptr(edge_feat),
+                                                    int(num_neighbors), level, _lib.ptr(prev), 0, rows, _lib.ptr(t),
+                                                    _lib.stream()))
+            else:
+                _lib.check(lib.flid_tgat_memo_build_owner_range(h, sampler.handle, _lib.ptr(node_feat),
+                                                                _lib.ptr(edge_feat), int(num_neighbors), level,
+                                                                _lib.ptr(prev), plan.pos_lo, plan.pos_hi, 1, _lib.ptr(t),
+                                                                _lib.stream()))
+            if engine.build_stats is not None:      # measurement runs only: reading the counters synchronises
+                st = (C.c_int64 * 4)()
+                _lib.check(lib.flid_tgat_last_stats(h, st))
+                engine.build_stats = [a + int(b) for a, b in zip(engine.build_stats, st[:3])]
+            if plan is not None:
+                plan.exchange_rows(t, dist)
             tables.append(t)
             prev = t
         engine.memo[depth] = (key, tables)
@@ -264,7 +282,7 @@ def _memo_for_call(engine, depth, time_encoder, conv_layers, merge_layers, sampl
     mode = engine.memo_mode
     if depth < 2 or not mode:
         return None
-    key = _memo_key(engine, depth, sampler, node_feat, edge_feat, k)
+    key = _memo_key(engine, depth, sampler, node_feat, edge_feat, k)    # includes engine.shard_tag
     have = engine.memo.get(depth)
     if have is not None and have[0] == key:
         return have[1]

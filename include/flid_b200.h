@@ -152,6 +152,23 @@ int flid_tgat_memo_build(flid_tgat* m, const flid_graph* g, const float* node_fe
 int flid_tgat_embed_memo(flid_tgat* m, const flid_graph* g, const float* node_feat, const float* edge_feat,
                          const float* const* memo_tables_host, const int64_t* nodes, const double* times,
                          int times_are_f32, int64_t n, int k, float* out, flid_stream stream);
+/* One rank's share of an owner-partitioned (multi-GPU) memo build: work items [item_lo, item_hi) are adjacency
+ * positions in owner-major order -- item q evaluates the query (owner of q, float32 time of q), i.e. the memo row of
+ * q's partner entry, and writes it to that row of memo_out (a full-size table; rows of other ranks' partitions are
+ * exchanged by the caller).  Every window an item reads lies inside the owner's adjacency list, so with item ranges
+ * cut at node boundaries a rank only reads table rows / projected entries of its own position range (see
+ * flid_tgat_set_bulk_range).  with_padded_row: also evaluate row `entries` (the padded slot's query (0, 0.0)).
+ * Needs a graph built from events (partner index).                                                            */
+int flid_tgat_memo_build_owner_range(flid_tgat* m, const flid_graph* g, const float* node_feat, const float* edge_feat,
+                                     int k, int level, const float* memo_prev, int64_t item_lo, int64_t item_hi,
+                                     int with_padded_row, float* memo_out, flid_stream stream);
+/* Restrict the per-entry tables of the projected bulk path to CSR positions [pos_lo, pos_hi) (+ the padded row):
+ * every target this handle is asked for from now on has its neighbour window inside that range (one rank of an
+ * owner-partitioned pass).  pos_hi < 0 restores the whole adjacency.                                          */
+int flid_tgat_set_bulk_range(flid_tgat* m, int64_t pos_lo, int64_t pos_hi);
+/* partner index of the adjacency (position of the same event's entry in the other endpoint's list), int32[entries],
+ * copied into a caller-owned device buffer; graphs built from events only                                      */
+int flid_graph_export_mirror(const flid_graph* g, int32_t* out_dev, flid_stream stream);
 /* Bulk calls (flid_tgat_memo_build; flid_tgat_embed_memo with at least entries / k roots) project every
  * adjacency entry once per pass -- the reference's key / value projections (models/modules.py:191-197) hoisted
  * from "per neighbour slot" to "per entry" -- and keep those tables inside the handle, keyed on the weights, the
