@@ -224,7 +224,9 @@ extern "C" {
 int flid_pseudo_label(const flid_mlp_weights* w, const float* emb, int64_t n, float* probs, int64_t* labels,
                       float* logits_or_null, flid_stream stream) {
     using namespace flid;
-    FLID_REQUIRE(w && emb && probs && labels, "flid_pseudo_label: null argument");
+    FLID_REQUIRE(w != nullptr, "flid_pseudo_label: null argument");
+    if (n <= 0) return FLID_OK;   // an empty batch has no buffers (a rank that owns no source endpoint)
+    FLID_REQUIRE(emb && probs && labels, "flid_pseudo_label: null argument");
     FLID_REQUIRE(w->input_dim > 0 && w->input_dim <= 512 && w->hidden1 > 0 && w->hidden1 <= 256 && w->hidden2 > 0 &&
                      w->num_classes > 0 && w->num_classes <= MAXC,
                  "flid_pseudo_label: unsupported decoder shape (input<=512, hidden1<=256, classes<=16)");
