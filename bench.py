@@ -508,7 +508,9 @@ def run_tgat(b, ci, cfg):
         clocks.start()
     _lib.check(lib.flid_tgat_profile(handle, 1))
     launches0 = lib.flid_launch_count()
+    passes.trace_report()      # (FLID_PASS_TRACE) drop the warm-up phases
     ms_total, wall_dev = b.timed(lambda: step_device(store), args.steps)
+    pass_trace = passes.trace_report()
     step_ms = list(b.last_step_ms)
     launches = lib.flid_launch_count() - launches0
     prof_ms = (ctypes.c_double * 4)()
@@ -606,6 +608,11 @@ def run_tgat(b, ci, cfg):
     }
     if same is not None:
         line["sharded_equals_single"] = same
+        plans = list(model._engine.shard_plans.values())
+        line["config"]["memo_row_exchange"] = ("one kernel storing into the peers' tables over NVLink (CUDA IPC)"
+                                               if plans and plans[0].p2p else "all_to_all_single (NCCL)")
+    if os.environ.get("FLID_PASS_TRACE") == "1":
+        line["pass_trace_ms_per_step"] = {k: v / args.steps for k, v in pass_trace.items()}
     line.update(secondary_modes)
     print(json.dumps(line), flush=True)
     assert 0.05 < kept < 0.95, f"EST mask is degenerate: kept fraction {kept}"

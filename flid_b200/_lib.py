@@ -87,6 +87,11 @@ _SIGNATURES = {
                                                    C.c_int64, C.c_int, c_void, c_void]),
     "flid_tgat_set_bulk_range": (C.c_int, [c_void, C.c_int64, C.c_int64]),
     "flid_graph_export_mirror": (C.c_int, [c_void, c_void, c_void]),
+    "flid_peer_alloc": (C.c_int, [C.c_int64, C.POINTER(c_void), c_void]),
+    "flid_peer_open": (C.c_int, [c_void, C.POINTER(c_void)]),
+    "flid_peer_close": (C.c_int, [c_void]),
+    "flid_peer_free": (C.c_int, [c_void]),
+    "flid_memo_exchange_p2p": (C.c_int, [c_void, c_void, C.POINTER(c_void), c_i64p, C.c_int, C.c_int, C.c_int, c_void]),
     "flid_tgat_set_bulk_projection": (C.c_int, [c_void, C.c_int]),
     "flid_tgat_profile": (C.c_int, [c_void, C.c_int]),
     "flid_tgat_profile_read": (C.c_int, [c_void, C.POINTER(C.c_double), c_i64p]),

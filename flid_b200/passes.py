@@ -11,6 +11,30 @@ import torch
 from .pseudo_label import MLPClassifier, emit_pseudo_labels, entropy_filter, prob_filter
 
 
+import os
+import time
+
+_TRACE = os.environ.get("FLID_PASS_TRACE") == "1"      # development: synchronising phase timer of the sharded pass
+_trace_acc = {}
+
+
+def _mark(name, t0):
+    """Phase timer (FLID_PASS_TRACE=1 only): synchronises, accumulates wall time per phase."""
+    if not _TRACE:
+        return t0
+    torch.cuda.synchronize()
+    now = time.perf_counter()
+    _trace_acc[name] = _trace_acc.get(name, 0.0) + (now - t0)
+    return now
+
+
+def trace_report(reset=True):
+    out = {k: round(1000.0 * v, 3) for k, v in _trace_acc.items()}
+    if reset:
+        _trace_acc.clear()
+    return out
+
+
 def shard_bounds(num_items: int, rank: int, world_size: int):
     """Contiguous, order-preserving split; every rank gets ceil(n / W) items except the tail."""
     per = -(-num_items // world_size) if num_items else 0
@@ -91,7 +115,8 @@ def _scatter_all_reduce(rows: torch.Tensor, index: torch.Tensor, total: int, dis
 def _owned_roots(model, src, dst, t, num_neighbors, dist, rank, world):
     """Owner-partitioned pass, first half: build the sharded layer memo, route the root queries of this rank's
     contiguous event slice to the ranks that own their nodes, embed the roots this rank owns.
-    Returns (embeddings [n_own, dn], global root index [n_own]: event i's source is i, its destination E + i)."""
+    Returns (embeddings [n_own, dn], global root index [n_own]: event i's source is i, its destination E + i,
+    n_src): the first ``n_src`` owned roots are source endpoints, the rest destinations."""
     from . import _lib
     from .shard import route_roots
     from .tgat import shard_plan
@@ -99,24 +124,45 @@ def _owned_roots(model, src, dst, t, num_neighbors, dist, rank, world):
     dev = model.node_raw_features.device
     lo, hi, _ = shard_bounds(e, rank, world)
     with torch.no_grad(), torch.cuda.device(dev):
+        t0 = _mark("start", time.perf_counter()) if _TRACE else 0.0
         prepare_layer_memo(model, 2 * e, num_neighbors, True)
-        if _is_tensor(src):
-            s_loc, d_loc, t_loc = src[lo:hi], dst[lo:hi], t[lo:hi]
-            is32 = t.dtype == torch.float32
-        else:
-            is32 = np.asarray(t).dtype == np.float32
-            s_loc = _lib.to_device(src[lo:hi], np.int64, dev, "p_src")
-            d_loc = _lib.to_device(dst[lo:hi], np.int64, dev, "p_dst")
-            t_loc = _lib.to_device(t[lo:hi], np.float64, dev, "p_t")      # float32 -> float64 is exact
-        ev = torch.arange(lo, hi, device=dev, dtype=torch.int64)
-        t64 = t_loc.to(torch.float64)
+        t0 = _mark("memo_build+exchange", t0)
         plan = shard_plan(model._engine, model.neighbor_sampler, dev)
-        nodes, times, gidx = route_roots(torch.cat([s_loc.to(torch.int64), d_loc.to(torch.int64)]), torch.cat([t64, t64]),
-                                         torch.cat([ev, ev + e]), plan.node_inner, world, dist)
-        if is32:
-            times = times.to(torch.float32)       # the recursion's dtype rule follows the caller's dtype
+        # device-resident inputs that did not change since the last pass (the E-step embeds the same event list in
+        # every EM iteration) keep their routing: it depends on the events and the partition only
+        key = None
+        if _is_tensor(src):
+            key = tuple((x.data_ptr(), x._version, tuple(x.shape), x.dtype) for x in (src, dst, t))
+        routed = plan.routing.get(key) if key is not None else None
+        if routed is None:
+            if _is_tensor(src):
+                s_loc, d_loc, t_loc = src[lo:hi], dst[lo:hi], t[lo:hi]
+                is32 = t.dtype == torch.float32
+            else:
+                is32 = np.asarray(t).dtype == np.float32
+                s_loc = _lib.to_device(src[lo:hi], np.int64, dev, "p_src")
+                d_loc = _lib.to_device(dst[lo:hi], np.int64, dev, "p_dst")
+                t_loc = _lib.to_device(t[lo:hi], np.float64, dev, "p_t")      # float32 -> float64 is exact
+            ev = torch.arange(lo, hi, device=dev, dtype=torch.int64)
+            t64 = t_loc.to(torch.float64)
+            nodes, times, gidx = route_roots(torch.cat([s_loc.to(torch.int64), d_loc.to(torch.int64)]),
+                                             torch.cat([t64, t64]), torch.cat([ev, ev + e]), plan.node_inner, world, dist)
+            # source endpoints first (stable): the single-way decoder then reads a prefix instead of a gather
+            is_dst = gidx >= e
+            order = torch.argsort(is_dst, stable=True)
+            nodes, times, gidx = nodes[order], times[order], gidx[order]
+            n_src = int(gidx.numel() - int(is_dst.sum()))
+            if is32:
+                times = times.to(torch.float32)       # the recursion's dtype rule follows the caller's dtype
+            routed = (nodes, times, gidx, n_src)
+            if key is not None:
+                plan.routing.clear()
+                plan.routing[key] = routed
+        nodes, times, gidx, n_src = routed
+        t0 = _mark("route_roots", t0)
         emb = model.compute_node_temporal_embeddings(nodes, times, model.num_layers, num_neighbors)
-    return emb, gidx
+        t0 = _mark("embed_roots", t0)
+    return emb, gidx, n_src
 
 
 def embed_events(model, src_node_ids, dst_node_ids, node_interact_times, num_neighbors: int = 20, sharded=None):
@@ -140,7 +186,7 @@ def embed_events(model, src_node_ids, dst_node_ids, node_interact_times, num_nei
             prepare_layer_memo(model, 2 * e, num_neighbors, False)
             return _embed_src_dst(model, src, dst, t, num_neighbors)
     try:
-        emb, gidx = _owned_roots(model, src, dst, t, num_neighbors, dist, rank, world)
+        emb, gidx, _ = _owned_roots(model, src, dst, t, num_neighbors, dist, rank, world)
         full = _scatter_all_reduce(emb, gidx, 2 * e, dist)
     finally:
         model._engine.shard_tag = None
@@ -178,15 +224,16 @@ def e_step_pass(model, decoder: MLPClassifier, src_node_ids, dst_node_ids, node_
         emb = (src_emb, dst_emb)
     else:
         try:
-            own, gidx = _owned_roots(model, src, dst, t, num_neighbors, dist, rank, world)
+            own, gidx, n_src = _owned_roots(model, src, dst, t, num_neighbors, dist, rank, world)
             if not double_way:                      # only the source endpoints are scored (PTCL/E_step.py:327-331)
-                keep = torch.nonzero(gidx < e).reshape(-1)
-                own_s, gidx_s = own.index_select(0, keep), gidx.index_select(0, keep)
+                own_s, gidx_s = own[:n_src], gidx[:n_src]
             else:
                 own_s, gidx_s = own, gidx
+            t0 = time.perf_counter()
             l_loc, p_loc = emit_pseudo_labels(decoder, own_s)
             packed = torch.cat([l_loc.to(torch.float32).unsqueeze(1), p_loc], dim=1)      # [n_own, 1 + C]
             full = _scatter_all_reduce(packed, gidx_s, ways * e, dist).reshape(ways, e, -1)
+            _mark("decode+combine", t0)
             labels, probs = full[:, :, 0].contiguous(), full[:, :, 1:].contiguous()
             emb = None
             if return_embeddings:

@@ -19,6 +19,8 @@ needs tables for its own position range:
 
 Host-side logic only; the collectives are NCCL over NVLink (gloo in the CPU tests).
 """
+import os
+
 import numpy as np
 import torch
 
@@ -84,7 +86,82 @@ class ShardPlan:
             _lib.check(_lib.lib().flid_graph_export_mirror(sampler.handle, _lib.ptr(mirror), _lib.stream()))
         local = mirror[self.pos_lo:self.pos_hi].to(torch.int64)
         self.send_idx, self.send_splits, self.recv_idx, self.recv_splits = exchange_lists(local, self.pos_bounds, rank)
+        self.routing = {}     # last routed root set of a device-resident pass (flid_b200.passes._owned_roots)
+        self.peers = {}       # (slot, rows, dn) -> (table, peer pointers, bounds, keep-alive)
+        self.p2p = None if os.environ.get("FLID_P2P", "1") != "0" else False   # None: not tried yet
+        self._flag = torch.zeros(1, dtype=torch.int32, device=device)
         del mirror
+
+    # ---- peer-mapped tables (CUDA IPC): the exchange as one kernel storing into the other ranks' HBM
+    def peer_table(self, slot: int, rows: int, dn: int, device, dist):
+        """A [rows, dn] float32 table of this rank that every other rank has mapped, or None when CUDA IPC is not
+        available on this box (the exchange then goes through all_to_all_single).  Allocated once per
+        (slot, shape) and reused by every pass; collective on first use."""
+        import ctypes as C
+        from . import _lib
+        key = (slot, rows, dn)
+        ent = self.peers.get(key)
+        if ent is not None:
+            return ent
+        if self.p2p is False:
+            return None
+        lib = _lib.lib()
+        ok, ptr, mapped = 1, C.c_void_p(None), []
+        handle = (C.c_ubyte * 64)()
+        try:
+            with torch.cuda.device(device):
+                _lib.check(lib.flid_peer_alloc(rows * dn * 4, C.byref(ptr), handle))
+        except Exception:
+            ok = 0
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle) if ok else None)
+        peers = (C.c_void_p * self.world)()
+        if ok and all(h is not None for h in handles):
+            try:
+                with torch.cuda.device(device):
+                    for r in range(self.world):
+                        if r == self.rank:
+                            peers[r] = ptr.value
+                        else:
+                            pp = C.c_void_p(None)
+                            buf = (C.c_ubyte * 64).from_buffer_copy(handles[r])
+                            _lib.check(lib.flid_peer_open(buf, C.byref(pp)))
+                            mapped.append(pp)
+                            peers[r] = pp.value
+            except Exception:
+                ok = 0
+        else:
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:           # some rank could not export / map: everyone uses the collective path
+            for pp in mapped:
+                lib.flid_peer_close(pp)
+            if ptr.value:
+                lib.flid_peer_free(ptr)
+            self.p2p = False
+            return None
+        self.p2p = True
+
+        class _DevArray:       # zero-copy torch view of the cudaMalloc'ed block
+            pass
+        arr = _DevArray()
+        arr.__cuda_array_interface__ = {"shape": (rows, dn), "typestr": "<f4", "data": (int(ptr.value), False),
+                                        "version": 3, "strides": None}
+        table = torch.as_tensor(arr, device=device)
+        bounds = (C.c_int64 * (self.world + 1))(*[int(x) for x in self.pos_bounds])
+        ent = (table, peers, bounds, arr)
+        self.peers[key] = ent
+        return ent
+
+    def exchange_rows_p2p(self, sampler, ent, dist):
+        """flid_memo_exchange_p2p + a stream-ordered cross-rank barrier (a one-element all-reduce): when it completes
+        on this rank, every rank's exchange kernel has finished storing into this rank's table."""
+        from . import _lib
+        table, peers, bounds, _ = ent
+        _lib.check(_lib.lib().flid_memo_exchange_p2p(sampler.handle, _lib.ptr(table), peers, bounds, self.world, self.rank,
+                                                     table.shape[1], _lib.stream()))
+        dist.all_reduce(self._flag)
 
     def exchange_rows(self, table: torch.Tensor, dist):
         """Send the rows this rank produced for other ranks' positions, receive the rows of this rank's positions

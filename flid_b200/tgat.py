@@ -251,7 +251,8 @@ def build_layer_memo(engine, depth, time_encoder, conv_layers, merge_layers, sam
         tables = []
         prev = None
         for level in range(1, depth):
-            t = torch.empty((rows, dn), dtype=torch.float32, device=device)
+            ent = plan.peer_table(level, rows, dn, device, dist) if plan is not None else None
+            t = ent[0] if ent is not None else torch.empty((rows, dn), dtype=torch.float32, device=device)
             if plan is None:
                 _lib.check(lib.flid_tgat_memo_build(h, sampler.handle, _lib.ptr(node_feat), _lib.ptr(edge_feat),
                                                     int(num_neighbors), level, _lib.ptr(prev), 0, rows, _lib.ptr(t),
@@ -266,7 +267,17 @@ def build_layer_memo(engine, depth, time_encoder, conv_layers, merge_layers, sam
                 _lib.check(lib.flid_tgat_last_stats(h, st))
                 engine.build_stats = [a + int(b) for a, b in zip(engine.build_stats, st[:3])]
             if plan is not None:
-                plan.exchange_rows(t, dist)
+                if os.environ.get("FLID_PASS_TRACE") == "1":
+                    from . import passes as _p
+                    import time as _time
+                    torch.cuda.synchronize()
+                    _t0 = _time.perf_counter()
+                    plan.exchange_rows_p2p(sampler, ent, dist) if ent is not None else plan.exchange_rows(t, dist)
+                    _p._mark("exchange", _t0)
+                elif ent is not None:
+                    plan.exchange_rows_p2p(sampler, ent, dist)
+                else:
+                    plan.exchange_rows(t, dist)
             tables.append(t)
             prev = t
         engine.memo[depth] = (key, tables)

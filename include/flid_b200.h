@@ -169,6 +169,20 @@ int flid_tgat_set_bulk_range(flid_tgat* m, int64_t pos_lo, int64_t pos_hi);
 /* partner index of the adjacency (position of the same event's entry in the other endpoint's list), int32[entries],
  * copied into a caller-owned device buffer; graphs built from events only                                      */
 int flid_graph_export_mirror(const flid_graph* g, int32_t* out_dev, flid_stream stream);
+/* Peer-mapped memo tables of an owner-partitioned pass (one process per GPU).  flid_peer_alloc: cudaMalloc + the
+ * 64-byte CUDA IPC handle to publish to the other ranks; flid_peer_open maps another rank's table into this process
+ * (lazy peer access over NVLink); close / free undo them.                                                        */
+int flid_peer_alloc(int64_t bytes, void** dev_ptr, void* handle_out_64_bytes);
+int flid_peer_open(const void* handle_64_bytes, void** dev_ptr);
+int flid_peer_close(void* dev_ptr);
+int flid_peer_free(void* dev_ptr);
+/* The per-level row exchange of the owner-partitioned memo build as one kernel: for every work item q of this rank's
+ * range [pos_bounds[rank], pos_bounds[rank+1]) whose produced row (position p = partner of q) belongs to another
+ * rank's range, copy row p of table_local into row p of that rank's table (peer_tables_host[dest], mapped with
+ * flid_peer_open), 16-byte stores over NVLink.  Every row has one producer; the caller puts a cross-rank barrier
+ * between this call and the first consumer of the tables.                                                      */
+int flid_memo_exchange_p2p(const flid_graph* g, const float* table_local, void* const* peer_tables_host,
+                           const int64_t* pos_bounds_host, int world, int rank, int row_dim, flid_stream stream);
 /* Bulk calls (flid_tgat_memo_build; flid_tgat_embed_memo with at least entries / k roots) project every
  * adjacency entry once per pass -- the reference's key / value projections (models/modules.py:191-197) hoisted
  * from "per neighbour slot" to "per entry" -- and keep those tables inside the handle, keyed on the weights, the

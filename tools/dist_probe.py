@@ -61,7 +61,7 @@ def main():
     with torch.no_grad():
         m.build_layer_memo(20, sharded=True)
     torch.cuda.synchronize()
-    log("sharded memo built")
+    log(f"sharded memo built; peer-mapped exchange: {plan.p2p}")
     for two in (False, True):
         m.invalidate_caches()
         p_sh, pr_sh, emb_sh = passes.e_step_pass(m, dec, g.src_node_ids, g.dst_node_ids, g.node_interact_times, 20, [],
