@@ -107,8 +107,10 @@ class _Engine:
         self.build_stats = None   # set to [0, 0, 0] to accumulate (evaluations, valid slots, queries) over memo builds
         self.served = {}     # depth -> (key, root queries answered without a memo)
         self.epoch = 0       # bumped by invalidate(): part of every cache key
-        # projected (per-entry K/V) formulation of bulk calls, flid_tgat_set_bulk_projection (FLID_BULK_KV=0: off)
-        self.bulk_projection = os.environ.get("FLID_BULK_KV", "1") != "0"
+        # projected (per-entry K/V) formulation of bulk calls, flid_tgat_set_bulk_projection.  Off by default: measured
+        # on the B200 it removes a third of the out-projection work but pays it back in per-entry
+        # GEMMs, 31.0 vs 30.8 ms per Reddit-shape pass in the fp32 mode; FLID_BULK_KV=1 / set_bulk_projection(True)
+        self.bulk_projection = os.environ.get("FLID_BULK_KV", "0") == "1"
         self.shard_tag = None         # (rank, world) while an owner-partitioned pass is running (flid_b200.passes)
         self.shard_plans = {}         # (sampler generation, rank, world) -> shard.ShardPlan
 
@@ -456,9 +458,9 @@ class TGAT(nn.Module):
             self._engine.memo.clear()
 
     def set_bulk_projection(self, enable: bool = True):
-        """Bulk calls (memo build, whole-pass embedding) project every adjacency entry once per pass and stream the
-        projected rows (csrc/bulk_kv.cu); results agree with the per-slot path to fp32 rounding.  ``False`` keeps
-        the per-slot stream everywhere: memoised results then equal the recursion bit for bit."""
+        """``True``: bulk calls (memo build, whole-pass embedding) project every adjacency entry once per pass and
+        stream the projected rows (csrc/bulk_kv.cu); results agree with the per-slot path to fp32 rounding.
+        ``False`` (default) keeps the per-slot stream everywhere: memoised results equal the recursion bit for bit."""
         self._engine.bulk_projection = bool(enable)
         self._engine.memo.clear()
 
