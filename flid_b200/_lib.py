@@ -243,9 +243,11 @@ def to_device_concat(arrays, dtype, device, tag, sync_follows=False):
     return out
 
 
-def to_host(t, tag):
-    """device tensor -> fresh numpy array via pinned staging (synchronises the current stream)."""
+def to_host(t, tag, copy=True):
+    """device tensor -> numpy array via pinned staging (synchronises the current stream).  ``copy=False`` returns
+    a view of the staging buffer, valid until the next ``to_host`` with the same tag."""
     stage = _pool.get(tag, t.numel(), t.dtype)
     stage.copy_(t.reshape(-1), non_blocking=True)
     torch.cuda.current_stream().synchronize()
-    return stage.numpy().reshape(t.shape).copy()
+    out = stage.numpy().reshape(t.shape)
+    return out.copy() if copy else out

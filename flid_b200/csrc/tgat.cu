@@ -27,9 +27,20 @@ __global__ void fold_qk_kernel(const float* __restrict__ wq, const float* __rest
     const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (idx >= (int64_t)H * kd * qd) return;
     const int row = (int)(idx / qd), b = (int)(idx % qd), h = row / kd, a = row % kd, hd = qd / H;
-    double s = 0.0;
-    for (int r = 0; r < hd; ++r) s += (double)wk[(int64_t)(h * hd + r) * kd + a] * (double)wq[(int64_t)(h * hd + r) * qd + b];
-    mfoldT[idx] = (float)(s * scale);
+    // four independent partial sums: the loop is bound by the latency of its loads, not by the float64 FMAs
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    const float* pk = wk + (int64_t)(h * hd) * kd + a;
+    const float* pq = wq + (int64_t)(h * hd) * qd + b;
+    int r = 0;
+#pragma unroll 2
+    for (; r + 3 < hd; r += 4) {
+        s0 += (double)__ldg(pk + (int64_t)r * kd) * (double)__ldg(pq + (int64_t)r * qd);
+        s1 += (double)__ldg(pk + (int64_t)(r + 1) * kd) * (double)__ldg(pq + (int64_t)(r + 1) * qd);
+        s2 += (double)__ldg(pk + (int64_t)(r + 2) * kd) * (double)__ldg(pq + (int64_t)(r + 2) * qd);
+        s3 += (double)__ldg(pk + (int64_t)(r + 3) * kd) * (double)__ldg(pq + (int64_t)(r + 3) * qd);
+    }
+    for (; r < hd; ++r) s0 += (double)__ldg(pk + (int64_t)r * kd) * (double)__ldg(pq + (int64_t)r * qd);
+    mfoldT[idx] = (float)(((s0 + s1) + (s2 + s3)) * scale);
 }
 
 __global__ void fold_vo_kernel(const float* __restrict__ wr, const float* __restrict__ wv, int qd, int kd, int H,
@@ -38,9 +49,19 @@ __global__ void fold_vo_kernel(const float* __restrict__ wr, const float* __rest
     const int zw = H * kd;
     if (idx >= (int64_t)qd * zw) return;
     const int o = (int)(idx / zw), c = (int)(idx % zw), h = c / kd, a = c % kd, hd = qd / H;
-    double s = 0.0;
-    for (int r = 0; r < hd; ++r) s += (double)wr[(int64_t)o * qd + h * hd + r] * (double)wv[(int64_t)(h * hd + r) * kd + a];
-    wvoT[idx] = (float)s;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    const float* pr = wr + (int64_t)o * qd + h * hd;
+    const float* pv = wv + (int64_t)(h * hd) * kd + a;
+    int r = 0;
+#pragma unroll 2
+    for (; r + 3 < hd; r += 4) {
+        s0 += (double)__ldg(pr + r) * (double)__ldg(pv + (int64_t)r * kd);
+        s1 += (double)__ldg(pr + r + 1) * (double)__ldg(pv + (int64_t)(r + 1) * kd);
+        s2 += (double)__ldg(pr + r + 2) * (double)__ldg(pv + (int64_t)(r + 2) * kd);
+        s3 += (double)__ldg(pr + r + 3) * (double)__ldg(pv + (int64_t)(r + 3) * kd);
+    }
+    for (; r < hd; ++r) s0 += (double)__ldg(pr + r) * (double)__ldg(pv + (int64_t)r * kd);
+    wvoT[idx] = (float)((s0 + s1) + (s2 + s3));
 }
 
 // te0 = cos(b) (time encoding of dt = 0) and the bounds the stream kernel uses to pick its cosine path

@@ -128,12 +128,22 @@ def _owned_roots(model, src, dst, t, num_neighbors, dist, rank, world):
         prepare_layer_memo(model, 2 * e, num_neighbors, True)
         t0 = _mark("memo_build+exchange", t0)
         plan = shard_plan(model._engine, model.neighbor_sampler, dev)
-        # device-resident inputs that did not change since the last pass (the E-step embeds the same event list in
-        # every EM iteration) keep their routing: it depends on the events and the partition only
-        key = None
+        # Inputs that did not change since the last pass (the E-step embeds the same event list in every EM iteration)
+        # keep their routing: it depends on the events and the partition only.  Device tensors are recognised by
+        # (pointer, version), host arrays by (pointer, shape) plus a sum / xor fingerprint of this rank's slice; the
+        # ranks agree on a hit with one small all-reduce, since a miss anywhere re-routes everywhere.
         if _is_tensor(src):
             key = tuple((x.data_ptr(), x._version, tuple(x.shape), x.dtype) for x in (src, dst, t))
+        else:
+            def fp(a):
+                v = np.ascontiguousarray(a[lo:hi]).view(np.uint64)
+                return (a.ctypes.data, a.shape, a.dtype.str, int(v.sum(dtype=np.uint64)), int(np.bitwise_xor.reduce(v)) if v.size else 0)
+            key = tuple(fp(np.asarray(x)) for x in (src, dst, t)) if all(np.asarray(x).dtype.itemsize == 8 for x in (src, dst, t)) else None
         routed = plan.routing.get(key) if key is not None else None
+        flag = torch.tensor([1 if routed is not None else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            routed = None
         if routed is None:
             if _is_tensor(src):
                 s_loc, d_loc, t_loc = src[lo:hi], dst[lo:hi], t[lo:hi]
