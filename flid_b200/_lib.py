@@ -100,6 +100,9 @@ _SIGNATURES = {
     "flid_tgn_rebuild": (C.c_int, [c_void, C.POINTER(TgnState), C.POINTER(GruWeights), c_void, c_void]),
     "flid_tgn_step": (C.c_int, [c_void, c_void, C.POINTER(TgnState), C.POINTER(GruWeights), c_void, c_void, c_void,
                                 c_void, c_void, c_void, C.c_int64, C.c_int, C.c_int, c_void, c_void, c_void]),
+    "flid_tgn_pass": (C.c_int, [c_void, c_void, C.POINTER(TgnState), C.POINTER(GruWeights), c_void, c_void, c_void,
+                                c_void, c_void, c_void, C.c_int64, C.c_int64, C.c_int, c_void, c_void, c_void, C.c_int,
+                                c_void]),
     "flid_pseudo_label": (C.c_int, [C.POINTER(MlpWeights), c_void, C.c_int64, c_void, c_void, c_void, c_void]),
     "flid_entropy_filter": (C.c_int, [C.POINTER(c_void), C.c_int, C.c_int64, C.c_int, C.c_float, c_void, c_void]),
     "flid_prob_filter": (C.c_int, [c_void, C.c_int64, C.c_int, C.c_float, c_void, c_void]),

@@ -73,6 +73,9 @@ struct flid_tgat {
     std::vector<flid::DevBuf> kv_tab;               // level l >= 2 (index l-2): [M+1, 2*qd] = [K | V] of entry p
     std::vector<KvKey> kv_tab_key;
     flid::DevBuf tgn_ids, tgn_times, tgn_eids, tgn_gi, tgn_gh;  // TGN step scratch (tgn.cu): per handle, hence per device
+    flid::DevBuf tgn_out, tgn_ctr;       // whole-pass driver (flid_tgn_pass): batch embeddings, device batch counter
+    cudaStream_t tgn_stream = nullptr;   // capturable stream of the whole-pass driver
+    cudaEvent_t tgn_ev = nullptr;
     int64_t stats[4] = {0, 0, 0, 0};
     int64_t valid_mult = 1;  // attention evaluations that consume each sampled neighbour list
     // optional per-kernel-class CUDA-event timing (bench.py's roofline numbers)

@@ -18,12 +18,20 @@
 namespace flid {
 
 
+// batch_ctr (nullable): device counter of the whole-pass driver (flid_tgn_pass) -- the batch starts at event
+// *batch_ctr * B of the arrays, so that one captured CUDA graph serves every batch of the pass
 __global__ void tgn_prep_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
                                 const double* __restrict__ times, const int64_t* __restrict__ eids, int64_t B,
                                 int64_t id_limit, int32_t* __restrict__ ids, double* __restrict__ t2,
-                                int32_t* __restrict__ e32, int32_t* __restrict__ err) {
+                                int32_t* __restrict__ e32, int32_t* __restrict__ err,
+                                const long long* __restrict__ batch_ctr = nullptr) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= B) return;
+    if (batch_ctr) {
+        const int64_t lo = (int64_t)(*batch_ctr) * B;
+        src += lo, dst += lo, times += lo;
+        if (eids) eids += lo;
+    }
     // id_limit = min(bank rows, sampler nodes + 1): an id the sampler has no list for is the reference's
     // IndexError in nodes_neighbor_times[node_id] (utils/utils.py:141), one beyond the bank its index error there
     int64_t s = src[i], d = dst[i], e = eids ? eids[i] : 0;
@@ -170,6 +178,23 @@ int flid_tgn_rebuild(flid_tgat* m, const flid_tgn_state* s, const flid_gru_weigh
     return FLID_OK;
 }
 
+// copy the [2B, dn] embeddings of the batch at *batch_ctr to rows [lo, lo + B) of the per-event outputs
+__global__ void tgn_store_kernel(const float* __restrict__ emb, int64_t B, int dn4, const long long* __restrict__ batch_ctr,
+                                 float* __restrict__ out_src, float* __restrict__ out_dst) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= 2 * B * dn4) return;
+    const int64_t row = idx / dn4, c = idx % dn4, lo = (int64_t)(*batch_ctr) * B;
+    const float4 v = reinterpret_cast<const float4*>(emb)[idx];
+    float4* dst = reinterpret_cast<float4*>(row < B ? out_src : out_dst) + (lo + (row < B ? row : row - B)) * dn4 + c;
+    *dst = v;
+}
+__global__ void tgn_advance_kernel(long long* batch_ctr) { *batch_ctr += 1; }
+
+static int tgn_step_body(flid_tgat* m, const flid_graph* g, const flid_tgn_state* s, const flid_gru_weights* gru,
+                         const float* node_raw, const float* edge_feat, const int64_t* src, const int64_t* dst,
+                         const double* times, const int64_t* eids, int64_t batch, int positive, int k, float* out,
+                         int32_t* err_flag, cudaStream_t st, const long long* batch_ctr);
+
 int flid_tgn_step(flid_tgat* m, const flid_graph* g, const flid_tgn_state* s, const flid_gru_weights* gru,
                   const float* node_raw, const float* edge_feat, const int64_t* src, const int64_t* dst,
                   const double* times, const int64_t* eids, int64_t batch, int positive, int k, float* out,
@@ -187,7 +212,15 @@ int flid_tgn_step(flid_tgat* m, const flid_graph* g, const flid_tgn_state* s, co
     FLID_REQUIRE(s->num_rows >= g->num_nodes + 1, "flid_tgn_step: memory bank has %lld rows but the sampler knows %lld nodes",
                  (long long)s->num_rows, (long long)g->num_nodes + 1);
     if (batch <= 0) return FLID_OK;
-    cudaStream_t st = (cudaStream_t)stream;
+    return tgn_step_body(m, g, s, gru, node_raw, edge_feat, src, dst, times, eids, batch, positive, k, out, err_flag,
+                         (cudaStream_t)stream, nullptr);
+}
+
+static int tgn_step_body(flid_tgat* m, const flid_graph* g, const flid_tgn_state* s, const flid_gru_weights* gru,
+                         const float* node_raw, const float* edge_feat, const int64_t* src, const int64_t* dst,
+                         const double* times, const int64_t* eids, int64_t batch, int positive, int k, float* out,
+                         int32_t* err_flag, cudaStream_t st, const long long* batch_ctr) {
+    using namespace flid;
     const int64_t B = batch, n2 = 2 * batch;
     FLID_TRY(m->tgn_ids.reserve(sizeof(int32_t) * n2));
     FLID_TRY(m->tgn_times.reserve(sizeof(double) * n2));
@@ -197,7 +230,7 @@ int flid_tgn_step(flid_tgat* m, const flid_graph* g, const flid_tgn_state* s, co
     int32_t* e32 = m->tgn_eids.as<int32_t>();
     tgn_prep_kernel<<<(unsigned)ceil_div(B, 256), 256, 0, st>>>(src, dst, times, eids, B,
                                                                std::min<int64_t>(s->num_rows, g->num_nodes + 1), ids, t2,
-                                                               e32, err_flag);
+                                                               e32, err_flag, batch_ctr);
     FLID_LAUNCH_CHECK();
     // (1)+(2): embeddings on memory' + raw   (models/MemoryModel.py:117-146)
     // out == nullptr: state update only (the training-mode host path computes the embeddings itself)
@@ -211,8 +244,102 @@ int flid_tgn_step(flid_tgat* m, const flid_graph* g, const flid_tgn_state* s, co
     FLID_LAUNCH_CHECK();
     FLID_TRY(gru_rows(m, s, gru, ids, n2, node_raw, 1, st));
     if (m->table_src == s->layer0 && m->table_rows > 0)
-        FLID_TRY(flid_tgat_refresh_node_rows(m, s->layer0, ids, n2, stream));
+        FLID_TRY(flid_tgat_refresh_node_rows(m, s->layer0, ids, n2, (flid_stream)st));
     return FLID_OK;
+}
+
+int flid_tgn_pass(flid_tgat* m, const flid_graph* g, const flid_tgn_state* s, const flid_gru_weights* gru,
+                  const float* node_raw, const float* edge_feat, const int64_t* src, const int64_t* dst,
+                  const double* times, const int64_t* eids, int64_t num_events, int64_t batch, int k, float* out_src,
+                  float* out_dst, int32_t* err_flag, int use_graph, flid_stream stream) {
+    using namespace flid;
+    FLID_REQUIRE(m && g && s && gru && node_raw && edge_feat && src && dst && times && eids && out_src && out_dst && err_flag,
+                 "flid_tgn_pass: null argument");
+    FLID_REQUIRE(m->have_weights, "flid_tgn_pass: weights not set");
+    FLID_REQUIRE(k > 0, "Number of sampled neighbors for each node should be greater than 0!");
+    FLID_REQUIRE(batch > 0, "flid_tgn_pass: batch size must be positive");
+    FLID_REQUIRE(s->num_rows >= g->num_nodes + 1, "flid_tgn_pass: memory bank has %lld rows but the sampler knows %lld nodes",
+                 (long long)s->num_rows, (long long)g->num_nodes + 1);
+    FLID_REQUIRE(m->dn % 4 == 0, "flid_tgn_pass: node dim must be a multiple of 4");
+    if (num_events <= 0) return FLID_OK;
+    cudaStream_t caller = (cudaStream_t)stream;
+    // the legacy default stream cannot be captured: run the pass on a stream of our own, ordered after / before the
+    // caller's stream with events
+    if (!m->tgn_stream) FLID_CUDA(cudaStreamCreateWithFlags(&m->tgn_stream, cudaStreamNonBlocking));
+    if (!m->tgn_ev) FLID_CUDA(cudaEventCreateWithFlags(&m->tgn_ev, cudaEventDisableTiming));
+    cudaStream_t st = m->tgn_stream;
+    FLID_CUDA(cudaEventRecord(m->tgn_ev, caller));
+    FLID_CUDA(cudaStreamWaitEvent(st, m->tgn_ev, 0));
+    const int64_t B = batch, full = num_events / B, rest = num_events - full * B;
+    FLID_TRY(m->tgn_out.reserve(sizeof(float) * 2 * B * m->dn));
+    FLID_TRY(m->tgn_ctr.reserve(sizeof(long long)));
+    float* emb = m->tgn_out.as<float>();
+    long long* ctr = m->tgn_ctr.as<long long>();
+    FLID_CUDA(cudaMemsetAsync(ctr, 0, sizeof(long long), st));
+    const int dn4 = m->dn / 4;
+    auto one_batch = [&]() -> int {   // the batch at *ctr, then ctr += 1
+        FLID_TRY(tgn_step_body(m, g, s, gru, node_raw, edge_feat, src, dst, times, eids, B, 1, k, emb, err_flag, st, ctr));
+        tgn_store_kernel<<<(unsigned)ceil_div(2 * B * dn4, 256), 256, 0, st>>>(emb, B, dn4, ctr, out_src, out_dst);
+        FLID_LAUNCH_CHECK();
+        tgn_advance_kernel<<<1, 1, 0, st>>>(ctr);
+        FLID_LAUNCH_CHECK();
+        return FLID_OK;
+    };
+    int status = FLID_OK;
+    int64_t done = 0;
+    if (full > 0) {
+        status = one_batch();   // direct launches: sizes every workspace, sets the kernel attributes
+        done = 1;
+    }
+    if (status == FLID_OK && full > done) {
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        if (use_graph && !m->prof_on && full - done >= 4) {
+            // every full batch runs the same launch sequence on fixed buffers; only the device counter differs
+            cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+            if (e == cudaSuccess) {
+                const int64_t launches0 = g_launches;
+                status = one_batch();
+                const int64_t per_batch = g_launches - launches0;
+                e = cudaStreamEndCapture(st, &graph);
+                if (status == FLID_OK && e == cudaSuccess && graph) e = cudaGraphInstantiate(&exec, graph, 0);
+                if (status == FLID_OK && e == cudaSuccess && exec) {
+                    g_launches -= per_batch;   // the capture itself launched nothing
+                    for (; done < full && e == cudaSuccess; ++done) {
+                        e = cudaGraphLaunch(exec, st);
+                        g_launches += per_batch;
+                    }
+                }
+                if (exec) cudaGraphExecDestroy(exec);
+                if (graph) cudaGraphDestroy(graph);
+                if (status == FLID_OK && e != cudaSuccess) {
+                    set_error("flid_tgn_pass: CUDA graph path failed: %s", cudaGetErrorString(e));
+                    status = FLID_ERR_CUDA;
+                }
+            } else {
+                cudaGetLastError();   // capture not available: fall through to direct launches
+            }
+        }
+        for (; status == FLID_OK && done < full; ++done) status = one_batch();
+    }
+    if (status == FLID_OK && rest > 0) {   // the last, shorter batch
+        const int64_t lo = full * B;
+        status = tgn_step_body(m, g, s, gru, node_raw, edge_feat, src + lo, dst + lo, times + lo, eids + lo, rest, 1, k, emb,
+                               err_flag, st, nullptr);
+        if (status == FLID_OK) {
+            cudaError_t e1 = cudaMemcpyAsync(out_src + lo * m->dn, emb, sizeof(float) * rest * m->dn, cudaMemcpyDeviceToDevice, st);
+            cudaError_t e2 = cudaMemcpyAsync(out_dst + lo * m->dn, emb + rest * m->dn, sizeof(float) * rest * m->dn,
+                                             cudaMemcpyDeviceToDevice, st);
+            if (e1 != cudaSuccess || e2 != cudaSuccess) {
+                set_error("flid_tgn_pass: output copy failed");
+                status = FLID_ERR_CUDA;
+            }
+        }
+    }
+    // hand the results back to the caller's stream
+    cudaEventRecord(m->tgn_ev, st);
+    cudaStreamWaitEvent(caller, m->tgn_ev, 0);
+    return status;
 }
 
 }  // extern "C"

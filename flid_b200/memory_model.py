@@ -304,6 +304,48 @@ class MemoryModel(nn.Module):
                 raise IndexError("flid_b200.MemoryModel: node or edge id out of range")
         return out[:b], out[b:]
 
+    def embed_pass(self, src_node_ids, dst_node_ids, node_interact_times, edge_ids, batch_size: int = 200,
+                   num_neighbors: int = 20, use_graph: bool = True):
+        """The whole chronological loop of ``compute_src_dst_node_temporal_embeddings(..., edges_are_positive=True)``
+        over consecutive batches of ``batch_size`` events as ONE C call (``flid_tgn_pass``): same kernels, same
+        batch boundaries and state updates as calling the method per batch, but the launch sequence of a batch is a
+        CUDA graph replayed with a device-side batch counter -- no per-batch Python, staging or synchronisation.
+        Eval / no-grad only.  Returns (src embeddings, dst embeddings) float32 [E, dn] on the device.  The
+        monotone-time assertion and the id range check are reported after the pass."""
+        dev = self.node_raw_features.device
+        _lib.require_cuda(dev)
+        if self.training:
+            raise RuntimeError("flid_b200.MemoryModel.embed_pass is an inference pass; call .eval() first")
+        sampler = self.embedding_module.neighbor_sampler
+        if not isinstance(sampler, NeighborSampler):
+            raise TypeError("flid_b200.MemoryModel needs a flid_b200.NeighborSampler")
+        emb = self.embedding_module
+        e = len(src_node_ids)
+        with torch.no_grad(), torch.cuda.device(dev):
+            h = self._engine.handle(self.num_layers, self.time_encoder, emb.temporal_conv_layers, emb.merge_layers, dev)
+            self._sync(h)
+            if self._err is None or self._err.device != dev:
+                self._err = torch.zeros(1, dtype=torch.int32, device=dev)
+            d_src = _lib.to_device(src_node_ids, np.int64, dev, "gp_src")
+            d_dst = _lib.to_device(dst_node_ids, np.int64, dev, "gp_dst")
+            d_t = _lib.to_device(node_interact_times, np.float64, dev, "gp_t")
+            d_e = _lib.to_device(edge_ids, np.int64, dev, "gp_e")
+            out_s = torch.empty((e, self.node_feat_dim), dtype=torch.float32, device=dev)
+            out_d = torch.empty_like(out_s)
+            s, g = self.memory_bank._c_state(), self._gru()
+            _lib.check(_lib.lib().flid_tgn_pass(h, sampler.handle, C.byref(s), C.byref(g), _lib.ptr(self.node_raw_features),
+                                                _lib.ptr(self.edge_raw_features), _lib.ptr(d_src), _lib.ptr(d_dst),
+                                                _lib.ptr(d_t), _lib.ptr(d_e), e, int(batch_size), int(num_neighbors),
+                                                _lib.ptr(out_s), _lib.ptr(out_d), _lib.ptr(self._err),
+                                                1 if use_graph else 0, _lib.stream()))
+            err = int(self._err.item())
+            if err:
+                self._err.zero_()
+                if err == 1:
+                    raise AssertionError("Trying to update memory to time in the past!")
+                raise IndexError("flid_b200.MemoryModel: node or edge id out of range")
+        return out_s, out_d
+
     def _autograd_step(self, sampler, src_node_ids, dst_node_ids, node_interact_times, edge_ids, positive, k):
         """Training-mode batch (models/MemoryModel.py:96-189 with dropout and a backward pass).
         Differentiable part in torch CUDA ops: the GRU update of every node with a pending message

@@ -263,18 +263,22 @@ def e_step_pass(model, decoder: MLPClassifier, src_node_ids, dst_node_ids, node_
 
 
 def tgn_pass(model, src_node_ids, dst_node_ids, node_interact_times, edge_ids, batch_size: int = 200,
-             num_neighbors: int = 20):
+             num_neighbors: int = 20, per_batch_calls: bool = False):
     """Full chronological TGN pass (PTCL/M_step.py:454-509 with model_name='TGN'): the bank is
     reset, events are fed in batches of ``batch_size`` (the batch boundary is part of the
-    semantics) and the per-event embeddings are returned as [E, dn] x 2."""
+    semantics) and the per-event embeddings are returned as [E, dn] x 2.
+    One C call with a CUDA graph per batch (``MemoryModel.embed_pass``); ``per_batch_calls=True`` issues the
+    reference's own loop of ``compute_src_dst_node_temporal_embeddings`` calls instead (same results, bit for bit)."""
     src, dst = np.asarray(src_node_ids), np.asarray(dst_node_ids)
     t, eid = np.asarray(node_interact_times), np.asarray(edge_ids)
     e = len(src)
     dev = model.node_raw_features.device
-    out_s = torch.empty((e, model.node_feat_dim), dtype=torch.float32, device=dev)
-    out_d = torch.empty_like(out_s)
     _require_eval(model)
     model.memory_bank.__init_memory_bank__()
+    if not per_batch_calls:
+        return model.embed_pass(src, dst, t, eid, batch_size, num_neighbors)
+    out_s = torch.empty((e, model.node_feat_dim), dtype=torch.float32, device=dev)
+    out_d = torch.empty_like(out_s)
     with torch.no_grad():
         for lo in range(0, e, batch_size):
             hi = min(lo + batch_size, e)

@@ -265,6 +265,17 @@ int flid_tgn_step(flid_tgat* m, const flid_graph* g, const flid_tgn_state* s, co
                   const double* times, const int64_t* eids, int64_t batch, int positive, int k,
                   float* out /* [2*batch, dn]: src rows then dst rows */, int32_t* err_flag, flid_stream stream);
 
+/* A whole chronological pass (the batch loop of PTCL/M_step.py:454-509 with model_name='TGN') as one call: events
+ * [0, num_events) of the device arrays are fed to flid_tgn_step's kernels in batches of `batch` (the batch boundary
+ * is part of the semantics), the per-event embeddings go to out_src / out_dst float32[num_events, dn].  use_graph:
+ * the launch sequence of a full batch is captured once as a CUDA graph and replayed with a device-side batch
+ * counter, so a batch costs one graph launch instead of ~25 kernel launches and a host synchronisation.  The error
+ * flag is cumulative and read by the caller after the pass (the reference raises inside the offending batch).   */
+int flid_tgn_pass(flid_tgat* m, const flid_graph* g, const flid_tgn_state* s, const flid_gru_weights* gru,
+                  const float* node_raw, const float* edge_feat, const int64_t* src, const int64_t* dst,
+                  const double* times, const int64_t* eids, int64_t num_events, int64_t batch, int k, float* out_src,
+                  float* out_dst, int32_t* err_flag, int use_graph, flid_stream stream);
+
 /* -------------------------------------------------------- pseudo-label scoring ----
  * MLPClassifier.forward (models/modules.py:86-97, eval) + softmax/argmax emission
  * (PTCL/E_step.py:334-335) fused: emb float32[n, in] -> probs float32[n, C], labels int64[n]. */

@@ -1052,3 +1052,31 @@ def test_bf16_projection_mode_tolerance_and_argmax():
     assert agree >= 0.999, f"bf16 mode: argmax agreement {agree:.5f} on {x32.shape[0]} roots"
     lscale = max(1.0, float(lg32.abs().max()))
     assert float((lg16 - lg32).abs().max()) <= 2e-2 * lscale
+
+
+def test_tgn_pass_graph_equals_per_batch_calls():
+    """flid_tgn_pass (one C call, CUDA graph per batch, device-side batch counter) against the reference's own loop
+    of per-batch calls: embeddings, bank, last-update times and pending messages identical bit for bit; ragged
+    last batch; the monotone-time assertion still fires."""
+    g = synth.wikipedia_shape(seed=2, scale=0.05)
+    p = otgn.default_params(172, 172, 100, 2, 2, seed=4, time_bias_scale=0.1)
+    e = g.num_interactions - 37            # not a multiple of the batch size
+    src, dst, ts, eid = g.src_node_ids[:e], g.dst_node_ids[:e], g.node_interact_times[:e], g.edge_ids[:e]
+    ref = None
+    for mode in ("calls", "graph", "nograph"):
+        m = tgn_model(g.node_raw_features, g.edge_raw_features, g.src_node_ids, g.dst_node_ids, g.edge_ids,
+                      g.node_interact_times, 2, p)
+        if mode == "calls":
+            a, c = passes.tgn_pass(m, src, dst, ts, eid, 200, 10, per_batch_calls=True)
+        else:
+            m.memory_bank.__init_memory_bank__()
+            a, c = m.embed_pass(src, dst, ts, eid, 200, 10, use_graph=(mode == "graph"))
+        state = (a, c, m.memory_bank.node_memories.data.clone(), m.memory_bank.node_last_updated_times.data.clone(),
+                 m.memory_bank._pending_msg.clone(), m.memory_bank._pending_ts.clone(), m.memory_bank._has_pending.clone())
+        if ref is None:
+            ref = state
+        else:
+            for x, y in zip(state, ref):
+                assert torch.equal(x, y), mode
+    with pytest.raises(AssertionError, match="time in the past"):
+        m.embed_pass(src[:400], dst[:400], ts[:400], eid[:400], 200, 10)      # the bank is already at the end of the stream
