@@ -412,6 +412,23 @@ static int prepare_weight(const float* W, int64_t sn, int64_t sk, int N, int K, 
     tc_prep_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(W, sn, sk, N, K, n_tile, n_blocks, k_chunks, single,
                                                                   reinterpret_cast<float4*>(w->buf));
     FLID_LAUNCH_CHECK();
+    // companion image for small launches
+    const int st_tile = 32, st_blocks = (N + st_tile - 1) / st_tile;
+    if (n_tile > st_tile) {
+        if (w->small_buf && (w->small_tile != st_tile || w->small_blocks != st_blocks)) {
+            FLID_CUDA(cudaDeviceSynchronize());
+            FLID_CUDA(cudaFree(w->small_buf));
+            w->small_buf = nullptr;
+        }
+        const int64_t stotal = (int64_t)st_blocks * k_chunks * 2 * C4 * st_tile;
+        if (!w->small_buf) FLID_CUDA(cudaMalloc((void**)&w->small_buf, (size_t)stotal * 16));
+        w->small_tile = st_tile, w->small_blocks = st_blocks;
+        tc_prep_kernel<<<(unsigned)ceil_div(stotal, 256), 256, 0, st>>>(W, sn, sk, N, K, st_tile, st_blocks, k_chunks, single,
+                                                                       reinterpret_cast<float4*>(w->small_buf));
+        FLID_LAUNCH_CHECK();
+    } else {
+        w->small_tile = 0, w->small_blocks = 0;
+    }
     return FLID_OK;
 }
 
@@ -425,7 +442,8 @@ int tc_prepare_weight_t(const float* Wt, int64_t ldw, int N, int K, TcWeight* w,
 
 void tc_free_weight(TcWeight* w) {
     if (w && w->buf) cudaFree(w->buf);
-    if (w) w->buf = nullptr;
+    if (w && w->small_buf) cudaFree(w->small_buf);
+    if (w) w->buf = nullptr, w->small_buf = nullptr;
 }
 
 template <int MS>
@@ -455,9 +473,18 @@ static int launch_ms(const TcGemmArgs& g, const TcWeight& w, TcShape sh, int sm_
     return FLID_OK;
 }
 
-int tc_gemm(const TcGemmArgs& g, const TcWeight& w, cudaStream_t st) {
+int tc_gemm(const TcGemmArgs& g, const TcWeight& w_in, cudaStream_t st) {
     if (g.M <= 0) return FLID_OK;
-    FLID_REQUIRE(w.buf != nullptr, "tc_gemm: weight not prepared");
+    FLID_REQUIRE(w_in.buf != nullptr, "tc_gemm: weight not prepared");
+    // few rows: the 32-column image, so that the 128-row tiles spread over many CTAs (same per-element arithmetic:
+    // the K order of the accumulation does not depend on the tile width)
+    TcWeight w = w_in;
+    static const bool small_ok = [] {
+        const char* e = getenv("FLID_GEMM_SMALL");
+        return !(e && e[0] == '0');
+    }();
+    if (small_ok && g.M <= TC_SMALL_M && w_in.small_buf != nullptr)
+        w.buf = w_in.small_buf, w.n_tile = w_in.small_tile, w.n_blocks = w_in.small_blocks;
     FLID_REQUIRE(g.w0 > 0 && g.w0 + g.w1 == w.K, "tc_gemm: A width %d+%d != weight K %d", g.w0, g.w1, w.K);
     FLID_REQUIRE((g.w0 % 4) == 0 && (g.w1 % 4) == 0 && (g.lda0 % 4) == 0 && (g.lda1 % 4) == 0,
                  "tc_gemm: segment widths / row strides must be multiples of 4 floats");

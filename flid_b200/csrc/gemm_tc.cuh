@@ -10,6 +10,7 @@
 namespace flid {
 
 constexpr int TC_KC = 16;  // K floats per pipeline stage (2 UMMA k-steps of 8)
+constexpr int TC_SMALL_M = 2048;  // launches up to this many rows use the 32-column weight image
 
 // weight pre-split into (hi, lo) and pre-tiled so that one (n-block, k-chunk) stage is a
 // single contiguous bulk copy:  [n_block][k_chunk][half][c4 = 4][n_tile][4 floats]
@@ -21,6 +22,10 @@ struct TcWeight {
     //    exactly representable in tf32), one MMA per product, fp32 accumulation -- the arithmetic of a bf16-in /
     //    fp32-acc GEMM on the same tensor pipe, with a third of the MMAs and half of the operand traffic
     int single = 0;
+    // second image with 32-column tiles for launches with few rows (per-batch calls, M <= TC_SMALL_M): a 128-row tile
+    // then spreads over N / 32 CTAs instead of one, which is what a B = 200 drop-in call (400 rows = 4 tiles) needs
+    float* small_buf = nullptr;
+    int small_tile = 0, small_blocks = 0;
     size_t bytes() const { return (size_t)n_blocks * k_chunks * 2 * (TC_KC / 4) * n_tile * 16; }
 };
 
