@@ -115,7 +115,9 @@ __device__ __forceinline__ Row4 ldg_row4(const void* p) {
 }
 
 // NV: float4 chunks per lane per row; TP: packed time-channel pairs per lane
-template <int H, int NV, int TP>
+// MULTI: more than 32 neighbour slots per target (taken in blocks of 32); the common k <= 32 instance keeps every
+// per-slot scalar in one register per lane and has no outer loop
+template <int H, int NV, int TP, bool MULTI>
 __global__ void __launch_bounds__(128, (H * NV <= 6 && NV <= 3) ? 4 : 2) attn_pk_kernel(AttnArgs a) {
     // the query fold u of the warp's target lives in shared memory (16-byte, lane-contiguous reads): 24-32
     // registers less than holding it, which is what lets a fourth block (16 warps) fit on the SM
@@ -131,17 +133,32 @@ __global__ void __launch_bounds__(128, (H * NV <= 6 && NV <= 3) ? 4 : 2) attn_pk
     // softmax state carries over.  Whether the target has any valid neighbour at all (the reference's all-masked
     // case: uniform weights over the padded rows) must be known before the first block is processed.
     bool all_masked = false;
-    if (k > 32) {
-        int any = 0;
-        for (int base = 0; base < k; base += 32)
-            any |= __any_sync(FULL, base + lane < k && __ldg(a.nbr + i * k + base + lane) != 0);
-        all_masked = !any;
-    }
     int nb_l = 0, e_l = 0;
     float dt_l = 0.f;
     int64_t hrow_l = 0;
     unsigned todo = 0u;
     u64 haddr = 0ull, eaddr = 0ull;
+    if constexpr (MULTI) {
+        int any = 0;
+        for (int base = 0; base < k; base += 32)
+            any |= __any_sync(FULL, base + lane < k && __ldg(a.nbr + i * k + base + lane) != 0);
+        all_masked = !any;
+    } else {
+        if (lane < k) {
+            nb_l = __ldg(a.nbr + i * k + lane);
+            e_l = __ldg(a.eid + i * k + lane);
+            dt_l = __ldg(a.dt + i * k + lane);
+            hrow_l = a.hrow_idx ? (int64_t)__ldg(a.hrow_idx + i * k + lane)
+                                : (a.hrow_by_id ? (int64_t)nb_l : a.hrow_offset + i * k + lane);
+        }
+        const unsigned valid = __ballot_sync(FULL, lane < k && nb_l != 0);
+        all_masked = (valid == 0u);
+        todo = all_masked ? (k >= 32 ? FULL : ((1u << k) - 1u)) : valid;
+        // byte addresses of this lane's slot rows (lane j owns slot j); the edge base is shifted so
+        // that chunk index f >= nv4 addresses the edge row directly
+        haddr = (u64)(reinterpret_cast<const char*>(a.hrow_base) + hrow_l * (int64_t)dn * 4);
+        eaddr = (u64)(reinterpret_cast<const char*>(a.edge_feat) + ((int64_t)e_l * ev4 - nv4) * 16);
+    }
     const float wmax = __ldg(a.time_bound), bmax = __ldg(a.time_bound + 1);
     const float* u = a.u_base + (a.u_index ? (int64_t)__ldg(a.u_index + i) : i) * (int64_t)(H * kd);
     // this warp's slice of shared memory: [H][NV][32] Row4 (row part of u) then [H][TP][32] packed pairs (time part)
@@ -289,7 +306,8 @@ __global__ void __launch_bounds__(128, (H * NV <= 6 && NV <= 3) ? 4 : 2) attn_pk
         }
     };
 
-    for (int base = 0; base < k; base += 32) {
+    for (int base = 0; base < (MULTI ? k : 1); base += 32) {
+      if constexpr (MULTI) {
         const int kb = min(32, k - base);
         if (lane < kb) {
             nb_l = __ldg(a.nbr + i * k + base + lane);
@@ -299,13 +317,13 @@ __global__ void __launch_bounds__(128, (H * NV <= 6 && NV <= 3) ? 4 : 2) attn_pk
                                 : (a.hrow_by_id ? (int64_t)nb_l : a.hrow_offset + i * k + base + lane);
         }
         const unsigned valid = __ballot_sync(FULL, lane < kb && nb_l != 0);
-        if (k <= 32) all_masked = (valid == 0u);
         todo = all_masked ? (kb >= 32 ? FULL : ((1u << kb) - 1u)) : valid;
         if (todo == 0u) continue;  // warp-uniform
         // byte addresses of this lane's slot rows; the edge base is shifted so that chunk index f >= nv4
         // addresses the edge row directly
         haddr = (u64)(reinterpret_cast<const char*>(a.hrow_base) + hrow_l * (int64_t)dn * 4);
         eaddr = (u64)(reinterpret_cast<const char*>(a.edge_feat) + ((int64_t)e_l * ev4 - nv4) * 16);
+      }
         int ja[G], jb[G];
         Row4 xa[G][NV], xb[G][NV];
         next_group(ja);
@@ -349,7 +367,10 @@ int launch_h(const AttnArgs& a, int nv, int tp, cudaStream_t st) {
     const unsigned blocks = (unsigned)ceil_div(a.n * 32, 128);
 #define FLID_ATTN_CASE(NV_, TP_)                                 \
     if (nv <= NV_ && tp <= TP_) {                                \
-        attn_pk_kernel<H, NV_, TP_><<<blocks, 128, 4 * H * 32 * (NV_ * 16 + TP_ * 8), st>>>(a);  \
+        if (a.k > 32)                                                                                  \
+            attn_pk_kernel<H, NV_, TP_, true><<<blocks, 128, 4 * H * 32 * (NV_ * 16 + TP_ * 8), st>>>(a);  \
+        else                                                                                           \
+            attn_pk_kernel<H, NV_, TP_, false><<<blocks, 128, 4 * H * 32 * (NV_ * 16 + TP_ * 8), st>>>(a); \
         FLID_LAUNCH_CHECK();                                     \
         return FLID_OK;                                          \
     }

@@ -78,7 +78,7 @@ struct TcShape {
 constexpr int TRACE_Q = 512;
 #define TRACE(role, q) do { if (sh.trace && blockIdx.x == 0 && (q) < TRACE_Q) sh.trace[(role) * TRACE_Q + (q)] = clock64(); } while (0)
 
-template <int MS>
+template <int MS, bool SINGLE>
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(TcGemmArgs g, const float4* __restrict__ wbuf, TcShape sh) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar_full[MAX_STAGES], bar_empty[MAX_STAGES], bar_acc_full[2], bar_acc_empty[2];
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(TcGemmArgs g, cons
             for (int i = 0; i < NL; ++i) {
                 const float4 x = v[i];
                 uint8_t* dst = st + (i >> 2) * A_SUB + (i & 3) * (32 * 16);  // sub-tile i / 4, rows (i % 4) * 32 + ...
-                if (sh.single) {
+                if (SINGLE) {
                     *reinterpret_cast<float4*>(dst) = make_float4(bf16_round(x.x), bf16_round(x.y), bf16_round(x.z), bf16_round(x.w));
                     continue;
                 }
@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(TcGemmArgs g, cons
                         const uint64_t d_alo = umma_desc(a0 + A_HALF, A_CSTRIDE, 128);
                         const uint32_t d = d0 + ms * sh.n_tile;
                         const uint64_t row_off = (uint64_t)((n_a * 16u) >> 4);  // start-address field is in 16 B units
-                        if (sh.single) {
+                        if (SINGLE) {
                             umma_tf32(d, d_ahi, d_bhi, idesc, (kc | j) ? 1u : 0u);
                             if (n_b) umma_tf32(d + n_a, d_ahi, d_bhi + row_off, idesc_b, (kc | j) ? 1u : 0u);
                             continue;
@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(TcGemmArgs g, cons
                 TRACE(5, tq);
                 ++tq;
                 uint8_t* st = smem + (size_t)s * stage_bytes + MS * A_SUB;
-                const uint32_t wbytes = sh.single ? b_half : 2 * b_half;  // the lo half is not used by a single-MMA product
+                const uint32_t wbytes = SINGLE ? b_half : 2 * b_half;  // the lo half is not used by a single-MMA product
                 mbar_arrive_expect_tx(&bar_full[s], wbytes);
                 bulk_g2s(st, wsrc + kc * chunk4, wbytes, &bar_full[s]);
                 if (++s == (uint32_t)sh.stages) s = 0, ph ^= 1;
@@ -450,7 +450,8 @@ template <int MS>
 static int launch_ms(const TcGemmArgs& g, const TcWeight& w, TcShape sh, int sm_count, int smem_max, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        FLID_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max - STATIC_SMEM));
+        FLID_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max - STATIC_SMEM));
+        FLID_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max - STATIC_SMEM));
         attr_set = true;
     }
     const size_t stage = (size_t)MS * A_SUB + 2 * (size_t)C4 * w.n_tile * 16;
@@ -467,8 +468,12 @@ static int launch_ms(const TcGemmArgs& g, const TcWeight& w, TcShape sh, int sm_
     const int64_t work = sh.m_groups * sh.n_blocks;
     FLID_REQUIRE(work < (1LL << 31) - 65536, "tc_gemm: too many tiles for one launch (M = %lld)", (long long)g.M);
     const unsigned grid = (unsigned)(work < sm_count ? work : sm_count);
-    gemm_tc_kernel<MS><<<grid, NTHREADS, sh.stages * stage + (sh.staged_epilogue ? EPI_BYTES : 0), st>>>(
-        g, reinterpret_cast<const float4*>(w.buf), sh);
+    if (w.single)
+        gemm_tc_kernel<MS, true><<<grid, NTHREADS, sh.stages * stage + (sh.staged_epilogue ? EPI_BYTES : 0), st>>>(
+            g, reinterpret_cast<const float4*>(w.buf), sh);
+    else
+        gemm_tc_kernel<MS, false><<<grid, NTHREADS, sh.stages * stage + (sh.staged_epilogue ? EPI_BYTES : 0), st>>>(
+            g, reinterpret_cast<const float4*>(w.buf), sh);
     FLID_LAUNCH_CHECK();
     return FLID_OK;
 }

@@ -54,6 +54,9 @@ struct TsShape {
 };
 #define TRACE(role, q) do { } while (0)
 
+// SINGLE: TcWeight::single (bf16-rounded operands, one MMA per product) as a compile-time switch, so that the fp32-grade
+// instance carries no trace of it
+template <bool SINGLE>
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_ts_kernel(TcGemmArgs g, const float4* __restrict__ wbuf, TsShape sh) {
     constexpr int MS = 1;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -143,13 +146,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_ts_kernel(TcGemmArgs g, c
                 const float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    hi[4 * i + e] = sh.single ? bf16_round(x[e]) : tf32_hi(x[e]);
+                    hi[4 * i + e] = SINGLE ? bf16_round(x[e]) : tf32_hi(x[e]);
                     lo[4 * i + e] = x[e] - hi[4 * i + e];
                 }
             }
             const uint32_t taddr = tmem + a_cols + stage * 32u + ((uint32_t)(pw * 32) << 16);
             tmem_st16(taddr, hi);
-            if (!sh.single) tmem_st16(taddr + 16u, lo);
+            if (!SINGLE) tmem_st16(taddr + 16u, lo);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
             mbar_arrive(&bar_full[stage]);
@@ -292,7 +295,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_ts_kernel(TcGemmArgs g, c
                     const uint64_t d_bhi = umma_desc(sb + (2 * j) * b_lbo, b_lbo, 128);
                     const uint64_t d_blo = umma_desc(sb + b_half + (2 * j) * b_lbo, b_lbo, 128);
                     const uint32_t a_hi = ta + 8u * j, a_lo = a_hi + 16u;
-                    if (sh.single) {
+                    if (SINGLE) {
                         umma_tf32_ts(d0, a_hi, d_bhi, idesc, (kc | j) ? 1u : 0u);
                         if (n_b) umma_tf32_ts(d0 + n_a, a_hi, d_bhi + (uint64_t)((n_a * 16u) >> 4), idesc_b, (kc | j) ? 1u : 0u);
                         continue;
@@ -322,7 +325,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_ts_kernel(TcGemmArgs g, c
             for (int kc = 0; kc < sh.k_chunks; ++kc) {
                 mbar_wait(&bar_empty[s], ph ^ 1);
                 uint8_t* st = smem + (size_t)s * stage_bytes;
-                const uint32_t wbytes = sh.single ? b_half : 2 * b_half;  // the lo half is not used by a single-MMA product
+                const uint32_t wbytes = SINGLE ? b_half : 2 * b_half;  // the lo half is not used by a single-MMA product
                 mbar_arrive_expect_tx(&bar_full[s], wbytes);
                 bulk_g2s(st, wsrc + kc * chunk4, wbytes, &bar_full[s]);
                 if (++s == (uint32_t)sh.stages) s = 0, ph ^= 1;
@@ -338,7 +341,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_ts_kernel(TcGemmArgs g, c
 int tc_gemm_ts(const TcGemmArgs& g, const TcWeight& w, int sm_count, int smem_max, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        FLID_CUDA(cudaFuncSetAttribute(gemm_tc_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max - STATIC_SMEM));
+        FLID_CUDA(cudaFuncSetAttribute(gemm_tc_ts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max - STATIC_SMEM));
+        FLID_CUDA(cudaFuncSetAttribute(gemm_tc_ts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max - STATIC_SMEM));
         attr_set = true;
     }
     TsShape sh;
@@ -359,8 +363,12 @@ int tc_gemm_ts(const TcGemmArgs& g, const TcWeight& w, int sm_count, int smem_ma
     const int64_t work = sh.m_groups * sh.n_blocks;
     FLID_REQUIRE(work < (1LL << 31) - 65536, "tc_gemm_ts: too many tiles for one launch");
     const unsigned grid = (unsigned)(work < sm_count ? work : sm_count);
-    gemm_tc_ts_kernel<<<grid, NTHREADS, sh.stages * stage + (sh.staged_epilogue ? EPI_BYTES : 0), st>>>(
-        g, reinterpret_cast<const float4*>(w.buf), sh);
+    if (w.single)
+        gemm_tc_ts_kernel<true><<<grid, NTHREADS, sh.stages * stage + (sh.staged_epilogue ? EPI_BYTES : 0), st>>>(
+            g, reinterpret_cast<const float4*>(w.buf), sh);
+    else
+        gemm_tc_ts_kernel<false><<<grid, NTHREADS, sh.stages * stage + (sh.staged_epilogue ? EPI_BYTES : 0), st>>>(
+            g, reinterpret_cast<const float4*>(w.buf), sh);
     FLID_LAUNCH_CHECK();
     return FLID_OK;
 }
