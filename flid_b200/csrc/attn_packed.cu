@@ -18,8 +18,6 @@
 // Padded slots (neighbour id 0) contribute exp(-1e10 - max) == 0 in the reference, so they are
 // skipped; a target with no neighbour at all gets the reference's uniform 1/k over its padded
 // rows (models/modules.py:217-224).
-#include <stdlib.h>
-
 #include "attn.cuh"
 
 namespace flid {
@@ -119,11 +117,8 @@ __device__ __forceinline__ Row4 ldg_row4(const void* p) {
 // NV: float4 chunks per lane per row; TP: packed time-channel pairs per lane
 // MULTI: more than 32 neighbour slots per target (taken in blocks of 32); the common k <= 32 instance keeps every
 // per-slot scalar in one register per lane and has no outer loop
-// MINB / PF: resident blocks per SM the kernel is compiled for, and whether the next slot pair's rows are
-// prefetched into registers while the current pair is reduced (PF) or latency is left to the other warps (more of
-// them fit: the prefetch buffer is a quarter of the registers).
-template <int H, int NV, int TP, bool MULTI, int MINB, bool PF>
-__global__ void __launch_bounds__(128, MINB) attn_pk_kernel(AttnArgs a) {
+template <int H, int NV, int TP, bool MULTI>
+__global__ void __launch_bounds__(128, (H * NV <= 6 && NV <= 3) ? 4 : 2) attn_pk_kernel(AttnArgs a) {
     // the query fold u of the warp's target lives in shared memory (16-byte, lane-contiguous reads): 24-32
     // registers less than holding it, which is what lets a fourth block (16 warps) fit on the SM
     extern __shared__ __align__(16) unsigned char u_smem[];
@@ -329,29 +324,19 @@ __global__ void __launch_bounds__(128, MINB) attn_pk_kernel(AttnArgs a) {
         haddr = (u64)(reinterpret_cast<const char*>(a.hrow_base) + hrow_l * (int64_t)dn * 4);
         eaddr = (u64)(reinterpret_cast<const char*>(a.edge_feat) + ((int64_t)e_l * ev4 - nv4) * 16);
       }
-        if constexpr (PF) {
-            int ja[G], jb[G];
-            Row4 xa[G][NV], xb[G][NV];
+        int ja[G], jb[G];
+        Row4 xa[G][NV], xb[G][NV];
+        next_group(ja);
+        load_group(ja, xa);
+        while (true) {
+            next_group(jb);
+            load_group(jb, xb);
+            process(ja, xa);
+            if (jb[0] < 0) break;
             next_group(ja);
             load_group(ja, xa);
-            while (true) {
-                next_group(jb);
-                load_group(jb, xb);
-                process(ja, xa);
-                if (jb[0] < 0) break;
-                next_group(ja);
-                load_group(ja, xa);
-                process(jb, xb);
-                if (ja[0] < 0) break;
-            }
-        } else {
-            while (todo) {
-                int ja[G];
-                Row4 xa[G][NV];
-                next_group(ja);
-                load_group(ja, xa);
-                process(ja, xa);
-            }
+            process(jb, xb);
+            if (ja[0] < 0) break;
         }
     }
 
@@ -380,24 +365,12 @@ __global__ void __launch_bounds__(128, MINB) attn_pk_kernel(AttnArgs a) {
 template <int H>
 int launch_h(const AttnArgs& a, int nv, int tp, cudaStream_t st) {
     const unsigned blocks = (unsigned)ceil_div(a.n * 32, 128);
-    static const int variant = [] {   // development knob: FLID_ATTN_VARIANT = 5 | 6 | 8 (blocks / SM, no register prefetch)
-        const char* e = getenv("FLID_ATTN_VARIANT");
-        return e ? atoi(e) : 0;
-    }();
 #define FLID_ATTN_CASE(NV_, TP_)                                 \
     if (nv <= NV_ && tp <= TP_) {                                \
-        constexpr int DEF_MINB = (H * NV_ <= 6 && NV_ <= 3) ? 4 : 2;                                   \
-        constexpr size_t SMEM = 4 * H * 32 * (NV_ * 16 + TP_ * 8);                                     \
         if (a.k > 32)                                                                                  \
-            attn_pk_kernel<H, NV_, TP_, true, DEF_MINB, true><<<blocks, 128, SMEM, st>>>(a);           \
-        else if (variant == 5 && DEF_MINB == 4)                                                        \
-            attn_pk_kernel<H, NV_, TP_, false, 5, false><<<blocks, 128, SMEM, st>>>(a);                \
-        else if (variant == 6 && DEF_MINB == 4)                                                        \
-            attn_pk_kernel<H, NV_, TP_, false, 6, false><<<blocks, 128, SMEM, st>>>(a);                \
-        else if (variant == 8 && DEF_MINB == 4)                                                        \
-            attn_pk_kernel<H, NV_, TP_, false, 8, false><<<blocks, 128, SMEM, st>>>(a);                \
+            attn_pk_kernel<H, NV_, TP_, true><<<blocks, 128, 4 * H * 32 * (NV_ * 16 + TP_ * 8), st>>>(a);  \
         else                                                                                           \
-            attn_pk_kernel<H, NV_, TP_, false, DEF_MINB, true><<<blocks, 128, SMEM, st>>>(a);          \
+            attn_pk_kernel<H, NV_, TP_, false><<<blocks, 128, 4 * H * 32 * (NV_ * 16 + TP_ * 8), st>>>(a); \
         FLID_LAUNCH_CHECK();                                     \
         return FLID_OK;                                          \
     }
