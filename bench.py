@@ -479,7 +479,10 @@ def run_tgat(b, ci, cfg):
     def step_e2e(store_prev):
         pseudo, probs, _ = one_pass(g.src_node_ids, g.dst_node_ids, g.node_interact_times, store_prev, world > 1)
         # host numpy out (views of the pinned staging buffers: no second host copy)
-        return _lib.to_host(pseudo, "b_pseudo", copy=False), _lib.to_host(probs, "b_probs", copy=False)
+        t0 = time.perf_counter()
+        out = _lib.to_host(pseudo, "b_pseudo", copy=False), _lib.to_host(probs, "b_probs", copy=False)
+        passes._mark("to_host", t0)
+        return out
 
     # probability store of the two earlier EM iterations (weights re-seeded 0, 1), then seed 2; the decoder is
     # made separable on the seed-0 embeddings so that the EST mask is mixed (asserted below)
@@ -524,7 +527,10 @@ def run_tgat(b, ci, cfg):
 
     # ---- end-to-end: host buffers in, host labels/probs out, through the public pass API
     step_e2e(store)
+    passes.trace_report()
     ev_ms, wall_ms = b.timed(lambda: step_e2e(store), args.steps)
+    e2e_trace = passes.trace_report()
+    e2e_trace["event_ms_total"], e2e_trace["wall_ms_total"] = ev_ms, wall_ms
     ms_e2e = max(ev_ms, wall_ms)
     clock_info = clocks.stop() if rank == 0 else None
     ms_total, ms_e2e = b.max_over_ranks(ms_total, ms_e2e)
@@ -617,6 +623,7 @@ def run_tgat(b, ci, cfg):
                                                if plans and plans[0].p2p else "all_to_all_single (NCCL)")
     if os.environ.get("FLID_PASS_TRACE") == "1":
         line["pass_trace_ms_per_step"] = {k: v / args.steps for k, v in pass_trace.items()}
+        line["e2e_trace_ms_per_step"] = {k: v / args.steps for k, v in e2e_trace.items()}
     line.update(secondary_modes)
     print(json.dumps(line), flush=True)
     assert 0.05 < kept < 0.95, f"EST mask is degenerate: kept fraction {kept}"

@@ -488,8 +488,10 @@ int tc_gemm(const TcGemmArgs& g, const TcWeight& w_in, cudaStream_t st) {
         const char* e = getenv("FLID_GEMM_SMALL");
         return !(e && e[0] == '0');
     }();
-    if (small_ok && g.M <= TC_SMALL_M && w_in.small_buf != nullptr)
+    const bool lnf = g.ln_c1 != nullptr;   // LayerNorm fold: A-from-TMEM kernel only (one path whatever the row count)
+    if (small_ok && g.M <= TC_SMALL_M && w_in.small_buf != nullptr && !lnf)
         w.buf = w_in.small_buf, w.n_tile = w_in.small_tile, w.n_blocks = w_in.small_blocks;
+    FLID_REQUIRE(!lnf || (w.n_blocks == 1 && (512 - w.n_tile) / 32 >= 4), "tc_gemm: the LayerNorm fold needs a single n block");
     FLID_REQUIRE(g.w0 > 0 && g.w0 + g.w1 == w.K, "tc_gemm: A width %d+%d != weight K %d", g.w0, g.w1, w.K);
     FLID_REQUIRE((g.w0 % 4) == 0 && (g.w1 % 4) == 0 && (g.lda0 % 4) == 0 && (g.lda1 % 4) == 0,
                  "tc_gemm: segment widths / row strides must be multiples of 4 floats");
@@ -510,7 +512,7 @@ int tc_gemm(const TcGemmArgs& g, const TcWeight& w_in, cudaStream_t st) {
             const char* e = getenv("FLID_GEMM_TS");
             ts = (e && e[0] == '0') ? 0 : 1;
         }
-        if (ts && w.n_blocks == 1 && (512 - w.n_tile) / 32 >= 4)  // >= 4 stages of A columns next to the accumulator
+        if ((ts || lnf) && w.n_blocks == 1 && (512 - w.n_tile) / 32 >= 4)  // >= 4 stages of A columns next to the accumulator
             return tc_gemm_ts(g, w, sm_count, smem_max, st);
     }
     TcShape sh;

@@ -44,6 +44,21 @@ struct TcGemmArgs {
     const float* bias = nullptr;
     int64_t M = 0;
     int relu = 0;
+    // LayerNorm folded into this product (fc1 of the MergeLayer after the attention block, models/modules.py:235-238 then
+    // :66): A0 holds residual_fc's outputs; the producers add the residual row [ln_self | ln_tail] on the fly and
+    // accumulate each row's sum and sum of squares (float64); the weight image is W diag(gamma); the epilogue applies
+    //     out = act( rstd * (acc - mean * ln_c1[n]) + ln_add[row][n] )
+    // with ln_c1 = row sums of W diag(gamma) and ln_add = everything that does not depend on the normalised row
+    // (W beta + bias + the raw-feature part of fc1, one row per node).  A-from-TMEM kernel, single n block only.
+    const float* ln_self = nullptr;      // [*, ln_self_w], row = ln_self_idx ? ln_self_idx[m] : m
+    const int32_t* ln_self_idx = nullptr;
+    int ln_self_w = 0;
+    const float* ln_tail = nullptr;      // [w0 - ln_self_w] constant tail of the residual
+    const float* ln_c1 = nullptr;        // [N]
+    const float* ln_add = nullptr;       // [*, ln_add_ld], row = ln_add_idx[m]
+    const int32_t* ln_add_idx = nullptr;
+    int64_t ln_add_ld = 0;
+    float ln_eps = 1e-5f;
 };
 
 // (re)build the tiled hi/lo image of W[N, K] (row stride ldw); allocates w->buf on first use

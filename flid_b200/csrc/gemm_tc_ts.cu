@@ -56,7 +56,10 @@ struct TsShape {
 
 // SINGLE: TcWeight::single (bf16-rounded operands, one MMA per product) as a compile-time switch, so that the fp32-grade
 // instance carries no trace of it
-template <bool SINGLE>
+// LNF: LayerNorm folded into the product (TcGemmArgs::ln_*): producers add the residual and keep row statistics,
+// the (staged) epilogue rescales.  Row statistics live behind the epilogue staging area: [2 items][2 groups][128 rows].
+constexpr int LN_BYTES = 2 * 2 * 128 * 16;
+template <bool SINGLE, bool LNF>
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_ts_kernel(TcGemmArgs g, const float4* __restrict__ wbuf, TsShape sh) {
     constexpr int MS = 1;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -104,6 +107,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_ts_kernel(TcGemmArgs g, c
         Cursor lc{blockIdx.x, blockIdx.x / nblk, blockIdx.x % nblk, pg};
         const float* p0 = g.A0;
         const float* p1 = g.A1;
+        const float* pr = g.ln_self;   // LNF: residual row of this thread's row
         bool row_ok = false;
         auto bind_row = [&]() {
             const int64_t row = (int64_t)lc.mg * 128 + pw * 32 + lane;
@@ -112,6 +116,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_ts_kernel(TcGemmArgs g, c
             if (row_ok) {
                 p0 = g.A0 + (g.idx0 ? (int64_t)__ldg(g.idx0 + row) : row) * g.lda0;
                 if (g.w1 > 0) p1 = g.A1 + (g.idx1 ? (int64_t)__ldg(g.idx1 + row) : row) * g.lda1;
+                if (LNF) pr = g.ln_self + (g.ln_self_idx ? (int64_t)__ldg(g.ln_self_idx + row) : row) * g.ln_self_w;
             }
         };
         if (lc.kc >= sh.k_chunks) lc.kc -= sh.k_chunks, next_item(lc);
@@ -123,7 +128,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_ts_kernel(TcGemmArgs g, c
                 const int k = k0 + 4 * i;
                 const float* src = k < g.w0 ? p0 + k : p1 + (k - g.w0);
                 v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (row_ok && k < ktot) v[i] = __ldg(reinterpret_cast<const float4*>(src));
+                if (row_ok && k < ktot) {
+                    v[i] = __ldg(reinterpret_cast<const float4*>(src));
+                    if (LNF) {   // + residual [self row | constant tail]
+                        const float4 r = __ldg(reinterpret_cast<const float4*>(k < g.ln_self_w ? pr + k : g.ln_tail + (k - g.ln_self_w)));
+                        v[i].x += r.x, v[i].y += r.y, v[i].z += r.z, v[i].w += r.w;
+                    }
+                }
             }
             lc.kc += 2;
             if (lc.kc >= sh.k_chunks) {  // next work item (rare path)
@@ -137,9 +148,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_ts_kernel(TcGemmArgs g, c
         const uint32_t total_q = my_items * (uint32_t)sh.k_chunks;
         uint32_t sq = (uint32_t)pg;
         uint32_t stage = (uint32_t)pg % (uint32_t)sh.stages, phase = 0;
+        double ln_s1 = 0.0, ln_s2 = 0.0;   // LNF: sum and sum of squares of this thread's share of its row
+        double2* ln_stats = reinterpret_cast<double2*>(smem + (size_t)sh.stages * stage_bytes + EPI_BYTES);
         auto store_next = [&](const float4 (&v)[4]) {
             mbar_wait(&bar_empty[stage], phase ^ 1);
             tc_fence_after();
+            if (LNF) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const double a = v[i].x, b = v[i].y, c = v[i].z, d = v[i].w;
+                    ln_s1 += (a + b) + (c + d);
+                    ln_s2 += (a * a + b * b) + (c * c + d * d);
+                }
+                // last chunk of this group in the work item: publish the partial statistics before the stage is handed
+                // over (the epilogue reads them after the accumulators are complete)
+                const uint32_t item = sq / (uint32_t)sh.k_chunks;
+                if ((sq + 2) / (uint32_t)sh.k_chunks != item) {
+                    ln_stats[((item & 1u) * 2 + pg) * 128 + pw * 32 + lane] = make_double2(ln_s1, ln_s2);
+                    ln_s1 = 0.0, ln_s2 = 0.0;
+                }
+            }
             float hi[16], lo[16];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -199,11 +227,54 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_ts_kernel(TcGemmArgs g, c
                 }
                 const int64_t row = row0 + lane;
                 float* crow = (row < g.M) ? g.C + (g.cidx ? (int64_t)__ldg(g.cidx + row) : row) * g.ldc : nullptr;
+                // LNF: mean / rstd and the additive row of the four rows this lane stores
+                float ln_mean[4], ln_rstd[4];
+                const float* ln_addrow[4];
+                if (LNF) {
+                    const double2* st2 = reinterpret_cast<const double2*>(smem + (size_t)sh.stages * stage_bytes + EPI_BYTES) +
+                                         (size_t)(it & 1u) * 2 * 128;
+                    const double inv_k = 1.0 / (double)ktot;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int rl = ew * 32 + j * 8 + sr;   // row within the tile
+                        const double2 a = st2[rl], b = st2[128 + rl];
+                        const double mean = (a.x + b.x) * inv_k;
+                        const double var = fmax((a.y + b.y) * inv_k - mean * mean, 0.0);
+                        ln_mean[j] = (float)mean;
+                        ln_rstd[j] = (float)(1.0 / sqrt(var + (double)g.ln_eps));
+                        const int64_t r = row0 + j * 8 + sr;
+                        ln_addrow[j] = (r < g.M) ? g.ln_add + (int64_t)__ldg(g.ln_add_idx + r) * g.ln_add_ld : g.ln_add;
+                    }
+                }
                 for (int c0 = 0; c0 < sh.n_tile; c0 += 16) {
                     float v[16];
                     tmem_ld16(taddr + (uint32_t)c0, v);
                     const int n0 = nb * sh.n_tile + c0;
                     if (n0 >= sh.N) continue;  // warp-uniform: padding columns of the last n block
+                    if (LNF) {
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4)
+                            *reinterpret_cast<float4*>(stg + lane * EPI_LD + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        __syncwarp();
+                        if (n0 + sc < sh.N) {
+                            const float4 c1 = __ldg(reinterpret_cast<const float4*>(g.ln_c1 + n0 + sc));
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                if (crow4[j] == nullptr) continue;
+                                const float4 o = *reinterpret_cast<const float4*>(stg + (j * 8 + sr) * EPI_LD + sc);
+                                const float4 ad = __ldg(reinterpret_cast<const float4*>(ln_addrow[j] + n0 + sc));
+                                float4 y;
+                                y.x = fmaf(ln_rstd[j], fmaf(-ln_mean[j], c1.x, o.x), ad.x);
+                                y.y = fmaf(ln_rstd[j], fmaf(-ln_mean[j], c1.y, o.y), ad.y);
+                                y.z = fmaf(ln_rstd[j], fmaf(-ln_mean[j], c1.z, o.z), ad.z);
+                                y.w = fmaf(ln_rstd[j], fmaf(-ln_mean[j], c1.w, o.w), ad.w);
+                                if (g.relu) y.x = fmaxf(y.x, 0.f), y.y = fmaxf(y.y, 0.f), y.z = fmaxf(y.z, 0.f), y.w = fmaxf(y.w, 0.f);
+                                *reinterpret_cast<float4*>(crow4[j] + n0 + sc) = y;
+                            }
+                        }
+                        __syncwarp();
+                        continue;
+                    }
                     if (vec_ok && !staged) {
                         if (crow != nullptr) {
                             if (n0 + 16 <= sh.N) {
@@ -341,9 +412,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_ts_kernel(TcGemmArgs g, c
 int tc_gemm_ts(const TcGemmArgs& g, const TcWeight& w, int sm_count, int smem_max, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        FLID_CUDA(cudaFuncSetAttribute(gemm_tc_ts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max - STATIC_SMEM));
-        FLID_CUDA(cudaFuncSetAttribute(gemm_tc_ts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max - STATIC_SMEM));
+        FLID_CUDA(cudaFuncSetAttribute(gemm_tc_ts_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max - STATIC_SMEM));
+        FLID_CUDA(cudaFuncSetAttribute(gemm_tc_ts_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max - STATIC_SMEM));
+        FLID_CUDA(cudaFuncSetAttribute(gemm_tc_ts_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max - STATIC_SMEM));
+        FLID_CUDA(cudaFuncSetAttribute(gemm_tc_ts_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max - STATIC_SMEM));
         attr_set = true;
+    }
+    const bool lnf = g.ln_c1 != nullptr;
+    if (lnf) {
+        FLID_REQUIRE(g.ln_self && g.ln_tail && g.ln_add && g.ln_add_idx && g.w1 == 0 && g.ln_self_w % 4 == 0 &&
+                         g.ln_self_w <= g.w0 && (g.ldc & 3) == 0 && (w.N & 3) == 0 && (g.ln_add_ld & 3) == 0,
+                     "tc_gemm_ts: bad LayerNorm-fold arguments");
     }
     TsShape sh;
     sh.trace = nullptr;
@@ -353,9 +432,10 @@ int tc_gemm_ts(const TcGemmArgs& g, const TcWeight& w, int sm_count, int smem_ma
     // two accumulator sets when that still leaves >= 4 stages of A columns, else one
     sh.acc_bufs = (2 * w.n_tile <= 512 && (512 - 2 * w.n_tile) / 32 >= 4) ? 2 : 1;
     const int a_stages = (512 - sh.acc_bufs * w.n_tile) / 32;
-    sh.staged_epilogue = (g.cidx != nullptr || w.k_chunks >= 48 || w.N >= 512) ? 1 : 0;
+    sh.staged_epilogue = (lnf || g.cidx != nullptr || w.k_chunks >= 48 || w.N >= 512) ? 1 : 0;
     const size_t stage = 2 * (size_t)C4 * w.n_tile * 16;
-    const size_t ring_bytes = (size_t)(smem_max - STATIC_SMEM) - (sh.staged_epilogue ? EPI_BYTES : 0);
+    const size_t tail_bytes = (sh.staged_epilogue ? EPI_BYTES : 0) + (lnf ? LN_BYTES : 0);
+    const size_t ring_bytes = (size_t)(smem_max - STATIC_SMEM) - tail_bytes;
     int stages = (int)(ring_bytes / stage);
     stages = stages > MAX_STAGES ? MAX_STAGES : stages;
     sh.stages = stages < a_stages ? stages : a_stages;
@@ -363,12 +443,18 @@ int tc_gemm_ts(const TcGemmArgs& g, const TcWeight& w, int sm_count, int smem_ma
     const int64_t work = sh.m_groups * sh.n_blocks;
     FLID_REQUIRE(work < (1LL << 31) - 65536, "tc_gemm_ts: too many tiles for one launch");
     const unsigned grid = (unsigned)(work < sm_count ? work : sm_count);
-    if (w.single)
-        gemm_tc_ts_kernel<true><<<grid, NTHREADS, sh.stages * stage + (sh.staged_epilogue ? EPI_BYTES : 0), st>>>(
-            g, reinterpret_cast<const float4*>(w.buf), sh);
-    else
-        gemm_tc_ts_kernel<false><<<grid, NTHREADS, sh.stages * stage + (sh.staged_epilogue ? EPI_BYTES : 0), st>>>(
-            g, reinterpret_cast<const float4*>(w.buf), sh);
+    const size_t dyn = sh.stages * stage + tail_bytes;
+    const float4* wb = reinterpret_cast<const float4*>(w.buf);
+    if (lnf) {
+        if (w.single)
+            gemm_tc_ts_kernel<true, true><<<grid, NTHREADS, dyn, st>>>(g, wb, sh);
+        else
+            gemm_tc_ts_kernel<false, true><<<grid, NTHREADS, dyn, st>>>(g, wb, sh);
+    } else if (w.single) {
+        gemm_tc_ts_kernel<true, false><<<grid, NTHREADS, dyn, st>>>(g, wb, sh);
+    } else {
+        gemm_tc_ts_kernel<false, false><<<grid, NTHREADS, dyn, st>>>(g, wb, sh);
+    }
     FLID_LAUNCH_CHECK();
     return FLID_OK;
 }

@@ -85,6 +85,31 @@ __global__ void u0_kernel(const float* __restrict__ mfoldT, const float* __restr
     u0[row] = s;
 }
 
+// LayerNorm fold of fc1: w1g = fc1_w[:, :qd] diag(gamma); c1 = row sums of w1g; c2 = fc1_w[:, :qd] beta + fc1_b
+__global__ void ln_fold_prep_kernel(const float* __restrict__ fc1_w, const float* __restrict__ fc1_b,
+                                    const float* __restrict__ gamma, const float* __restrict__ beta, int dn, int qd,
+                                    float* __restrict__ w1g, float* __restrict__ c1, float* __restrict__ c2) {
+    const int c = blockIdx.x;          // one block per output row
+    const int ld = qd + dn;
+    double s1 = 0.0, s2 = 0.0;
+    for (int k = threadIdx.x; k < qd; k += blockDim.x) {
+        const float w = fc1_w[(int64_t)c * ld + k];
+        const float wg = w * gamma[k];
+        w1g[(int64_t)c * qd + k] = wg;
+        s1 += (double)wg, s2 += (double)w * (double)beta[k];
+    }
+    __shared__ double sh1[32], sh2[32];
+    for (int o = 16; o > 0; o >>= 1) s1 += __shfl_xor_sync(FULL, s1, o), s2 += __shfl_xor_sync(FULL, s2, o);
+    if ((threadIdx.x & 31) == 0) sh1[threadIdx.x >> 5] = s1, sh2[threadIdx.x >> 5] = s2;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) a += sh1[w], b += sh2[w];
+        c1[c] = (float)a;
+        c2[c] = (float)(b + (double)fc1_b[c]);
+    }
+}
+
 // ------------------------------------------------------------------ root conversion
 __global__ void roots_kernel(const int64_t* __restrict__ nodes, const double* __restrict__ times, int64_t n,
                              int64_t num_nodes, int32_t* __restrict__ ids, double* __restrict__ t_out,
@@ -298,6 +323,19 @@ static int output_chain(flid_tgat* m, int layer, int64_t n, const float* Z, cons
         const int zw = kv ? m->qd + m->H * m->T : m->zw;
         t1.A0 = Z, t1.lda0 = zw, t1.w0 = zw, t1.C = O, t1.ldc = m->qd, t1.bias = ld.res_b, t1.M = n;
         FLID_TRY(tc_gemm(t1, kv ? ld.tc_o2 : ld.tc_o, st));
+        if (m->ln_fold && m->nt_src == merge_feat && ids != nullptr && ld.nt.p != nullptr) {
+            // bulk passes: + residual, LayerNorm and fc1 in one GEMM (no LayerNorm kernel, no normalised rows in HBM,
+            // fc1's raw-feature block as a per-node table); see TcGemmArgs::ln_*
+            TcGemmArgs t2;
+            t2.A0 = O, t2.lda0 = m->qd, t2.w0 = m->qd, t2.C = Hd, t2.ldc = m->dn, t2.M = n, t2.relu = 1;
+            t2.ln_self = self_base, t2.ln_self_idx = self_idx, t2.ln_self_w = m->dn, t2.ln_tail = m->te0;
+            t2.ln_c1 = ld.ln_c1, t2.ln_add = ld.nt.as<float>(), t2.ln_add_idx = ids, t2.ln_add_ld = m->dn;
+            FLID_TRY(tc_gemm(t2, ld.tc_f1g, st));
+            TcGemmArgs t3;
+            t3.A0 = Hd, t3.lda0 = m->dn, t3.w0 = m->dn, t3.C = out, t3.ldc = m->dn, t3.bias = ld.fc2_b, t3.M = n;
+            t3.cidx = out_idx;
+            return tc_gemm(t3, ld.tc_f2, st);
+        }
         FLID_TRY(launch_ln(O, self_base, self_idx, m->te0, ld.ln_w, ld.ln_b, A, n, m->dn, m->T, st));
         TcGemmArgs t2;   // fc1 on [attention output | layer-0 row of the target], ReLU fused
         t2.A0 = A, t2.lda0 = m->qd, t2.w0 = m->qd, t2.A1 = merge_feat, t2.lda1 = m->dn, t2.idx1 = ids, t2.w1 = m->dn;
@@ -760,6 +798,7 @@ void flid_tgat_free(flid_tgat* m) {
         flid::tc_free_weight(&l.tc_q), flid::tc_free_weight(&l.tc_o), flid::tc_free_weight(&l.tc_f1);
         flid::tc_free_weight(&l.tc_f2);
         flid::kv_free_layer(l);
+        cudaFree(l.lnw), flid::tc_free_weight(&l.tc_f1g), flid::tc_free_weight(&l.tc_f1n), l.nt.release();
     }
     m->kv_vn1.release(), m->kv_ve1.release(), m->kv_s1.release();
     for (auto& t : m->kv_tab) t.release();
@@ -817,7 +856,18 @@ int flid_tgat_set_weights(flid_tgat* m, const float* time_w, const float* time_b
         FLID_TRY(tc_prepare_weight(d.fc1_w, qd + dn, dn, qd + dn, &d.tc_f1, st, m->numeric));
         FLID_TRY(tc_prepare_weight(d.fc2_w, dn, dn, dn, &d.tc_f2, st, m->numeric));
         FLID_TRY(kv_fold_layer(m, l, w.query_w, w.key_w, w.value_w, w.res_w, st));
+        if (m->use_tc && qd % 4 == 0 && dn % 4 == 0) {
+            if (!d.lnw) {
+                FLID_CUDA(cudaMalloc((void**)&d.lnw, sizeof(float) * ((size_t)dn * qd + 2 * dn)));
+                d.w1g = d.lnw, d.ln_c1 = d.lnw + (size_t)dn * qd, d.ln_c2 = d.ln_c1 + dn;
+            }
+            ln_fold_prep_kernel<<<dn, 128, 0, st>>>(d.fc1_w, d.fc1_b, d.ln_w, d.ln_b, dn, qd, d.w1g, d.ln_c1, d.ln_c2);
+            FLID_LAUNCH_CHECK();
+            FLID_TRY(tc_prepare_weight(d.w1g, qd, dn, qd, &d.tc_f1g, st, m->numeric));
+            FLID_TRY(tc_prepare_weight(d.fc1_w + qd, qd + dn, dn, dn, &d.tc_f1n, st, m->numeric));
+        }
     }
+    m->nt_src = nullptr;
     m->weights_version += 1;
     m->have_weights = true;
     m->table_src = nullptr;  // cached query folds are stale now
@@ -833,6 +883,19 @@ int flid_tgat_cache_node_table(flid_tgat* m, const float* node_feat, int64_t row
     FLID_TRY(query_fold(m, 0, node_feat, nullptr, rows, m->table.as<float>(), (cudaStream_t)stream));
     m->table_src = node_feat;
     m->table_rows = rows;
+    // per-layer node part of the LayerNorm-folded fc1: node_feat . fc1_w[:, qd:]^T + (fc1_w[:, :qd] beta + fc1_b)
+    m->nt_src = nullptr;
+    if (m->use_tc && m->ln_fold) {
+        for (auto& ld : m->layers) {
+            if (!ld.tc_f1n.buf) return FLID_OK;
+            FLID_TRY(ld.nt.reserve(sizeof(float) * (size_t)rows * m->dn));
+            TcGemmArgs t;
+            t.A0 = node_feat, t.lda0 = m->dn, t.w0 = m->dn, t.C = ld.nt.as<float>(), t.ldc = m->dn, t.bias = ld.ln_c2;
+            t.M = rows;
+            FLID_TRY(tc_gemm(t, ld.tc_f1n, (cudaStream_t)stream));
+        }
+        m->nt_src = node_feat;
+    }
     return FLID_OK;
 }
 
@@ -853,6 +916,7 @@ int flid_tgat_refresh_node_rows(flid_tgat* m, const float* node_feat, const int3
     FLID_TRY(query_fold(m, 0, node_feat, row_ids, n, m->ws_u.as<float>(), st));
     scatter_rows_kernel<<<(unsigned)n, 256, 0, st>>>(m->ws_u.as<float>(), row_ids, n, m->zw, m->table.as<float>());
     FLID_LAUNCH_CHECK();
+    m->nt_src = nullptr;   // the per-node fc1 tables of the LayerNorm fold are not refreshed (mutable tables: TGN)
     return FLID_OK;
 }
 
@@ -979,6 +1043,14 @@ int flid_tgat_set_self_from_memo(flid_tgat* m, int enable) {
     using namespace flid;
     FLID_REQUIRE(m != nullptr, "flid_tgat_set_self_from_memo: null handle");
     m->self_from_memo = enable != 0;
+    return FLID_OK;
+}
+
+int flid_tgat_set_ln_fold(flid_tgat* m, int enable) {
+    using namespace flid;
+    FLID_REQUIRE(m != nullptr, "flid_tgat_set_ln_fold: null handle");
+    if (m->ln_fold != (enable != 0)) m->table_src = nullptr, m->table_rows = 0, m->nt_src = nullptr;  // rebuild with / without the fc1 tables
+    m->ln_fold = enable != 0;
     return FLID_OK;
 }
 

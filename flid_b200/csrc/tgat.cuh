@@ -14,6 +14,11 @@ struct LayerDev {
     float *res_b = nullptr, *ln_w = nullptr, *ln_b = nullptr;              // [qd]
     float *fc1_w = nullptr, *fc1_b = nullptr, *fc2_w = nullptr, *fc2_b = nullptr;  // merge layer, reference layout
     TcWeight tc_q, tc_o, tc_f1, tc_f2;  // hi/lo-split, tiled images for the tcgen05 GEMM
+    // LayerNorm folded into fc1 (bulk passes; gemm_tc.cuh TcGemmArgs::ln_*)
+    float* lnw = nullptr;                  // one allocation: w1g [dn, qd] = fc1_w[:, :qd] diag(gamma), c1 [dn] its row sums,
+    float *w1g = nullptr, *ln_c1 = nullptr, *ln_c2 = nullptr;   // c2 [dn] = fc1_w[:, :qd] beta + fc1_b
+    TcWeight tc_f1g, tc_f1n;               // W diag(gamma) (K = qd) and the raw-feature block fc1_w[:, qd:] (K = dn)
+    DevBuf nt;                             // [table rows, dn] = node_feat . fc1_w[:, qd:]^T + c2, per cached node table
     // projected bulk path (bulk_kv.cu): per-entry K/V rows instead of per-slot raw rows.  Row layouts are
     // head-interleaved (kv_perm) so that a lane of the stream kernel only ever touches its own head.
     float* kvw = nullptr;     // one allocation holding the small fp32 matrices below
@@ -30,6 +35,8 @@ struct flid_tgat {
     int dn = 0, de = 0, T = 0, L = 0, H = 0;
     int qd = 0, kd = 0, hd = 0, zw = 0;  // zw = H * kd
     bool have_weights = false;
+    bool ln_fold = false;   // flid_tgat_set_ln_fold: bulk passes fold LayerNorm into fc1 (one path whatever the chunk size)
+    const float* nt_src = nullptr;   // node table the per-layer `nt` tables were built from
     int numeric = 0;     // flid_tgat_set_numeric_mode: 0 fp32-grade (3xTF32), 1 bf16-rounded operands / one MMA per product
     bool use_tc = true;  // projection GEMMs on tcgen05 (3xTF32); false = fp32 SIMT (FLID_GEMM=simt)
     float *time_w = nullptr, *time_b = nullptr, *te0 = nullptr, *time_bound = nullptr;

@@ -14,6 +14,9 @@ from .pseudo_label import MLPClassifier, emit_pseudo_labels, entropy_filter, pro
 import os
 import time
 
+# whole-pass calls with at least this many root queries (a global property of the call, so that every rank and the
+# unsharded run decide alike) use the LayerNorm-folded fc1 (flid_tgat_set_ln_fold)
+BULK_MIN_ROOTS = 1
 _TRACE = os.environ.get("FLID_PASS_TRACE") == "1"      # development: synchronising phase timer of the sharded pass
 _trace_acc = {}
 
@@ -191,15 +194,21 @@ def embed_events(model, src_node_ids, dst_node_ids, node_interact_times, num_nei
     else:
         src, dst, t = np.asarray(src_node_ids), np.asarray(dst_node_ids), np.asarray(node_interact_times)
     e = len(src)
-    if not sharded or world == 1:
-        with torch.no_grad():
-            prepare_layer_memo(model, 2 * e, num_neighbors, False)
-            return _embed_src_dst(model, src, dst, t, num_neighbors)
+    eng = getattr(model, "_engine", None)
+    if eng is None:                 # a backbone without the TGAT engine (GraphMixer, TCL): plain full-size call
+        return model.compute_src_dst_node_temporal_embeddings(np.asarray(src), np.asarray(dst), np.asarray(t), num_neighbors)
+    bulk = 2 * e >= BULK_MIN_ROOTS
     try:
+        eng.ln_fold = bulk          # whole-pass calls fold LayerNorm into fc1: one path for every chunk of the pass
+        if not sharded or world == 1:
+            with torch.no_grad():
+                prepare_layer_memo(model, 2 * e, num_neighbors, False)
+                return _embed_src_dst(model, src, dst, t, num_neighbors)
         emb, gidx, _ = _owned_roots(model, src, dst, t, num_neighbors, dist, rank, world)
         full = _scatter_all_reduce(emb, gidx, 2 * e, dist)
     finally:
-        model._engine.shard_tag = None
+        eng.shard_tag = None
+        eng.ln_fold = False
     return full[:e], full[e:]
 
 
@@ -234,6 +243,7 @@ def e_step_pass(model, decoder: MLPClassifier, src_node_ids, dst_node_ids, node_
         emb = (src_emb, dst_emb)
     else:
         try:
+            model._engine.ln_fold = 2 * e >= BULK_MIN_ROOTS
             own, gidx, n_src = _owned_roots(model, src, dst, t, num_neighbors, dist, rank, world)
             if not double_way:                      # only the source endpoints are scored (PTCL/E_step.py:327-331)
                 own_s, gidx_s = own[:n_src], gidx[:n_src]
@@ -251,14 +261,17 @@ def e_step_pass(model, decoder: MLPClassifier, src_node_ids, dst_node_ids, node_
                 emb = (both[:e], both[e:])
         finally:
             model._engine.shard_tag = None
+            model._engine.ln_fold = False
     if not double_way:
         probs = probs[0]
     store.append(probs)
     pseudo = labels.contiguous()
+    t0 = time.perf_counter()
     if ps_filter == 'entropy':
         pseudo = entropy_filter(pseudo, store, threshold)
     elif ps_filter == 'probability':
         pseudo = prob_filter(pseudo, store, threshold)
+    _mark("filter", t0)
     return pseudo, probs, (emb if return_embeddings or not sharded else None)
 
 

@@ -112,6 +112,8 @@ class _Engine:
         # GEMMs, 31.0 vs 30.8 ms per Reddit-shape pass in the fp32 mode; FLID_BULK_KV=1 / set_bulk_projection(True)
         self.bulk_projection = os.environ.get("FLID_BULK_KV", "0") == "1"
         self.shard_tag = None         # (rank, world) while an owner-partitioned pass is running (flid_b200.passes)
+        self.ln_fold = False          # bulk passes fold LayerNorm into fc1 (flid_tgat_set_ln_fold); set by flid_b200.passes
+        self.ln_state = {}            # depth -> value last handed to the C handle
         self.shard_plans = {}         # (sampler generation, rank, world) -> shard.ShardPlan
 
     def invalidate(self):
@@ -132,6 +134,7 @@ class _Engine:
             except Exception:
                 pass
         self.handles.clear()
+        self.ln_state.clear()
 
     def handle(self, depth, time_encoder, conv_layers, merge_layers, device):
         lib = _lib.lib()
@@ -177,6 +180,11 @@ class _Engine:
             self.versions[depth] = fp
             self.tables.pop(depth, None)
             self.memo.pop(depth, None)
+        want = bool(self.ln_fold) and os.environ.get("FLID_LN_FOLD", "1") != "0"
+        if self.ln_state.get(depth) != want:
+            _lib.check(lib.flid_tgat_set_ln_fold(h, 1 if want else 0))
+            self.ln_state[depth] = want
+            self.tables.pop(depth, None)      # the node table is re-cached with / without the per-node fc1 tables
         return h
 
     def ensure_table(self, depth, h, node_feat):

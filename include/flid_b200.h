@@ -208,6 +208,13 @@ int flid_tgat_set_self_from_memo(flid_tgat* m, int enable);
  * Takes effect at the next flid_tgat_set_weights (the weight images are tiled per mode).  The gather /
  * time-encode / softmax stream and the decoder stay fp32 in both modes.                              */
 int flid_tgat_set_numeric_mode(flid_tgat* m, int mode);
+/* Bulk passes: fold "+ residual, LayerNorm" (models/modules.py:235-238) into the first MergeLayer product
+ * (:66): the GEMM's producers add the residual row and keep each row's sum and sum of squares, its epilogue applies
+ * rstd * (acc - mean * rowsum(W diag(gamma))) + (W beta + bias + raw-feature block, one row per node).  No LayerNorm
+ * kernel, no normalised rows in HBM, K = qd instead of qd + dn.  Same algebra, different rounding order (fp32
+ * tolerance, not bit-identical to the unfolded path); the switch is per handle so that every chunk of a pass takes
+ * the same path whatever its size.  Takes effect at the next flid_tgat_cache_node_table.  Static node tables only. */
+int flid_tgat_set_ln_fold(flid_tgat* m, int enable);
 /* upper bound on layer-1 targets processed per internal chunk (workspace ~7 KB per target;
  * default 606208 = 148 x 4096).  Results do not depend on it.                                   */
 int flid_tgat_set_chunk_targets(flid_tgat* m, int64_t max_layer1_targets);
