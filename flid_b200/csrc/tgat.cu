@@ -487,10 +487,11 @@ int tgat_embed_ids(flid_tgat* m, const flid_graph* g, const float* node_feat, co
 // feature of target p itself is memo_{l-1}[p] (same key).
 __global__ void memo_targets_kernel(const int2* __restrict__ adj, const double* __restrict__ ts, int64_t M,
                                     int64_t lo, int64_t n, int32_t* __restrict__ ids, double* __restrict__ times,
-                                    const int32_t* __restrict__ mirror, int32_t* __restrict__ rows) {
+                                    const int32_t* __restrict__ mirror, int32_t* __restrict__ rows, int64_t range_hi) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     int64_t p = lo + i;
+    if (p >= range_hi) p = M;   // the item after an owner range: the padded slot's query
     // Owner-major order: work item q evaluates the table row of q's partner entry, i.e. the query
     // (owner of q, time of q).  Consecutive items then ask for the same node at increasing times and
     // their neighbour windows overlap in all but one slot, so the gathered rows are cache hits.
@@ -603,7 +604,7 @@ int tgat_memo_build(flid_tgat* m, const flid_graph* g, const float* node_feat, c
     const int64_t M = g->num_entries;
     const bool use_table = level == 1 && (m->table_src == node_feat && m->table_rows > 0);
     const int64_t chunk = std::max<int64_t>(1, m->max_l1_targets);
-    const int64_t ws_rows = std::max<int64_t>(1, std::min(chunk, row_hi - row_lo));
+    const int64_t ws_rows = std::max<int64_t>(1, std::min(chunk, row_hi - row_lo)) + (with_padded_row ? 1 : 0);
     FLID_TRY(reserve_layer_ws(m, ws_rows, k, !use_table));
     unsigned long long* d_valid = m->ws_misc.as<unsigned long long>();
     FLID_CUDA(cudaMemsetAsync(d_valid, 0, sizeof(unsigned long long), st));
@@ -628,13 +629,21 @@ int tgat_memo_build(flid_tgat* m, const flid_graph* g, const float* node_feat, c
     // chunks of the range, then (owner-range builds) the padded slot's query as an item of its own
     std::vector<std::pair<int64_t, int64_t>> chunks;
     for (int64_t c0 = row_lo; c0 < row_hi; c0 += chunk) chunks.push_back({c0, std::min(chunk, row_hi - c0)});
-    if (with_padded_row && row_hi <= M) chunks.push_back({M, 1});
+    if (with_padded_row && row_hi <= M) {
+        // the padded slot's query rides along as one more item of the last chunk (memo_targets_kernel maps items past
+        // the range to row M) instead of costing a launch chain of its own
+        if (!chunks.empty() && chunks.back().second < chunk)
+            chunks.back().second += 1;
+        else
+            chunks.push_back({M, 1});
+    }
     for (const auto& ch : chunks) {
         const int64_t c0 = ch.first, n = ch.second;
         {
             ProfScope prof(m, PROF_SAMPLE, st);
             memo_targets_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(g->adj, g->ts, M, c0, n, w_ids, w_times,
-                                                                         owner_major ? g->mirror : nullptr, w_rows);
+                                                                         owner_major ? g->mirror : nullptr, w_rows,
+                                                                         with_padded_row ? row_hi : M + 1);
             FLID_LAUNCH_CHECK();
             level_sample_kernel<<<(unsigned)ceil_div(n * LS_W, 256), 256, 0, st>>>(
                 g->indptr, g->adj, g->ts, w_ids, w_times, n, 0, k, m->ws_nbr.as<int32_t>(), m->ws_eid.as<int32_t>(),
