@@ -22,6 +22,8 @@ def _free_port():
 
 
 def _worker(rank, world, port, q):
+    import faulthandler
+    faulthandler.dump_traceback_later(240, exit=True)      # a wedged collective must not hang the suite
     import torch.distributed as dist
     import flid_b200
     from flid_b200 import passes, synth
@@ -65,9 +67,14 @@ def test_sharded_pass_equals_single_gpu_world2():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    out = q.get(timeout=600)
+    try:
+        out = q.get(timeout=300)
+    finally:
+        for p in procs:
+            p.join(timeout=60)
+            if p.is_alive():
+                p.terminate()
     for p in procs:
-        p.join(timeout=120)
         assert p.exitcode == 0
     for two, flags in out.items():
         assert all(flags), (two, flags)
