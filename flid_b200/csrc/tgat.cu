@@ -816,6 +816,7 @@ void flid_tgat_free(flid_tgat* m) {
                             &m->ws_nbr, &m->ws_eid, &m->ws_dt, &m->ws_h, &m->ws_u, &m->ws_z, &m->ws_o,
                             &m->ws_a, &m->ws_hd, &m->ws_misc, &m->ws_rid, &m->ws_rt, &m->ws_bad, &m->ws_pos, &m->ws_self, &m->ws_sort,
                             &m->tgn_ids, &m->tgn_times, &m->tgn_eids, &m->tgn_gi, &m->tgn_gh, &m->ws_win, &m->tgn_out, &m->tgn_ctr};
+    flid::tc_free_weight(&m->tc_gih), flid::tc_free_weight(&m->tc_ghh);
     if (m->tgn_stream) cudaStreamDestroy(m->tgn_stream);
     if (m->tgn_ev) cudaEventDestroy(m->tgn_ev);
     for (auto* b : bufs) b->release();

@@ -81,6 +81,8 @@ struct flid_tgat {
     std::vector<KvKey> kv_tab_key;
     flid::DevBuf tgn_ids, tgn_times, tgn_eids, tgn_gi, tgn_gh;  // TGN step scratch (tgn.cu): per handle, hence per device
     flid::DevBuf tgn_out, tgn_ctr;       // whole-pass driver (flid_tgn_pass): batch embeddings, device batch counter
+    flid::TcWeight tc_gih, tc_ghh;       // GRU weights tiled for the tcgen05 GEMM (flid_tgn_rebuild), fp32-grade in both numeric modes
+    const float *gru_ih_src = nullptr, *gru_hh_src = nullptr;
     cudaStream_t tgn_stream = nullptr;   // capturable stream of the whole-pass driver
     cudaEvent_t tgn_ev = nullptr;
     int64_t stats[4] = {0, 0, 0, 0};

@@ -145,10 +145,22 @@ static int gru_rows(flid_tgat* m, const flid_tgn_state* s, const flid_gru_weight
     FLID_TRY(m->tgn_gi.reserve(sizeof(float) * rows * 3 * dn));
     FLID_TRY(m->tgn_gh.reserve(sizeof(float) * rows * 3 * dn));
     float *gi = m->tgn_gi.as<float>(), *gh = m->tgn_gh.as<float>();
-    GemmArgs a{s->pending_msg, msg, ids, gru->weight_ih, msg, gi, 3 * dn, gru->bias_ih, rows, 3 * dn, msg, 0, 0};
-    FLID_TRY(launch_gemm(a, st));
-    GemmArgs b{s->memories, dn, ids, gru->weight_hh, dn, gh, 3 * dn, gru->bias_hh, rows, 3 * dn, dn, 0, 0};
-    FLID_TRY(launch_gemm(b, st));
+    if (m->use_tc && m->gru_ih_src == gru->weight_ih && m->gru_hh_src == gru->weight_hh && m->tc_gih.buf && m->tc_ghh.buf &&
+        msg % 4 == 0 && dn % 4 == 0) {
+        // W_ih x + b_ih and W_hh h + b_hh on the tcgen05 GEMM (3xTF32, fp32-grade): two ~19 us launches per batch of
+        // 400 rows instead of two ~32 us SIMT ones (ncu launch list of the pass, profiles/r2_tgn_pass_launches.txt)
+        TcGemmArgs a;
+        a.A0 = s->pending_msg, a.lda0 = msg, a.idx0 = ids, a.w0 = msg, a.C = gi, a.ldc = 3 * dn, a.bias = gru->bias_ih, a.M = rows;
+        FLID_TRY(tc_gemm(a, m->tc_gih, st));
+        TcGemmArgs b;
+        b.A0 = s->memories, b.lda0 = dn, b.idx0 = ids, b.w0 = dn, b.C = gh, b.ldc = 3 * dn, b.bias = gru->bias_hh, b.M = rows;
+        FLID_TRY(tc_gemm(b, m->tc_ghh, st));
+    } else {
+        GemmArgs a{s->pending_msg, msg, ids, gru->weight_ih, msg, gi, 3 * dn, gru->bias_ih, rows, 3 * dn, msg, 0, 0};
+        FLID_TRY(launch_gemm(a, st));
+        GemmArgs b{s->memories, dn, ids, gru->weight_hh, dn, gh, 3 * dn, gru->bias_hh, rows, 3 * dn, dn, 0, 0};
+        FLID_TRY(launch_gemm(b, st));
+    }
     tgn_gate_kernel<<<(unsigned)ceil_div(rows * dn, 256), 256, 0, st>>>(*s, ids, rows, dn, gi, gh, node_raw,
                                                                        reset_scratch);
     FLID_LAUNCH_CHECK();
@@ -173,6 +185,12 @@ int flid_tgn_rebuild(flid_tgat* m, const flid_tgn_state* s, const flid_gru_weigh
     using namespace flid;
     FLID_REQUIRE(m && s && gru && node_raw, "flid_tgn_rebuild: null argument");
     cudaStream_t st = (cudaStream_t)stream;
+    if (m->use_tc) {   // the caller rebuilds whenever the GRU parameters changed: re-tile them here
+        const int dn = m->dn, msg = 2 * m->dn + m->T + m->de;
+        FLID_TRY(tc_prepare_weight(gru->weight_ih, msg, 3 * dn, msg, &m->tc_gih, st, 0));
+        FLID_TRY(tc_prepare_weight(gru->weight_hh, dn, 3 * dn, dn, &m->tc_ghh, st, 0));
+        m->gru_ih_src = gru->weight_ih, m->gru_hh_src = gru->weight_hh;
+    }
     FLID_TRY(gru_rows(m, s, gru, nullptr, s->num_rows, node_raw, 0, st));
     if (m->have_weights) FLID_TRY(flid_tgat_cache_node_table(m, s->layer0, s->num_rows, stream));
     return FLID_OK;
