@@ -718,7 +718,7 @@ def run_tgn(b, ci, cfg):
 
     def step_e2e():
         a, c = step()
-        return _lib.to_host(a, "b_tgn_src"), _lib.to_host(c, "b_tgn_dst")
+        return _lib.to_host(a, "b_tgn_src", copy=False), _lib.to_host(c, "b_tgn_dst", copy=False)
 
     for _ in range(max(args.warmup, 3)):
         step()
