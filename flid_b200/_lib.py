@@ -109,6 +109,19 @@ _SIGNATURES = {
     "flid_prob_filter": (C.c_int, [c_void, C.c_int64, C.c_int, C.c_float, c_void, c_void]),
     "flid_neighbor_mean": (C.c_int, [c_void, c_void, C.c_int, c_void, c_void, C.c_int, C.c_int64, C.c_int, C.c_int, c_void,
                                      c_void]),
+    "flid_dense_weight_create": (c_void, [c_void, C.c_int64, C.c_int, C.c_int, c_void]),
+    "flid_dense_weight_update": (C.c_int, [c_void, c_void, C.c_int64, c_void]),
+    "flid_dense_weight_free": (None, [c_void]),
+    "flid_dense": (C.c_int, [c_void, c_void, c_void, C.c_int64, C.c_int, c_void, c_void, C.c_int64, C.c_int, c_void, c_void,
+                             C.c_int64, C.c_int, c_void, C.c_int64, C.c_int64, c_void]),
+    "flid_time_rows": (C.c_int, [c_void, c_void, c_void, c_void, C.c_int, c_void, C.c_int64, c_void]),
+    "flid_token_mix": (C.c_int, [c_void, C.c_int, C.c_int, c_void, c_void, C.c_float, c_void, c_void, c_void, c_void, C.c_int,
+                                 c_void, C.c_int64, c_void]),
+    "flid_token_mean": (C.c_int, [c_void, C.c_int, C.c_int, c_void, C.c_int64, C.c_int64, c_void]),
+    "flid_row_layernorm": (C.c_int, [c_void, C.c_int64, c_void, c_void, C.c_float, c_void, C.c_int64, C.c_int64, C.c_int, c_void]),
+    "flid_add_periodic_rows": (C.c_int, [c_void, c_void, C.c_int, C.c_int, C.c_int64, c_void]),
+    "flid_seq_attention": (C.c_int, [c_void, C.c_int64, c_void, C.c_int64, c_void, C.c_int64, c_void, C.c_int, C.c_int, C.c_int,
+                                     c_void, C.c_int64, C.c_int, C.c_int64, c_void]),
     "flid_attn_train_partials": (C.c_int64, [C.c_int64]),
     "flid_attn_train_fwd": (C.c_int, [c_void] * 9 + [C.c_int64] + [C.c_int] * 5 + [C.c_float, C.c_uint64, c_void,
                                                                                   c_void, c_void]),

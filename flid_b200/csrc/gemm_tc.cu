@@ -265,6 +265,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(TcGemmArgs g, cons
                             }
                         }
                     } else if (staged) {
+                        const bool late = g.resid != nullptr || g.gelu;   // residual / GELU are applied in the store phase
 #pragma unroll
                         for (int i = 0; i < 16; i += 4) {
                             float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
@@ -272,15 +273,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(TcGemmArgs g, cons
                                 const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + i));
                                 o.x += b.x, o.y += b.y, o.z += b.z, o.w += b.w;
                             }
-                            if (g.relu) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
+                            if (g.relu && !late) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
                             *reinterpret_cast<float4*>(stg + lane * EPI_LD + i) = o;
                         }
                         __syncwarp();
                         if (n0 + sc < sh.N) {
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                const float4 o = *reinterpret_cast<const float4*>(stg + (j * 8 + sr) * EPI_LD + sc);
-                                if (crow4[j] != nullptr) *reinterpret_cast<float4*>(crow4[j] + n0 + sc) = o;
+                                float4 o = *reinterpret_cast<const float4*>(stg + (j * 8 + sr) * EPI_LD + sc);
+                                if (crow4[j] == nullptr) continue;
+                                if (late) {
+                                    if (g.resid) {
+                                        const float4 r = __ldg(reinterpret_cast<const float4*>(g.resid + (row0 + j * 8 + sr) * g.ldr + n0 + sc));
+                                        o.x += r.x, o.y += r.y, o.z += r.z, o.w += r.w;
+                                    }
+                                    if (g.gelu) {
+                                        o.x = 0.5f * o.x * (1.0f + erff(o.x * 0.70710678118654752f));
+                                        o.y = 0.5f * o.y * (1.0f + erff(o.y * 0.70710678118654752f));
+                                        o.z = 0.5f * o.z * (1.0f + erff(o.z * 0.70710678118654752f));
+                                        o.w = 0.5f * o.w * (1.0f + erff(o.w * 0.70710678118654752f));
+                                    } else if (g.relu) {
+                                        o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
+                                    }
+                                }
+                                *reinterpret_cast<float4*>(crow4[j] + n0 + sc) = o;
                             }
                         }
                         __syncwarp();
@@ -459,6 +475,7 @@ static int launch_ms(const TcGemmArgs& g, const TcWeight& w, TcShape sh, int sm_
     // clear win for scattered rows and for the wide query-fold output; the narrow short-K shapes store directly
     sh.staged_epilogue = (g.cidx != nullptr || w.k_chunks >= 48 || w.N >= 512) ? 1 : 0;
     if (const char* e = getenv("FLID_GEMM_EPI")) sh.staged_epilogue = e[0] == '1';  // development knob
+    if (g.resid != nullptr || g.gelu) sh.staged_epilogue = 1;   // applied in the staged store phase only
     const size_t ring_bytes = (size_t)(smem_max - STATIC_SMEM) - (sh.staged_epilogue ? EPI_BYTES : 0);
     int stages = (int)(ring_bytes / stage);
     sh.stages = stages > MAX_STAGES ? MAX_STAGES : stages;
@@ -495,6 +512,8 @@ int tc_gemm(const TcGemmArgs& g, const TcWeight& w_in, cudaStream_t st) {
     FLID_REQUIRE(g.w0 > 0 && g.w0 + g.w1 == w.K, "tc_gemm: A width %d+%d != weight K %d", g.w0, g.w1, w.K);
     FLID_REQUIRE((g.w0 % 4) == 0 && (g.w1 % 4) == 0 && (g.lda0 % 4) == 0 && (g.lda1 % 4) == 0,
                  "tc_gemm: segment widths / row strides must be multiples of 4 floats");
+    FLID_REQUIRE((g.resid == nullptr && !g.gelu) || ((g.ldc & 3) == 0 && (w_in.N & 3) == 0 && (g.ldr & 3) == 0),
+                 "tc_gemm: residual / GELU epilogue needs 16-byte aligned rows");
     static int sm_count = 0, smem_max = 0, ms_cap = 1;
     if (sm_count == 0) {
         int dev = 0;

@@ -44,6 +44,10 @@ struct TcGemmArgs {
     const float* bias = nullptr;
     int64_t M = 0;
     int relu = 0;
+    // dense layers of the other sampler consumers (dense.cu): out = act(acc + bias + resid[m]); resid has C's row order
+    int gelu = 0;                        // exact (erf) GELU instead of ReLU
+    const float* resid = nullptr;
+    int64_t ldr = 0;
     // LayerNorm folded into this product (fc1 of the MergeLayer after the attention block, models/modules.py:235-238 then
     // :66): A0 holds residual_fc's outputs; the producers add the residual row [ln_self | ln_tail] on the fly and
     // accumulate each row's sum and sum of squares (float64); the weight image is W diag(gamma); the epilogue applies

@@ -302,6 +302,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_ts_kernel(TcGemmArgs g, c
                             }
                         }
                     } else if (staged) {
+                        const bool late = g.resid != nullptr || g.gelu;   // residual / GELU are applied in the store phase
 #pragma unroll
                         for (int i = 0; i < 16; i += 4) {
                             float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
@@ -309,15 +310,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_ts_kernel(TcGemmArgs g, c
                                 const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + i));
                                 o.x += b.x, o.y += b.y, o.z += b.z, o.w += b.w;
                             }
-                            if (g.relu) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
+                            if (g.relu && !late) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
                             *reinterpret_cast<float4*>(stg + lane * EPI_LD + i) = o;
                         }
                         __syncwarp();
                         if (n0 + sc < sh.N) {
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                const float4 o = *reinterpret_cast<const float4*>(stg + (j * 8 + sr) * EPI_LD + sc);
-                                if (crow4[j] != nullptr) *reinterpret_cast<float4*>(crow4[j] + n0 + sc) = o;
+                                float4 o = *reinterpret_cast<const float4*>(stg + (j * 8 + sr) * EPI_LD + sc);
+                                if (crow4[j] == nullptr) continue;
+                                if (late) {
+                                    if (g.resid) {
+                                        const float4 r = __ldg(reinterpret_cast<const float4*>(g.resid + (row0 + j * 8 + sr) * g.ldr + n0 + sc));
+                                        o.x += r.x, o.y += r.y, o.z += r.z, o.w += r.w;
+                                    }
+                                    if (g.gelu) {
+                                        o.x = 0.5f * o.x * (1.0f + erff(o.x * 0.70710678118654752f));
+                                        o.y = 0.5f * o.y * (1.0f + erff(o.y * 0.70710678118654752f));
+                                        o.z = 0.5f * o.z * (1.0f + erff(o.z * 0.70710678118654752f));
+                                        o.w = 0.5f * o.w * (1.0f + erff(o.w * 0.70710678118654752f));
+                                    } else if (g.relu) {
+                                        o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
+                                    }
+                                }
+                                *reinterpret_cast<float4*>(crow4[j] + n0 + sc) = o;
                             }
                         }
                         __syncwarp();
@@ -432,7 +448,7 @@ int tc_gemm_ts(const TcGemmArgs& g, const TcWeight& w, int sm_count, int smem_ma
     // two accumulator sets when that still leaves >= 4 stages of A columns, else one
     sh.acc_bufs = (2 * w.n_tile <= 512 && (512 - 2 * w.n_tile) / 32 >= 4) ? 2 : 1;
     const int a_stages = (512 - sh.acc_bufs * w.n_tile) / 32;
-    sh.staged_epilogue = (lnf || g.cidx != nullptr || w.k_chunks >= 48 || w.N >= 512) ? 1 : 0;
+    sh.staged_epilogue = (lnf || g.cidx != nullptr || w.k_chunks >= 48 || w.N >= 512 || g.resid != nullptr || g.gelu) ? 1 : 0;
     const size_t stage = 2 * (size_t)C4 * w.n_tile * 16;
     const size_t tail_bytes = (sh.staged_epilogue ? EPI_BYTES : 0) + (lnf ? LN_BYTES : 0);
     const size_t ring_bytes = (size_t)(smem_max - STATIC_SMEM) - tail_bytes;

@@ -8,16 +8,18 @@ consumer of the time-sorted device CSR:
 * the node encoder (gather of up to 2000 feature rows per query, masked softmax, mean;
   GraphMixer.py:119-146) is one kernel, ``flid_neighbor_mean`` (csrc/mixer.cu) -- the reference
   materialises a ``[B, 2000, dn]`` tensor for it;
-* the link encoder's dense part (Linear(T, 100), MLP-Mixer blocks, output layer: small GEMMs over
-  ``[B, k, 100]``) is composed from torch CUDA ops on the modules below, so it trains with autograd
-  as the reference does (the time encoder is frozen in GraphMixer, the sampler outputs and raw
-  node features are constants: nothing on the kernel side needs a gradient).
+* the link encoder's dense part (Linear(T, 100), MLP-Mixer blocks, output layer) runs, in evaluation
+  (``model.eval()`` under ``torch.no_grad()``), on the library's own kernels (csrc/dense.cu): every Linear on the
+  tcgen05 3xTF32 GEMM with bias / GELU / residual in its epilogue, token mixing as one kernel per block;
+* in training the same modules are composed from torch CUDA ops, so it trains with autograd as the reference
+  does (the time encoder is frozen in GraphMixer, the sampler outputs and raw node features are constants:
+  nothing on the kernel side needs a gradient).
 """
 import numpy as np
 import torch
 import torch.nn as nn
 
-from . import _lib
+from . import _lib, dense
 from .sampler import NeighborSampler
 from .tgat import TimeEncoder
 
@@ -75,6 +77,25 @@ class GraphMixer(nn.Module):
                                                   channel_dim_expansion_factor, dropout) for _ in range(num_layers)])
         self.output_layer = nn.Linear(self.num_channels + self.node_feat_dim, self.node_feat_dim, bias=True)
         self.chunk_queries = 65536          # bulk calls are processed in chunks: [chunk, k, 100] activations
+        self._dense = dense.DenseWeights()  # tiled weight images of the evaluation path
+
+    def _link_encoder_eval(self, dt, nbr, m, k):
+        """GraphMixer.py:103-117 on csrc/dense.cu: [m, k] time differences / neighbour ids -> [m, 100]."""
+        lib, st, c = _lib.lib(), _lib.stream(), self.num_channels
+        te = dense.time_rows(dt, nbr, self.time_encoder)                                   # [m * k, T], padded rows zero
+        x = dense.linear(self._dense, te, self.projection_layer.weight, self.projection_layer.bias)
+        for mixer in self.mlp_mixers:
+            tf, cf = mixer.token_feedforward.ffn, mixer.channel_feedforward.ffn
+            x1 = torch.empty_like(x)
+            _lib.check(lib.flid_token_mix(_lib.ptr(x), k, c, _lib.ptr(mixer.token_norm.weight), _lib.ptr(mixer.token_norm.bias),
+                                          float(mixer.token_norm.eps), _lib.ptr(tf[0].weight), _lib.ptr(tf[0].bias),
+                                          _lib.ptr(tf[3].weight), _lib.ptr(tf[3].bias), tf[0].weight.shape[0], _lib.ptr(x1), m, st))
+            y = dense.layernorm(x1, mixer.channel_norm)
+            h = dense.linear(self._dense, y, cf[0].weight, cf[0].bias, act=2)
+            x = dense.linear(self._dense, h, cf[3].weight, cf[3].bias, resid=x1)
+        link = torch.empty((m, c), dtype=torch.float32, device=x.device)
+        _lib.check(lib.flid_token_mean(_lib.ptr(x), k, c, _lib.ptr(link), c, m, st))
+        return link
 
     def compute_src_dst_node_temporal_embeddings(self, src_node_ids: np.ndarray, dst_node_ids: np.ndarray,
                                                  node_interact_times: np.ndarray, num_neighbors: int = 20,
@@ -115,18 +136,25 @@ class GraphMixer(nn.Module):
                     dt = c_t.to(torch.float32)[:, None] - ts
                 else:                             # float64 minus float32 in float64, then .float()
                     dt = (c_t[:, None] - ts.to(torch.float64)).to(torch.float32)
-                te = torch.cos(torch.addcmul(b_t, dt.unsqueeze(-1), w_t))               # single-rounded fma, as nn.Linear(1, T)
-                te = te.masked_fill((nbr == 0).unsqueeze(-1), 0.0)
-                x = self.projection_layer(te)
-                for mixer in self.mlp_mixers:
-                    x = mixer(x)
-                link = torch.mean(x, dim=1)
+                fast = dense.fast_path(self) and m > 0
+                if fast:
+                    link = self._link_encoder_eval(dt, nbr, m, k)
+                else:
+                    te = torch.cos(torch.addcmul(b_t, dt.unsqueeze(-1), w_t))           # single-rounded fma, as nn.Linear(1, T)
+                    te = te.masked_fill((nbr == 0).unsqueeze(-1), 0.0)
+                    x = self.projection_layer(te)
+                    for mixer in self.mlp_mixers:
+                        x = mixer(x)
+                    link = torch.mean(x, dim=1)
                 # node encoder (GraphMixer.py:119-146): one gather / reduce kernel
                 node_part = torch.empty((m, self.node_feat_dim), dtype=torch.float32, device=dev)
                 _lib.check(_lib.lib().flid_neighbor_mean(sampler.handle, _lib.ptr(self.node_raw_features), self.node_feat_dim,
                                                          _lib.ptr(c_ids), _lib.ptr(c_t), 0, m, int(time_gap), 1,
                                                          _lib.ptr(node_part), _lib.stream()))
-                outs.append(self.output_layer(torch.cat([link, node_part], dim=1)))
+                if fast:
+                    outs.append(dense.linear(self._dense, link, self.output_layer.weight, self.output_layer.bias, x2=node_part))
+                else:
+                    outs.append(self.output_layer(torch.cat([link, node_part], dim=1)))
         return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
 
     def set_neighbor_sampler(self, neighbor_sampler: NeighborSampler):

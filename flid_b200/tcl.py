@@ -2,18 +2,21 @@
 ``models/modules.py:248-312``): same constructor, method names and ``state_dict`` keys.  SURVEY.md
 section 8(f) rank 4 -- another consumer of the time-sorted device CSR: the two
 ``get_historical_neighbors`` calls per batch and the sequence assembly ([node ; its k recent
-neighbours], edge id 0 and time difference 0 in front) stay on the device; the encoder itself
+neighbours], edge id 0 and time difference 0 in front) stay on the device.  The encoder itself
 (three input projections + depth embedding, nn.MultiheadAttention self / cross attention over
-21-token sequences, feed-forward, LayerNorm) is dense library work composed from torch CUDA
-modules with the reference's parameter names, so checkpoints load unchanged and it trains with
-autograd as the reference does.
+21-token sequences, feed-forward, LayerNorm) runs, in evaluation (``model.eval()`` under
+``torch.no_grad()``), on the library's own kernels (csrc/dense.cu): every Linear -- including the
+attention in / out projections -- on the tcgen05 3xTF32 GEMM with the feature-row gathers, bias, ReLU
+and residual fused, the 21 x 21 attention as one CTA per sequence.  In training it is composed from
+torch CUDA modules with the reference's parameter names, so checkpoints load unchanged and it trains
+with autograd as the reference does.
 """
 import numpy as np
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import _lib
+from . import _lib, dense
 from .sampler import NeighborSampler
 from .tgat import TimeEncoder
 
@@ -73,6 +76,50 @@ class TCL(nn.Module):
                                            for _ in range(num_layers)])
         self.output_layer = nn.Linear(self.node_feat_dim, self.node_feat_dim, bias=True)
         self.chunk_events = 16384           # bulk calls are processed in chunks of events
+        self._dense = dense.DenseWeights()  # tiled weight images of the evaluation path
+        self._cat = {}                      # derived evaluation-path parameters, keyed by the versions of their sources
+
+    # ------------------------------------------------------------------ evaluation path on csrc/dense.cu
+    def _features_eval(self, ids, eids, dt):
+        """TCL.py:108-131 as two GEMMs: [node[ids] | edge[eids]] @ [Wn | We]^T + (bn + be + bt), then the time
+        projection with that as its residual, then the depth rows.  Returns [m * S, d]."""
+        pn, pe, pt = self.projection_layer['node'], self.projection_layer['edge'], self.projection_layer['time']
+        ver = (pn.weight._version, pe.weight._version, pn.bias._version, pe.bias._version, pt.bias._version,
+               pn.weight.data_ptr(), pe.weight.data_ptr())
+        if self._cat.get('ver') != ver:
+            self._cat = {'ver': ver, 'w': torch.cat([pn.weight, pe.weight], dim=1).contiguous(),
+                         'b': (pn.bias + pe.bias + pt.bias).contiguous()}
+        m, s = ids.shape
+        assert s == self.depth_embedding.weight.shape[0]
+        i32, e32 = ids.reshape(-1).to(torch.int32), eids.reshape(-1).to(torch.int32)
+        base = dense.linear(self._dense, self.node_raw_features, self._cat['w'], self._cat['b'], idx=i32,
+                            x2=self.edge_raw_features, idx2=e32)
+        te = dense.time_rows(dt, None, self.time_encoder)
+        x = dense.linear(self._dense, te, pt.weight, None, resid=base)
+        _lib.check(_lib.lib().flid_add_periodic_rows(_lib.ptr(x), _lib.ptr(self.depth_embedding.weight), s, x.shape[1],
+                                                     x.shape[0], _lib.stream()))
+        return x
+
+    def _encoder_eval(self, tr, xq, xkv, key_ids, s, q_rows=None):
+        """TransformerEncoder.forward (modules.py:270-312) on [m * S, d] rows; ``xkv is xq``: self-attention."""
+        mha, d = tr.multi_head_attention, xq.shape[1]
+        w_in, b_in, heads = mha.in_proj_weight, mha.in_proj_bias, mha.num_heads
+        m = xq.shape[0] // s
+        if xkv is xq:
+            qkv = dense.linear(self._dense, xq, w_in, b_in)
+            q, kk, vv = qkv, qkv[:, d:], qkv[:, 2 * d:]
+        else:
+            q = dense.linear(self._dense, xq, w_in[:d], b_in[:d])
+            kv = dense.linear(self._dense, xkv, w_in[d:], b_in[d:])
+            kk, vv = kv, kv[:, d:]
+        ctx = torch.empty((m * s, d), dtype=torch.float32, device=xq.device)
+        _lib.check(_lib.lib().flid_seq_attention(_lib.ptr(q), q.stride(0), _lib.ptr(kk), kk.stride(0), _lib.ptr(vv), vv.stride(0),
+                                                 _lib.ptr(key_ids), s, heads, d // heads, _lib.ptr(ctx), d, s, m, _lib.stream()))
+        y = dense.linear(self._dense, ctx, mha.out_proj.weight, mha.out_proj.bias, resid=xq)
+        out = dense.layernorm(y, tr.norm_layers[0], out=y)
+        h = dense.linear(self._dense, out, tr.linear_layers[0].weight, tr.linear_layers[0].bias, act=1)
+        y2 = dense.linear(self._dense, h, tr.linear_layers[1].weight, tr.linear_layers[1].bias, resid=out)
+        return dense.layernorm(y2, tr.norm_layers[1], out=y2)
 
     def _sequences(self, d_ids, d_t, f32_times, k):
         """[node ; k recent neighbours] on the device: ids / edge ids int64 [m, k+1], time differences float32 (TCL.py:75-106, :178-180)."""
@@ -121,6 +168,21 @@ class TCL(nn.Module):
                 hi = lo + self.chunk_events
                 ids_s, eid_s, dt_s = self._sequences(d_src[lo:hi], d_t[lo:hi], f32, k)
                 ids_d, eid_d, dt_d = self._sequences(d_dst[lo:hi], d_t[lo:hi], f32, k)
+                if dense.fast_path(self) and ids_s.shape[0] > 0:
+                    m, s = ids_s.shape
+                    ids_s, ids_d = ids_s.contiguous(), ids_d.contiguous()
+                    xs, xd = self._features_eval(ids_s, eid_s, dt_s), self._features_eval(ids_d, eid_d, dt_d)
+                    es = ed = None
+                    for transformer in self.transformers:                   # TCL.py:133-151
+                        xs = self._encoder_eval(transformer, xs, xs, ids_s, s)
+                        xd = self._encoder_eval(transformer, xd, xd, ids_d, s)
+                        es = self._encoder_eval(transformer, xs, xd, ids_d, s)
+                        ed = self._encoder_eval(transformer, xd, xs, ids_s, s)
+                        xs, xd = es, ed
+                    w_o, b_o, d = self.output_layer.weight, self.output_layer.bias, self.node_feat_dim
+                    outs_s.append(dense.linear(self._dense, es, w_o, b_o, rows=m, ldx=s * d))   # token 0 of every sequence
+                    outs_d.append(dense.linear(self._dense, ed, w_o, b_o, rows=m, ldx=s * d))
+                    continue
                 xs, xd = self._features(ids_s, eid_s, dt_s), self._features(ids_d, eid_d, dt_d)
                 es = ed = None
                 for transformer in self.transformers:                       # TCL.py:133-151

@@ -391,6 +391,50 @@ int flid_neighbor_mean(const flid_graph* g, const float* node_feat, int node_dim
                        const void* times, int times_are_f32, int64_t n, int time_gap, int add_self, float* out,
                        flid_stream stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Dense halves of GraphMixer's link encoder (models/GraphMixer.py:91-117, :172-246) and TCL's encoder
+ * (models/TCL.py:108-157, models/modules.py:248-312), evaluation (forward-only) path; csrc/dense.cu.
+ * Everything is float32, row-major, on the current device; pointers are device pointers.                        */
+typedef struct flid_dense_weight flid_dense_weight;   /* tiled tensor-core image of one nn.Linear weight */
+
+/* weight: [n_out, n_in] with row stride ldw (nn.Linear layout; a row slice of a larger matrix is fine), n_in % 4 == 0.
+ * Returns NULL on error (flid_last_error).  _update re-tiles after the parameter changed.                          */
+flid_dense_weight* flid_dense_weight_create(const float* weight, int64_t ldw, int n_out, int n_in, flid_stream stream);
+int flid_dense_weight_update(flid_dense_weight* h, const float* weight, int64_t ldw, flid_stream stream);
+void flid_dense_weight_free(flid_dense_weight* h);
+
+/* c[r, :] = act( [a0[i0(r), :w0] | a1[i1(r), :w1]] @ W^T + bias + resid[r, :] ),  r < m.
+ * i(r) = idx[r] when idx is given (int32 row gather: torch's x[ids]), else r; w0 + w1 == n_in; w1 == 0: one segment;
+ * bias, resid nullable; act 0 none, 1 ReLU, 2 exact (erf) GELU -- F.relu / nn.GELU() of the reference modules.   */
+int flid_dense(const flid_dense_weight* h, const float* a0, const int32_t* idx0, int64_t lda0, int w0, const float* a1,
+               const int32_t* idx1, int64_t lda1, int w1, const float* bias, const float* resid, int64_t ldr, int act,
+               float* c, int64_t ldc, int64_t m, flid_stream stream);
+
+/* out[r, :] = cos(dt[r] * w + b) (TimeEncoder, modules.py:25-38), zeros where ids[r] == 0 (ids nullable)
+ * -- GraphMixer.py:103-108, TCL.py:118.                                                                            */
+int flid_time_rows(const float* dt, const int64_t* ids, const float* w, const float* b, int time_dim, float* out, int64_t n,
+                   flid_stream stream);
+
+/* MLPMixer token mixing (GraphMixer.py:226-236): x, out [m, num_tokens, channels];
+ * out = x + (Linear(hidden, tokens) o GELU o Linear(tokens, hidden) o LayerNorm_tokens)(x^T)^T.                    */
+int flid_token_mix(const float* x, int num_tokens, int channels, const float* ln_w, const float* ln_b, float eps,
+                   const float* w1, const float* b1, const float* w2, const float* b2, int hidden, float* out, int64_t m,
+                   flid_stream stream);
+/* out[q, :channels] = mean over the tokens of x[q] (GraphMixer.py:117); out row stride ldo.                        */
+int flid_token_mean(const float* x, int num_tokens, int channels, float* out, int64_t ldo, int64_t m, flid_stream stream);
+/* nn.LayerNorm over the last dimension (dim % 4 == 0, <= 1024).  y may alias x.                                    */
+int flid_row_layernorm(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, float* y, int64_t ldy,
+                       int64_t m, int dim, flid_stream stream);
+/* x[r, :] += table[r % period, :] -- the depth embedding rows of TCL.py:127-131 over [batch * period, dim].       */
+int flid_add_periodic_rows(float* x, const float* table, int period, int dim, int64_t m, flid_stream stream);
+/* Core of nn.MultiheadAttention as TransformerEncoder calls it (modules.py:287-300): per sequence of seq_len tokens
+ * softmax(q k^T / sqrt(head_dim) with keys whose key_ids == 0 masked out) v for every head; q, k, v are the
+ * in-projected rows [num_seqs * seq_len, num_heads * head_dim] with their own row strides; only the first q_rows
+ * query tokens of each sequence are evaluated (seq_len: all of them).                                              */
+int flid_seq_attention(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                       const int64_t* key_ids, int seq_len, int num_heads, int head_dim, float* out, int64_t ldo,
+                       int q_rows, int64_t num_seqs, flid_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -158,3 +158,126 @@ def test_empty_batches():
             with torch.set_grad_enabled(train):
                 a, b = m.compute_src_dst_node_temporal_embeddings(*args)
             assert a.shape == (0, 172) and b.shape == (0, 172), type(m).__name__
+
+
+# ===================================================================== csrc/dense.cu, kernel by kernel
+def _rel(got, want):
+    return float((got.double() - want.double()).abs().max()) / max(1.0, float(want.abs().max()))
+
+
+@pytest.mark.parametrize("rows", [1, 300, 5000])
+@pytest.mark.parametrize("n_out,n_in", [(100, 100), (400, 100), (100, 400), (516, 172), (688, 172), (172, 688), (172, 272)])
+def test_dense_linear_vs_torch(rows, n_out, n_in):
+    """flid_dense (bias, ReLU / GELU, residual, two gathered segments) against float64 torch; both weight images
+    (32-column tiles up to 2048 rows, wide tiles above) and both GEMM kernels are reached by these shapes."""
+    from flid_b200 import dense
+    gen = torch.Generator().manual_seed(rows * 1000 + n_out + n_in)
+    w = (torch.randn(n_out, n_in, generator=gen) / n_in ** 0.5).to(DEV)
+    b = torch.randn(n_out, generator=gen).to(DEV)
+    x = torch.randn(rows, n_in, generator=gen).to(DEV)
+    r = torch.randn(rows, n_out, generator=gen).to(DEV)
+    cache = dense.DenseWeights()
+    ref = x.double() @ w.double().t() + b.double()
+    assert _rel(dense.linear(cache, x, w, b), ref) <= 1e-5
+    assert _rel(dense.linear(cache, x, w, None), ref - b.double()) <= 1e-5
+    assert _rel(dense.linear(cache, x, w, b, act=1), torch.relu(ref)) <= 1e-5
+    assert _rel(dense.linear(cache, x, w, b, act=2), torch.nn.functional.gelu(ref)) <= 1e-5
+    assert _rel(dense.linear(cache, x, w, b, resid=r), ref + r.double()) <= 1e-5
+    assert _rel(dense.linear(cache, x, w, b, act=1, resid=r), torch.relu(ref + r.double())) <= 1e-5
+    # two row-gathered segments: torch's cat([t0[i0], t1[i1]], 1)
+    w0 = (n_in // 8) * 4
+    t0 = torch.randn(37, w0, generator=gen).to(DEV)
+    t1 = torch.randn(53, n_in - w0, generator=gen).to(DEV)
+    i0 = torch.randint(0, 37, (rows,), generator=gen).to(DEV)
+    i1 = torch.randint(0, 53, (rows,), generator=gen).to(DEV)
+    ref2 = torch.cat([t0[i0], t1[i1]], 1).double() @ w.double().t() + b.double()
+    got2 = dense.linear(cache, t0, w, b, idx=i0.to(torch.int32), x2=t1, idx2=i1.to(torch.int32))
+    assert _rel(got2, ref2) <= 1e-5
+    # the cached image follows an in-place parameter update
+    w.mul_(0.5)
+    assert _rel(dense.linear(cache, x, w, b), (ref - b.double()) * 0.5 + b.double()) <= 1e-5
+    # strided rows: every 3rd row of x
+    if rows >= 3:
+        got3 = dense.linear(cache, x, w, b, rows=rows // 3, ldx=3 * n_in)
+        assert _rel(got3, (x[::3][:rows // 3].double() @ w.double().t() + b.double())) <= 1e-5
+    cache.clear()
+
+
+@pytest.mark.parametrize("k,hid", [(20, 10), (5, 2), (33, 16), (64, 32)])
+def test_token_mix_layernorm_mean_vs_torch(k, hid):
+    from flid_b200 import dense
+    from flid_b200.graphmixer import MLPMixer
+    torch.manual_seed(k)
+    m, c = 77, 100
+    mixer = MLPMixer(k, c, hid / k + 1e-9, 4.0, 0.0).to(DEV).eval()
+    with torch.no_grad():
+        mixer.token_norm.weight.uniform_(0.5, 1.5), mixer.token_norm.bias.normal_(0, 0.2)
+        mixer.channel_norm.weight.uniform_(0.5, 1.5), mixer.channel_norm.bias.normal_(0, 0.2)
+        x = torch.randn(m, k, c, device=DEV)
+        tf = mixer.token_feedforward.ffn
+        assert tf[0].weight.shape == (hid, k)
+        want = mixer.token_feedforward(mixer.token_norm(x.permute(0, 2, 1))).permute(0, 2, 1) + x
+        got = torch.empty_like(x)
+        _lib.check(_lib.lib().flid_token_mix(_lib.ptr(x), k, c, _lib.ptr(mixer.token_norm.weight), _lib.ptr(mixer.token_norm.bias),
+                                             1e-5, _lib.ptr(tf[0].weight), _lib.ptr(tf[0].bias), _lib.ptr(tf[3].weight),
+                                             _lib.ptr(tf[3].bias), hid, _lib.ptr(got), m, _lib.stream()))
+        assert _rel(got, want) <= 1e-5
+        flat = x.reshape(m * k, c)
+        assert _rel(dense.layernorm(flat, mixer.channel_norm), mixer.channel_norm(flat)) <= 1e-5
+        mean = torch.empty(m, c, device=DEV)
+        _lib.check(_lib.lib().flid_token_mean(_lib.ptr(x), k, c, _lib.ptr(mean), c, m, _lib.stream()))
+        assert _rel(mean, x.mean(1)) <= 1e-5
+
+
+@pytest.mark.parametrize("s,heads,d", [(21, 2, 172), (5, 2, 172), (7, 4, 64), (33, 1, 100)])
+def test_seq_attention_vs_multihead_attention(s, heads, d):
+    """flid_seq_attention + flid_dense in / out projections against nn.MultiheadAttention with a key padding mask
+    (self and cross attention), the way TransformerEncoder calls it (models/modules.py:287-300)."""
+    from flid_b200 import dense
+    torch.manual_seed(s * d)
+    m = 41
+    mha = torch.nn.MultiheadAttention(d, heads, dropout=0.0).to(DEV).eval()
+    cache = dense.DenseWeights()
+    with torch.no_grad():
+        mha.in_proj_bias.normal_(0, 0.3), mha.out_proj.bias.normal_(0, 0.3)
+        xq, xkv = torch.randn(m, s, d, device=DEV), torch.randn(m, s, d, device=DEV)
+        ids = torch.randint(0, 3, (m, s), device=DEV)
+        ids[:, 0] = 1                                  # the node itself is never padding
+        ids[3, 1:] = 0                                 # a sequence with no neighbours
+        for kv in (xq, xkv):
+            want = mha(xq.transpose(0, 1), kv.transpose(0, 1), kv.transpose(0, 1), key_padding_mask=ids == 0)[0].transpose(0, 1)
+            w_in, b_in = mha.in_proj_weight, mha.in_proj_bias
+            fq, fkv = xq.reshape(m * s, d), kv.reshape(m * s, d)
+            if kv is xq:
+                qkv = dense.linear(cache, fq, w_in, b_in)
+                q, kk, vv = qkv, qkv[:, d:], qkv[:, 2 * d:]
+            else:
+                q = dense.linear(cache, fq, w_in[:d], b_in[:d])
+                kvp = dense.linear(cache, fkv, w_in[d:], b_in[d:])
+                kk, vv = kvp, kvp[:, d:]
+            ctx = torch.zeros(m * s, d, device=DEV)
+            for q_rows in (s, 1):
+                _lib.check(_lib.lib().flid_seq_attention(_lib.ptr(q), q.stride(0), _lib.ptr(kk), kk.stride(0), _lib.ptr(vv),
+                                                         vv.stride(0), _lib.ptr(ids), s, heads, d // heads, _lib.ptr(ctx), d,
+                                                         q_rows, m, _lib.stream()))
+                got = dense.linear(cache, ctx, mha.out_proj.weight, mha.out_proj.bias).reshape(m, s, d)
+                assert _rel(got[:, :q_rows], want[:, :q_rows]) <= 1e-5, (q_rows, kv is xq)
+    cache.clear()
+
+
+def test_eval_path_equals_torch_modules():
+    """The forward-only kernels (model.eval() under no_grad) and the torch modules (grad enabled) agree on both models."""
+    src, dst, eid, ts, nf, ef = cases.small_stream()
+    s = flid_b200.NeighborSampler(None, "recent", seed=1, device=DEV, _events=(src, dst, eid, ts, nf.shape[0] - 1))
+    torch.manual_seed(3)
+    gm = flid_b200.GraphMixer(nf, ef, s, 100, 20, 2, device=DEV).to(DEV).eval()
+    tcl = flid_b200.TCL(nf, ef, s, 100, 2, 2, 21, 0.1, DEV).to(DEV).eval()
+    sel = np.arange(50, 450)
+    for m in (gm, tcl):
+        with torch.no_grad():
+            a, b = m.compute_src_dst_node_temporal_embeddings(src[sel], dst[sel], ts[sel], 20)
+        with torch.enable_grad():
+            ra, rb = m.compute_src_dst_node_temporal_embeddings(src[sel], dst[sel], ts[sel], 20)
+        assert ra.requires_grad and not a.requires_grad
+        close(a.cpu().numpy(), ra.detach().cpu().numpy(), type(m).__name__ + " src")
+        close(b.cpu().numpy(), rb.detach().cpu().numpy(), type(m).__name__ + " dst")
