@@ -37,13 +37,14 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 // ---------------------------------------------------------------- token mixing (GraphMixer.py:226-236)
 // x [m, k, C]: per (query, channel) the k token values -> LayerNorm over tokens -> Linear(k, hid) -> GELU ->
 // Linear(hid, k) -> + input.  Weights in shared memory; the token vector and the output vector live in registers.
-template <int KMAX>
-__global__ void __launch_bounds__(128) token_mix_kernel(const float* __restrict__ x, int k, int C, const float* __restrict__ ln_w,
+template <int KMAX, bool EXACT>   // EXACT: k == KMAX, the token loops carry no predicates
+__global__ void __launch_bounds__(128) token_mix_kernel(const float* __restrict__ x, int k_rt, int C, const float* __restrict__ ln_w,
                                                         const float* __restrict__ ln_b, float eps, const float* __restrict__ w1,
                                                         const float* __restrict__ b1, const float* __restrict__ w2,
                                                         const float* __restrict__ b2, int hid, float* __restrict__ out,
                                                         int64_t m) {
-    extern __shared__ float sm[];
+    extern __shared__ __align__(16) float sm[];
+    const int k = EXACT ? KMAX : k_rt;
     float* s_w1 = sm;                 // [hid][k]
     float* s_w2t = s_w1 + hid * k;    // [hid][k]  (W2 transposed)
     float* s_b1 = s_w2t + hid * k;    // [hid]
@@ -58,45 +59,63 @@ __global__ void __launch_bounds__(128) token_mix_kernel(const float* __restrict_
     for (int i = threadIdx.x; i < hid; i += blockDim.x) s_b1[i] = __ldg(b1 + i);
     for (int i = threadIdx.x; i < k; i += blockDim.x) s_b2[i] = __ldg(b2 + i), s_g[i] = __ldg(ln_w + i), s_be[i] = __ldg(ln_b + i);
     __syncthreads();
-    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (idx >= m * C) return;
-    const int64_t q = idx / C;
-    const int c = (int)(idx - q * C);
-    const float* xp = x + q * (int64_t)k * C + c;
-    float v[KMAX], y[KMAX], o[KMAX];
-    float sum = 0.f;
+    const float inv_k = 1.0f / (float)k;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < m * C; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t q = idx / C;
+        const int c = (int)(idx - q * C);
+        const float* xp = x + q * (int64_t)k * C + c;
+        float v[KMAX], y[KMAX], o[KMAX];
+        float sum = 0.f;
 #pragma unroll
-    for (int t = 0; t < KMAX; ++t) {
-        v[t] = t < k ? __ldg(xp + (int64_t)t * C) : 0.f;
-        sum += v[t];
-    }
-    const float mean = sum / (float)k;
-    float var = 0.f;
+        for (int t = 0; t < KMAX; ++t) {
+            v[t] = (EXACT || t < k) ? __ldg(xp + (int64_t)t * C) : 0.f;
+            sum += v[t];
+        }
+        const float mean = sum * inv_k;
+        float var = 0.f;
 #pragma unroll
-    for (int t = 0; t < KMAX; ++t) {
-        const float d = t < k ? v[t] - mean : 0.f;
-        var = fmaf(d, d, var);
-    }
-    const float rstd = rsqrtf(var / (float)k + eps);
+        for (int t = 0; t < KMAX; ++t) {
+            const float d = (EXACT || t < k) ? v[t] - mean : 0.f;
+            var = fmaf(d, d, var);
+        }
+        const float rstd = rsqrtf(var * inv_k + eps);
 #pragma unroll
-    for (int t = 0; t < KMAX; ++t) {
-        y[t] = t < k ? fmaf((v[t] - mean) * rstd, s_g[t], s_be[t]) : 0.f;
-        o[t] = t < k ? s_b2[t] : 0.f;
-    }
-    for (int j = 0; j < hid; ++j) {
-        float h = s_b1[j];
+        for (int t = 0; t < KMAX; ++t) {
+            y[t] = (EXACT || t < k) ? fmaf((v[t] - mean) * rstd, s_g[t], s_be[t]) : 0.f;
+            o[t] = (EXACT || t < k) ? s_b2[t] : 0.f;
+        }
+        for (int j = 0; j < hid; ++j) {
+            float h = s_b1[j];
+            const float* wr = s_w1 + j * k;
+            const float* wt = s_w2t + j * k;
+            if (EXACT && (KMAX & 3) == 0) {   // rows of k floats stay 16-byte aligned: 128-bit shared loads
+#pragma unroll
+                for (int t = 0; t < KMAX; t += 4) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(wr + t);
+                    h = fmaf(w4.x, y[t], h), h = fmaf(w4.y, y[t + 1], h), h = fmaf(w4.z, y[t + 2], h), h = fmaf(w4.w, y[t + 3], h);
+                }
+                h = gelu_erf(h);
+#pragma unroll
+                for (int t = 0; t < KMAX; t += 4) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(wt + t);
+                    o[t] = fmaf(w4.x, h, o[t]), o[t + 1] = fmaf(w4.y, h, o[t + 1]), o[t + 2] = fmaf(w4.z, h, o[t + 2]),
+                    o[t + 3] = fmaf(w4.w, h, o[t + 3]);
+                }
+            } else {
+#pragma unroll
+                for (int t = 0; t < KMAX; ++t)
+                    if (EXACT || t < k) h = fmaf(wr[t], y[t], h);
+                h = gelu_erf(h);
+#pragma unroll
+                for (int t = 0; t < KMAX; ++t)
+                    if (EXACT || t < k) o[t] = fmaf(wt[t], h, o[t]);
+            }
+        }
+        float* op = out + q * (int64_t)k * C + c;
 #pragma unroll
         for (int t = 0; t < KMAX; ++t)
-            if (t < k) h = fmaf(s_w1[j * k + t], y[t], h);
-        h = gelu_erf(h);
-#pragma unroll
-        for (int t = 0; t < KMAX; ++t)
-            if (t < k) o[t] = fmaf(s_w2t[j * k + t], h, o[t]);
+            if (EXACT || t < k) op[(int64_t)t * C] = v[t] + o[t];
     }
-    float* op = out + q * (int64_t)k * C + c;
-#pragma unroll
-    for (int t = 0; t < KMAX; ++t)
-        if (t < k) op[(int64_t)t * C] = v[t] + o[t];
 }
 
 // ---------------------------------------------------------------- mean over tokens (GraphMixer.py:117)
@@ -207,15 +226,30 @@ __global__ void __launch_bounds__(128) seq_attention_kernel(const float* __restr
     }
     for (int i = tid; i < S; i += nt) s_mask[i] = __ldg(key_ids + e * S + i) == 0;
     __syncthreads();
-    for (int idx = tid; idx < H * q_rows * S; idx += nt) {
-        const int j = idx % S, i = (idx / S) % q_rows, h = idx / (S * q_rows);
-        const float* qp = s_q + i * ld + h * hd;
-        const float* kp = s_k + j * ld + h * hd;
-        float a0 = 0.f, a1 = 0.f;
-        int c = 0;
-        for (; c + 1 < hd; c += 2) a0 = fmaf(qp[c], kp[c], a0), a1 = fmaf(qp[c + 1], kp[c + 1], a1);
-        if (c < hd) a0 = fmaf(qp[c], kp[c], a0);
-        s_p[(h * S + i) * ps + j] = s_mask[j] ? -INFINITY : a0 + a1;
+    // scores in 3 x 3 register tiles: 6 shared loads per 9 products (S = 21: 2 x 7 x 7 tiles for the 128 threads)
+    const int ti_n = (q_rows + 2) / 3, tj_n = (S + 2) / 3;
+    for (int idx = tid; idx < H * ti_n * tj_n; idx += nt) {
+        const int tj = idx % tj_n, ti = (idx / tj_n) % ti_n, h = idx / (tj_n * ti_n);
+        const int i0 = ti * 3, j0 = tj * 3;
+        // rows past the end are clamped (their products are computed and dropped)
+        const float* q0 = s_q + min(i0, q_rows - 1) * ld + h * hd;
+        const float* q1 = s_q + min(i0 + 1, q_rows - 1) * ld + h * hd;
+        const float* q2 = s_q + min(i0 + 2, q_rows - 1) * ld + h * hd;
+        const float* k0 = s_k + min(j0, S - 1) * ld + h * hd;
+        const float* k1 = s_k + min(j0 + 1, S - 1) * ld + h * hd;
+        const float* k2 = s_k + min(j0 + 2, S - 1) * ld + h * hd;
+        float a[3][3] = {};
+        for (int c = 0; c < hd; ++c) {
+            const float x0 = q0[c], x1 = q1[c], x2 = q2[c], y0 = k0[c], y1 = k1[c], y2 = k2[c];
+            a[0][0] = fmaf(x0, y0, a[0][0]), a[0][1] = fmaf(x0, y1, a[0][1]), a[0][2] = fmaf(x0, y2, a[0][2]);
+            a[1][0] = fmaf(x1, y0, a[1][0]), a[1][1] = fmaf(x1, y1, a[1][1]), a[1][2] = fmaf(x1, y2, a[1][2]);
+            a[2][0] = fmaf(x2, y0, a[2][0]), a[2][1] = fmaf(x2, y1, a[2][1]), a[2][2] = fmaf(x2, y2, a[2][2]);
+        }
+#pragma unroll
+        for (int di = 0; di < 3; ++di)
+#pragma unroll
+            for (int dj = 0; dj < 3; ++dj)
+                if (i0 + di < q_rows && j0 + dj < S) s_p[(h * S + i0 + di) * ps + j0 + dj] = s_mask[j0 + dj] ? -INFINITY : a[di][dj];
     }
     __syncthreads();
     for (int row = tid; row < H * q_rows; row += nt) {
@@ -233,12 +267,21 @@ __global__ void __launch_bounds__(128) seq_attention_kernel(const float* __restr
         for (int j = 0; j < S; ++j) p[j] *= inv;
     }
     __syncthreads();
-    for (int idx = tid; idx < q_rows * d; idx += nt) {
-        const int i = idx / d, c = idx - i * d, h = c / hd;
-        const float* p = s_p + (h * S + i) * ps;
-        float a = 0.f;
-        for (int j = 0; j < S; ++j) a = fmaf(p[j], s_v[j * ld + c], a);
-        out[(e * S + i) * ldo + c] = a;
+    // P V: one thread per (3 query rows, column): 4 shared loads per 3 products
+    for (int idx = tid; idx < ti_n * d; idx += nt) {
+        const int ti = idx / d, c = idx - ti * d, h = c / hd;
+        const int i0 = ti * 3;
+        const float* p0 = s_p + (h * S + min(i0, q_rows - 1)) * ps;
+        const float* p1 = s_p + (h * S + min(i0 + 1, q_rows - 1)) * ps;
+        const float* p2 = s_p + (h * S + min(i0 + 2, q_rows - 1)) * ps;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        for (int j = 0; j < S; ++j) {
+            const float vv = s_v[j * ld + c];
+            a0 = fmaf(p0[j], vv, a0), a1 = fmaf(p1[j], vv, a1), a2 = fmaf(p2[j], vv, a2);
+        }
+        out[(e * S + i0) * ldo + c] = a0;
+        if (i0 + 1 < q_rows) out[(e * S + i0 + 1) * ldo + c] = a1;
+        if (i0 + 2 < q_rows) out[(e * S + i0 + 2) * ldo + c] = a2;
     }
 }
 
@@ -306,15 +349,24 @@ extern "C" int flid_token_mix(const float* x, int num_tokens, int channels, cons
     FLID_REQUIRE(num_tokens > 0 && num_tokens <= 64 && hidden > 0 && hidden <= 256 && channels > 0,
                  "flid_token_mix: supports 1..64 tokens and 1..256 hidden units (got %d, %d)", num_tokens, hidden);
     const size_t smem = sizeof(float) * (2 * (size_t)hidden * num_tokens + hidden + 3 * num_tokens);
-    const unsigned blocks = (unsigned)ceil_div(m * channels, 128);
+    int dev = 0, sms = 0;
+    FLID_CUDA(cudaGetDevice(&dev));
+    FLID_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int64_t want = ceil_div(m * channels, 128);
+    const unsigned blocks = (unsigned)(want < (int64_t)sms * 16 ? want : (int64_t)sms * 16);   // weights staged once per CTA
     cudaStream_t st = (cudaStream_t)stream;
-    if (num_tokens <= 32) {
-        if (smem > 48 * 1024) FLID_CUDA(cudaFuncSetAttribute(token_mix_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        token_mix_kernel<32><<<blocks, 128, smem, st>>>(x, num_tokens, channels, ln_w, ln_b, eps, w1, b1, w2, b2, hidden, out, m);
-    } else {
-        if (smem > 48 * 1024) FLID_CUDA(cudaFuncSetAttribute(token_mix_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        token_mix_kernel<64><<<blocks, 128, smem, st>>>(x, num_tokens, channels, ln_w, ln_b, eps, w1, b1, w2, b2, hidden, out, m);
-    }
+#define FLID_TOKEN_MIX(KM, EX)                                                                                                     \
+    do {                                                                                                                           \
+        if (smem > 48 * 1024)                                                                                                      \
+            FLID_CUDA(cudaFuncSetAttribute(token_mix_kernel<KM, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+        token_mix_kernel<KM, EX><<<blocks, 128, smem, st>>>(x, num_tokens, channels, ln_w, ln_b, eps, w1, b1, w2, b2, hidden, out, m); \
+    } while (0)
+    if (num_tokens == 20) FLID_TOKEN_MIX(20, true);        // the reference's default num_neighbors
+    else if (num_tokens == 10) FLID_TOKEN_MIX(10, true);
+    else if (num_tokens == 32) FLID_TOKEN_MIX(32, true);
+    else if (num_tokens <= 32) FLID_TOKEN_MIX(32, false);
+    else FLID_TOKEN_MIX(64, false);
+#undef FLID_TOKEN_MIX
     FLID_LAUNCH_CHECK();
     return FLID_OK;
 }

@@ -47,13 +47,17 @@ class DenseWeights:
             pass
 
 
-def linear(cache: DenseWeights, x, weight, bias=None, *, act=0, resid=None, idx=None, x2=None, idx2=None, rows=None, ldx=None):
+def linear(cache: DenseWeights, x, weight, bias=None, *, act=0, resid=None, idx=None, x2=None, idx2=None, rows=None, ldx=None,
+           out=None):
     """act([x[idx] | x2[idx2]] @ weight.T + bias + resid) as one GEMM launch.  ``x`` / ``x2``: 2-D float32 with unit
     column stride; ``idx`` / ``idx2``: int32 row gathers; ``rows``: number of output rows when no plain segment tells
-    it; ``ldx``: row stride override for ``x`` (e.g. every S-th row of a [m * S, d] matrix)."""
+    it; ``ldx``: row stride override for ``x`` (e.g. every S-th row of a [m * S, d] matrix); ``out``: destination view
+    (unit column stride, any row stride)."""
     m = int(rows if rows is not None else (idx.shape[0] if idx is not None else x.shape[0]))
     n_out = weight.shape[0]
-    out = torch.empty((m, n_out), dtype=torch.float32, device=x.device)
+    if out is None:
+        out = torch.empty((m, n_out), dtype=torch.float32, device=x.device)
+    assert out.shape == (m, n_out) and out.stride(1) == 1
     w0 = x.shape[1]
     w1 = x2.shape[1] if x2 is not None else 0
     assert w0 + w1 == weight.shape[1], (w0, w1, tuple(weight.shape))

@@ -100,21 +100,33 @@ class TCL(nn.Module):
                                                      x.shape[0], _lib.stream()))
         return x
 
-    def _encoder_eval(self, tr, xq, xkv, key_ids, s, q_rows=None):
-        """TransformerEncoder.forward (modules.py:270-312) on [m * S, d] rows; ``xkv is xq``: self-attention."""
+    def _encoder_eval(self, tr, xq, xkv, key_ids, s, first_only=False):
+        """TransformerEncoder.forward (modules.py:270-312) on [m * S, d] rows; ``xkv is xq``: self-attention.
+        ``first_only``: only token 0 of every query sequence is evaluated and returned ([m, d]) -- the last block's
+        cross-attention outputs are read at token 0 alone (TCL.py:153-157), and everything after the attention
+        is per token."""
         mha, d = tr.multi_head_attention, xq.shape[1]
         w_in, b_in, heads = mha.in_proj_weight, mha.in_proj_bias, mha.num_heads
         m = xq.shape[0] // s
+        if first_only:
+            assert xkv is not xq
+            xq = xq.view(m, s * d)[:, :d]                                   # token-0 rows, row stride S * d
+            q = torch.empty((m, s * d), dtype=torch.float32, device=xq.device)[:, :d]
+            dense.linear(self._dense, xq, w_in[:d], b_in[:d], out=q)
+            ctx = torch.empty((m, s * d), dtype=torch.float32, device=xq.device)[:, :d]
+        else:
+            ctx = torch.empty((m * s, d), dtype=torch.float32, device=xq.device)
         if xkv is xq:
             qkv = dense.linear(self._dense, xq, w_in, b_in)
-            q, kk, vv = qkv, qkv[:, d:], qkv[:, 2 * d:]
+            q, kk, vv, ldq = qkv, qkv[:, d:], qkv[:, 2 * d:], 3 * d
         else:
-            q = dense.linear(self._dense, xq, w_in[:d], b_in[:d])
+            if not first_only:
+                q = dense.linear(self._dense, xq, w_in[:d], b_in[:d])
             kv = dense.linear(self._dense, xkv, w_in[d:], b_in[d:])
-            kk, vv = kv, kv[:, d:]
-        ctx = torch.empty((m * s, d), dtype=torch.float32, device=xq.device)
-        _lib.check(_lib.lib().flid_seq_attention(_lib.ptr(q), q.stride(0), _lib.ptr(kk), kk.stride(0), _lib.ptr(vv), vv.stride(0),
-                                                 _lib.ptr(key_ids), s, heads, d // heads, _lib.ptr(ctx), d, s, m, _lib.stream()))
+            kk, vv, ldq = kv, kv[:, d:], d                                  # the strided q / ctx are [m * S, d] with holes
+        _lib.check(_lib.lib().flid_seq_attention(_lib.ptr(q), ldq, _lib.ptr(kk), kk.stride(0), _lib.ptr(vv), vv.stride(0),
+                                                 _lib.ptr(key_ids), s, heads, d // heads, _lib.ptr(ctx), d,
+                                                 1 if first_only else s, m, _lib.stream()))
         y = dense.linear(self._dense, ctx, mha.out_proj.weight, mha.out_proj.bias, resid=xq)
         out = dense.layernorm(y, tr.norm_layers[0], out=y)
         h = dense.linear(self._dense, out, tr.linear_layers[0].weight, tr.linear_layers[0].bias, act=1)
@@ -173,15 +185,15 @@ class TCL(nn.Module):
                     ids_s, ids_d = ids_s.contiguous(), ids_d.contiguous()
                     xs, xd = self._features_eval(ids_s, eid_s, dt_s), self._features_eval(ids_d, eid_d, dt_d)
                     es = ed = None
-                    for transformer in self.transformers:                   # TCL.py:133-151
+                    for li, transformer in enumerate(self.transformers):    # TCL.py:133-151
+                        last = li == len(self.transformers) - 1
                         xs = self._encoder_eval(transformer, xs, xs, ids_s, s)
                         xd = self._encoder_eval(transformer, xd, xd, ids_d, s)
-                        es = self._encoder_eval(transformer, xs, xd, ids_d, s)
-                        ed = self._encoder_eval(transformer, xd, xs, ids_s, s)
+                        es = self._encoder_eval(transformer, xs, xd, ids_d, s, first_only=last)
+                        ed = self._encoder_eval(transformer, xd, xs, ids_s, s, first_only=last)
                         xs, xd = es, ed
-                    w_o, b_o, d = self.output_layer.weight, self.output_layer.bias, self.node_feat_dim
-                    outs_s.append(dense.linear(self._dense, es, w_o, b_o, rows=m, ldx=s * d))   # token 0 of every sequence
-                    outs_d.append(dense.linear(self._dense, ed, w_o, b_o, rows=m, ldx=s * d))
+                    outs_s.append(dense.linear(self._dense, es, self.output_layer.weight, self.output_layer.bias))   # token-0 rows
+                    outs_d.append(dense.linear(self._dense, ed, self.output_layer.weight, self.output_layer.bias))
                     continue
                 xs, xd = self._features(ids_s, eid_s, dt_s), self._features(ids_d, eid_d, dt_d)
                 es = ed = None

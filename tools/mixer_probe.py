@@ -53,6 +53,15 @@ def main():
             res["kernels" if mode == "1" else "torch_modules"] = {"s_per_pass": round(min(vals), 4), "checksum": chk}
         res["speedup"] = round(res["torch_modules"]["s_per_pass"] / res["kernels"]["s_per_pass"], 2)
         out[name] = res
+    if os.environ.get("MIXER_PROFILE"):
+        os.environ["FLID_DENSE"] = "1"
+        from torch.profiler import profile, ProfilerActivity
+        for name, m in models.items():
+            with profile(activities=[ProfilerActivity.CUDA]) as prof, torch.no_grad():
+                m.compute_src_dst_node_temporal_embeddings(src, dst, ts, 20)
+                torch.cuda.synchronize()
+            rows = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)[:12]
+            out[name]["top_kernels_ms"] = [[e.key[:60], e.count, round(e.device_time_total / 1e3, 2)] for e in rows]
     print(json.dumps(out))
 
 
