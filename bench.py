@@ -535,6 +535,12 @@ def run_tgat(b, ci, cfg):
     clock_info = clocks.stop() if rank == 0 else None
     ms_total, ms_e2e = b.max_over_ranks(ms_total, ms_e2e)
 
+    if os.environ.get("FLID_BENCH_TIMELINE") and rank == 0:
+        dump_timeline(lambda: step_device(store), os.environ["FLID_BENCH_TIMELINE"], world)
+    elif os.environ.get("FLID_BENCH_TIMELINE"):
+        step_device(store)      # the other ranks take part in the pass's collectives
+        step_device(store)
+
     # ---- outside the timed region: sharded == single, bit for bit
     same = None
     if world > 1:
@@ -796,6 +802,45 @@ def run_tgn(b, ci, cfg):
                                           "(the reference's own loop shape): same kernels, ~25 launches and one "
                                           "synchronisation per batch"}
     print(json.dumps(line), flush=True)
+
+
+def dump_timeline(step, out_dir, world):
+    """Development aid (FLID_BENCH_TIMELINE=<dir>): one extra pass under torch.profiler after the timed region;
+    writes the device timeline summary of rank 0 -- kernel busy time, span, the idle gaps and what surrounds them."""
+    from torch.profiler import profile, ProfilerActivity
+    step()                      # re-primes the caches keyed by the inputs (the e2e steps used host arrays)
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+        step()
+        torch.cuda.synchronize()
+    ev = [x for x in prof.events() if str(x.device_type).endswith("CUDA") and x.time_range.end > x.time_range.start]
+    ev.sort(key=lambda x: x.time_range.start)
+    if not ev:
+        return
+    t0, t1 = ev[0].time_range.start, max(x.time_range.end for x in ev)
+    busy, cur_end, gaps = 0.0, t0, []
+    for i, x in enumerate(ev):
+        a, z = x.time_range.start, x.time_range.end
+        if a > cur_end:
+            if a - cur_end >= 15.0:
+                gaps.append([round(a - cur_end, 1), round(cur_end - t0, 1), ev[i - 1].name[:48], x.name[:48]])
+            busy += z - a
+            cur_end = z
+        elif z > cur_end:
+            busy += z - cur_end
+            cur_end = z
+    by = {}
+    for x in ev:
+        k = x.name[:60]
+        by[k] = [by.get(k, [0, 0])[0] + 1, by.get(k, [0, 0])[1] + (x.time_range.end - x.time_range.start)]
+    top = sorted(([k, v[0], round(v[1], 1)] for k, v in by.items()), key=lambda r: -r[2])
+    os.makedirs(out_dir, exist_ok=True)
+    with open(os.path.join(out_dir, f"timeline_N{world}.json"), "w") as f:
+        json.dump({"span_us": round(t1 - t0, 1), "busy_us": round(busy, 1), "kernels": len(ev),
+                   "gaps_ge_15us": sorted(gaps, key=lambda r: -r[0])[:60], "gap_total_us": round(sum(r[0] for r in gaps), 1),
+                   "by_kernel_us": top[:70],
+                   "sequence": [[round(x.time_range.start - t0, 1), round(x.time_range.end - x.time_range.start, 1), x.name[:44]]
+                                for x in ev]}, f, indent=0)
 
 
 def run_scaling(b, ci, cfg):

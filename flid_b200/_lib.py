@@ -83,6 +83,8 @@ _SIGNATURES = {
     "flid_tgat_set_chunk_targets": (C.c_int, [c_void, C.c_int64]),
     "flid_tgat_set_numeric_mode": (C.c_int, [c_void, C.c_int]),
     "flid_tgat_set_ln_fold": (C.c_int, [c_void, C.c_int]),
+    "flid_tgat_set_sort_queries": (C.c_int, [c_void, C.c_int]),
+    "flid_tgat_set_wait_event": (C.c_int, [c_void, c_void]),
     "flid_tgat_bulk_invalidate": (C.c_int, [c_void]),
     "flid_tgat_memo_build_owner_range": (C.c_int, [c_void, c_void, c_void, c_void, C.c_int, C.c_int, c_void, C.c_int64,
                                                    C.c_int64, C.c_int, c_void, c_void]),

@@ -7,6 +7,8 @@
 // position belongs to rank s are written to the same row of rank s's table.  Every row has exactly one producer, so
 // there are no write conflicts; the caller separates the exchange from its consumers with a cross-rank barrier.
 #include "common.cuh"
+#include <stdlib.h>
+
 #include "graph.cuh"
 
 namespace flid {
@@ -18,20 +20,56 @@ struct PeerArgs {
     int world, rank;
 };
 
-// one warp per work item q of this rank's range; 16-byte copies
-__global__ void __launch_bounds__(256) memo_exchange_kernel(const int32_t* __restrict__ mirror, const float* __restrict__ local,
+// A persistent grid of small CTAs (one 128-thread CTA per SM): each warp walks over groups of XR consecutive work items
+// of this rank's range, 16-byte copies.  All loads of a group are issued before its first remote store (2 * XR float4
+// in flight per lane): the stores are posted writes over NVLink, the local gather is what needs the memory-level
+// parallelism.  The grid is kept this small on purpose -- the kernel runs on a side stream beside the next call's
+// query-side GEMM (448 threads, ~48 K registers, most of the shared memory per SM) and must fit next to it.
+constexpr int XR = 8;
+__global__ void __launch_bounds__(128) memo_exchange_kernel(const int32_t* __restrict__ mirror, const float* __restrict__ local,
                                                             PeerArgs a, int64_t item_lo, int64_t n, int row4) {
     const int lane = threadIdx.x & 31;
-    const int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    if (w >= n) return;
-    const int64_t p = __ldg(mirror + item_lo + w);
-    int dest = 0;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t w0 = ((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5) * XR; w0 < n; w0 += warps * XR) {
+        int64_t p[XR];
+        int dest[XR];
+#pragma unroll
+        for (int i = 0; i < XR; ++i) {
+            dest[i] = a.rank;
+            p[i] = 0;
+            if (w0 + i < n) {
+                p[i] = __ldg(mirror + item_lo + w0 + i);
+                int d = 0;
 #pragma unroll 1
-    for (int r = 1; r < a.world; ++r) dest += (p >= a.bound[r]);
-    if (dest == a.rank) return;
-    const float4* src = reinterpret_cast<const float4*>(local) + p * row4;
-    float4* dst = reinterpret_cast<float4*>(a.table[dest]) + p * row4;
-    for (int c = lane; c < row4; c += 32) dst[c] = src[c];
+                for (int r = 1; r < a.world; ++r) d += (p[i] >= a.bound[r]);
+                dest[i] = d;
+            }
+        }
+        if (row4 <= 64) {
+            float4 v[XR][2];
+#pragma unroll
+            for (int i = 0; i < XR; ++i) {
+                if (dest[i] == a.rank) continue;
+                const float4* src = reinterpret_cast<const float4*>(local) + p[i] * row4;
+                if (lane < row4) v[i][0] = __ldg(src + lane);
+                if (lane + 32 < row4) v[i][1] = __ldg(src + lane + 32);
+            }
+#pragma unroll
+            for (int i = 0; i < XR; ++i) {
+                if (dest[i] == a.rank) continue;
+                float4* dst = reinterpret_cast<float4*>(a.table[dest[i]]) + p[i] * row4;
+                if (lane < row4) dst[lane] = v[i][0];
+                if (lane + 32 < row4) dst[lane + 32] = v[i][1];
+            }
+            continue;
+        }
+        for (int i = 0; i < XR; ++i) {
+            if (dest[i] == a.rank) continue;
+            const float4* src = reinterpret_cast<const float4*>(local) + p[i] * row4;
+            float4* dst = reinterpret_cast<float4*>(a.table[dest[i]]) + p[i] * row4;
+            for (int c = lane; c < row4; c += 32) dst[c] = src[c];
+        }
+    }
 }
 
 }  // namespace flid
@@ -93,8 +131,16 @@ int flid_memo_exchange_p2p(const flid_graph* g, const float* table_local, void* 
     for (int r = 0; r <= world; ++r) a.bound[r] = pos_bounds_host[r];
     const int64_t lo = a.bound[rank], n = a.bound[rank + 1] - lo;
     if (n <= 0 || world == 1) return FLID_OK;
-    memo_exchange_kernel<<<(unsigned)ceil_div(n * 32, 256), 256, 0, (cudaStream_t)stream>>>(g->mirror, table_local, a, lo, n,
-                                                                                           row_dim / 4);
+    static int sms = 0, per_sm = 1;
+    if (sms == 0) {
+        int dev = 0;
+        FLID_CUDA(cudaGetDevice(&dev));
+        FLID_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        if (const char* e = getenv("FLID_XCHG_CTAS")) per_sm = atoi(e) > 0 ? atoi(e) : 1;   // development knob
+    }
+    const int64_t want = ceil_div(ceil_div(n, XR) * 32, 128);
+    const unsigned grid = (unsigned)(want < (int64_t)sms * per_sm ? want : (int64_t)sms * per_sm);
+    memo_exchange_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(g->mirror, table_local, a, lo, n, row_dim / 4);
     FLID_LAUNCH_CHECK();
     return FLID_OK;
 }

@@ -551,6 +551,10 @@ static int layer_eval(flid_tgat* m, int layer, const LayerCall& c, const float* 
         a.u_base = U, a.u_index = nullptr;
     }
     {
+        if (layer > 1 && m->wait_event) {   // memo rows produced by other ranks: their exchange ran beside the query fold
+            FLID_CUDA(cudaStreamWaitEvent(st, m->wait_event, 0));
+            m->wait_event = nullptr;
+        }
         ProfScope prof(m, PROF_ATTN, st);
         FLID_TRY(launch_attn(a, m->H, st));
     }
@@ -817,6 +821,11 @@ void flid_tgat_free(flid_tgat* m) {
                             &m->ws_a, &m->ws_hd, &m->ws_misc, &m->ws_rid, &m->ws_rt, &m->ws_bad, &m->ws_pos, &m->ws_self, &m->ws_sort,
                             &m->tgn_ids, &m->tgn_times, &m->tgn_eids, &m->tgn_gi, &m->tgn_gh, &m->ws_win, &m->tgn_out, &m->tgn_ctr};
     flid::tc_free_weight(&m->tc_gih), flid::tc_free_weight(&m->tc_ghh);
+    for (int i = 0; i < flid_tgat::PREP_STREAMS; ++i) {
+        if (m->prep_stream[i]) cudaStreamDestroy(m->prep_stream[i]);
+        if (m->prep_join[i]) cudaEventDestroy(m->prep_join[i]);
+    }
+    if (m->prep_fork) cudaEventDestroy(m->prep_fork);
     if (m->tgn_stream) cudaStreamDestroy(m->tgn_stream);
     if (m->tgn_ev) cudaEventDestroy(m->tgn_ev);
     for (auto* b : bufs) b->release();
@@ -838,7 +847,31 @@ int flid_tgat_set_weights(flid_tgat* m, const float* time_w, const float* time_b
     // python: head_dim ** -0.5 is a float64; multiplying a float32 tensor by it uses its float32 value
     // the stream kernel evaluates softmax with exp2, so log2(e) is folded into the scale here
     const double scale = (double)(float)pow((double)m->hd, -0.5) * 1.4426950408889634074;
-    for (int l = 0; l < m->L; ++l) {
+    // Three independent chains per layer (query fold, output fold, MergeLayer weights), each a handful of small
+    // launches: they run side by side on the prep streams (an E-step pass follows an M-step, so this upload is part
+    // of every pass; serialised it is ~0.4 ms of 4-70 us kernels), joined back into `st` at the end.
+    constexpr int NS = flid_tgat::PREP_STREAMS;
+    static const bool multi = [] {
+        const char* e = getenv("FLID_PREP_STREAMS");
+        return !(e && e[0] == '0');
+    }();
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    FLID_CUDA(cudaStreamIsCapturing(st, &cap));
+    const bool fork = multi && cap == cudaStreamCaptureStatusNone;
+    if (fork) {
+        if (!m->prep_fork) {
+            FLID_CUDA(cudaEventCreateWithFlags(&m->prep_fork, cudaEventDisableTiming));
+            for (int i = 0; i < NS; ++i) {
+                FLID_CUDA(cudaStreamCreateWithFlags(&m->prep_stream[i], cudaStreamNonBlocking));
+                FLID_CUDA(cudaEventCreateWithFlags(&m->prep_join[i], cudaEventDisableTiming));
+            }
+        }
+        FLID_CUDA(cudaEventRecord(m->prep_fork, st));
+        for (int i = 0; i < NS; ++i) FLID_CUDA(cudaStreamWaitEvent(m->prep_stream[i], m->prep_fork, 0));
+    }
+    auto chain = [&](int l, int j) { return fork ? m->prep_stream[(3 * l + j) % NS] : st; };
+    const int64_t tot = (int64_t)zw * qd;
+    for (int l = 0; l < m->L; ++l) {   // the two long kernels of every layer first: they run while the host enqueues the rest
         const flid_tgat_layer_weights& w = layers_host[l];
         LayerDev& d = m->layers[l];
         FLID_REQUIRE(w.query_w && w.key_w && w.value_w && w.ln_w && w.ln_b && w.res_w && w.res_b && w.fc1_w &&
@@ -847,34 +880,47 @@ int flid_tgat_set_weights(flid_tgat* m, const float* time_w, const float* time_b
         if (!d.mfoldT) FLID_CUDA(cudaMalloc((void**)&d.mfoldT, sizeof(float) * (size_t)zw * qd));
         if (!d.wvoT) FLID_CUDA(cudaMalloc((void**)&d.wvoT, sizeof(float) * (size_t)zw * qd));
         if (!d.u0) FLID_CUDA(cudaMalloc((void**)&d.u0, sizeof(float) * zw));
-        const int64_t tot = (int64_t)zw * qd;
-        fold_qk_kernel<<<(unsigned)ceil_div(tot, 256), 256, 0, st>>>(w.query_w, w.key_w, qd, kd, H, scale, d.mfoldT);
+        fold_vo_kernel<<<(unsigned)ceil_div(tot, 256), 256, 0, chain(l, 1)>>>(w.res_w, w.value_w, qd, kd, H, d.wvoT);
         FLID_LAUNCH_CHECK();
-        fold_vo_kernel<<<(unsigned)ceil_div(tot, 256), 256, 0, st>>>(w.res_w, w.value_w, qd, kd, H, d.wvoT);
+        fold_qk_kernel<<<(unsigned)ceil_div(tot, 256), 256, 0, chain(l, 0)>>>(w.query_w, w.key_w, qd, kd, H, scale, d.mfoldT);
         FLID_LAUNCH_CHECK();
-        u0_kernel<<<(unsigned)ceil_div(zw, 128), 128, 0, st>>>(d.mfoldT, m->te0, zw, qd, dn, T, d.u0);
+    }
+    for (int l = 0; l < m->L; ++l) {
+        const flid_tgat_layer_weights& w = layers_host[l];
+        LayerDev& d = m->layers[l];
+        cudaStream_t sq = chain(l, 0), so = chain(l, 1), sm = chain(l, 2);
+        // chain 1: query fold -> u0 -> its tiled image
+        u0_kernel<<<(unsigned)ceil_div(zw, 128), 128, 0, sq>>>(d.mfoldT, m->te0, zw, qd, dn, T, d.u0);
         FLID_LAUNCH_CHECK();
-        FLID_TRY(dev_copy(&d.res_b, w.res_b, qd, st));
-        FLID_TRY(dev_copy(&d.ln_w, w.ln_w, qd, st));
-        FLID_TRY(dev_copy(&d.ln_b, w.ln_b, qd, st));
-        FLID_TRY(dev_copy(&d.fc1_w, w.fc1_w, (size_t)dn * (qd + dn), st));
-        FLID_TRY(dev_copy(&d.fc1_b, w.fc1_b, dn, st));
-        FLID_TRY(dev_copy(&d.fc2_w, w.fc2_w, (size_t)dn * dn, st));
-        FLID_TRY(dev_copy(&d.fc2_b, w.fc2_b, dn, st));
-        FLID_TRY(tc_prepare_weight(d.mfoldT, qd, zw, dn, &d.tc_q, st, m->numeric));
-        FLID_TRY(tc_prepare_weight(d.wvoT, zw, qd, zw, &d.tc_o, st, m->numeric));
-        FLID_TRY(tc_prepare_weight(d.fc1_w, qd + dn, dn, qd + dn, &d.tc_f1, st, m->numeric));
-        FLID_TRY(tc_prepare_weight(d.fc2_w, dn, dn, dn, &d.tc_f2, st, m->numeric));
-        FLID_TRY(kv_fold_layer(m, l, w.query_w, w.key_w, w.value_w, w.res_w, st));
+        FLID_TRY(tc_prepare_weight(d.mfoldT, qd, zw, dn, &d.tc_q, sq, m->numeric));
+        // chain 2: output fold -> its tiled image
+        FLID_TRY(dev_copy(&d.res_b, w.res_b, qd, so));
+        FLID_TRY(tc_prepare_weight(d.wvoT, zw, qd, zw, &d.tc_o, so, m->numeric));
+        // chain 3: LayerNorm / MergeLayer parameters and their images
+        FLID_TRY(dev_copy(&d.ln_w, w.ln_w, qd, sm));
+        FLID_TRY(dev_copy(&d.ln_b, w.ln_b, qd, sm));
+        FLID_TRY(dev_copy(&d.fc1_w, w.fc1_w, (size_t)dn * (qd + dn), sm));
+        FLID_TRY(dev_copy(&d.fc1_b, w.fc1_b, dn, sm));
+        FLID_TRY(dev_copy(&d.fc2_w, w.fc2_w, (size_t)dn * dn, sm));
+        FLID_TRY(dev_copy(&d.fc2_b, w.fc2_b, dn, sm));
+        FLID_TRY(tc_prepare_weight(d.fc1_w, qd + dn, dn, qd + dn, &d.tc_f1, sm, m->numeric));
+        FLID_TRY(tc_prepare_weight(d.fc2_w, dn, dn, dn, &d.tc_f2, sm, m->numeric));
+        FLID_TRY(kv_fold_layer(m, l, w.query_w, w.key_w, w.value_w, w.res_w, sm));
         if (m->use_tc && qd % 4 == 0 && dn % 4 == 0) {
             if (!d.lnw) {
                 FLID_CUDA(cudaMalloc((void**)&d.lnw, sizeof(float) * ((size_t)dn * qd + 2 * dn)));
                 d.w1g = d.lnw, d.ln_c1 = d.lnw + (size_t)dn * qd, d.ln_c2 = d.ln_c1 + dn;
             }
-            ln_fold_prep_kernel<<<dn, 128, 0, st>>>(d.fc1_w, d.fc1_b, d.ln_w, d.ln_b, dn, qd, d.w1g, d.ln_c1, d.ln_c2);
+            ln_fold_prep_kernel<<<dn, 128, 0, sm>>>(d.fc1_w, d.fc1_b, d.ln_w, d.ln_b, dn, qd, d.w1g, d.ln_c1, d.ln_c2);
             FLID_LAUNCH_CHECK();
-            FLID_TRY(tc_prepare_weight(d.w1g, qd, dn, qd, &d.tc_f1g, st, m->numeric));
-            FLID_TRY(tc_prepare_weight(d.fc1_w + qd, qd + dn, dn, dn, &d.tc_f1n, st, m->numeric));
+            FLID_TRY(tc_prepare_weight(d.w1g, qd, dn, qd, &d.tc_f1g, sm, m->numeric));
+            FLID_TRY(tc_prepare_weight(d.fc1_w + qd, qd + dn, dn, dn, &d.tc_f1n, sm, m->numeric));
+        }
+    }
+    if (fork) {
+        for (int i = 0; i < NS; ++i) {
+            FLID_CUDA(cudaEventRecord(m->prep_join[i], m->prep_stream[i]));
+            FLID_CUDA(cudaStreamWaitEvent(st, m->prep_join[i], 0));
         }
     }
     m->nt_src = nullptr;
@@ -1061,6 +1107,21 @@ int flid_tgat_set_ln_fold(flid_tgat* m, int enable) {
     FLID_REQUIRE(m != nullptr, "flid_tgat_set_ln_fold: null handle");
     if (m->ln_fold != (enable != 0)) m->table_src = nullptr, m->table_rows = 0, m->nt_src = nullptr;  // rebuild with / without the fc1 tables
     m->ln_fold = enable != 0;
+    return FLID_OK;
+}
+
+int flid_tgat_set_wait_event(flid_tgat* m, void* cuda_event) {
+    using namespace flid;
+    FLID_REQUIRE(m != nullptr, "flid_tgat_set_wait_event: null handle");
+    m->wait_event = (cudaEvent_t)cuda_event;
+    return FLID_OK;
+}
+
+int flid_tgat_set_sort_queries(flid_tgat* m, int enable) {
+    using namespace flid;
+    FLID_REQUIRE(m != nullptr, "flid_tgat_set_sort_queries: null handle");
+    const char* so = getenv("FLID_SORT_QUERIES");
+    m->sort_bulk_queries = enable != 0 && !(so && so[0] == '0');
     return FLID_OK;
 }
 

@@ -83,6 +83,13 @@ struct flid_tgat {
     flid::DevBuf tgn_out, tgn_ctr;       // whole-pass driver (flid_tgn_pass): batch embeddings, device batch counter
     flid::TcWeight tc_gih, tc_ghh;       // GRU weights tiled for the tcgen05 GEMM (flid_tgn_rebuild), fp32-grade in both numeric modes
     const float *gru_ih_src = nullptr, *gru_hh_src = nullptr;
+    // set by flid_tgat_set_wait_event: the next attention launch above level 1 (the first reader of exchanged memo
+    // rows) waits for it; consumed once
+    cudaEvent_t wait_event = nullptr;
+    // weight upload: the independent fold / tiling chains of all layers run side by side on these streams
+    static constexpr int PREP_STREAMS = 6;
+    cudaStream_t prep_stream[PREP_STREAMS] = {};
+    cudaEvent_t prep_fork = nullptr, prep_join[PREP_STREAMS] = {};
     cudaStream_t tgn_stream = nullptr;   // capturable stream of the whole-pass driver
     cudaEvent_t tgn_ev = nullptr;
     int64_t stats[4] = {0, 0, 0, 0};

@@ -128,13 +128,18 @@ def _owned_roots(model, src, dst, t, num_neighbors, dist, rank, world):
     lo, hi, _ = shard_bounds(e, rank, world)
     with torch.no_grad(), torch.cuda.device(dev):
         t0 = _mark("start", time.perf_counter()) if _TRACE else 0.0
-        prepare_layer_memo(model, 2 * e, num_neighbors, True)
-        t0 = _mark("memo_build+exchange", t0)
         plan = shard_plan(model._engine, model.neighbor_sampler, dev)
         # Inputs that did not change since the last pass (the E-step embeds the same event list in every EM iteration)
         # keep their routing: it depends on the events and the partition only.  Device tensors are recognised by
         # (pointer, version), host arrays by (pointer, shape) plus a sum / xor fingerprint of this rank's slice; the
-        # ranks agree on a hit with one small all-reduce, since a miss anywhere re-routes everywhere.
+        # ranks agree on a hit with one small all-reduce, since a miss anywhere re-routes everywhere.  The agreement
+        # runs on the hosts (ShardPlan.all_agree) after the memo build has been enqueued, so it overlaps device work.
+        model._engine.overlap_exchange = not _TRACE      # an embedding call follows: it waits for the exchange itself
+        try:
+            prepare_layer_memo(model, 2 * e, num_neighbors, True)
+        finally:
+            model._engine.overlap_exchange = False
+        t0 = _mark("memo_build+exchange", t0)
         if _is_tensor(src):
             key = tuple((x.data_ptr(), x._version, tuple(x.shape), x.dtype) for x in (src, dst, t))
         else:
@@ -143,9 +148,7 @@ def _owned_roots(model, src, dst, t, num_neighbors, dist, rank, world):
                 return (a.ctypes.data, a.shape, a.dtype.str, int(v.sum(dtype=np.uint64)), int(np.bitwise_xor.reduce(v)) if v.size else 0)
             key = tuple(fp(np.asarray(x)) for x in (src, dst, t)) if all(np.asarray(x).dtype.itemsize == 8 for x in (src, dst, t)) else None
         routed = plan.routing.get(key) if key is not None else None
-        flag = torch.tensor([1 if routed is not None else 0], dtype=torch.int32, device=dev)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if int(flag.item()) == 0:
+        if not plan.all_agree(routed is not None, dist):
             routed = None
         if routed is None:
             if _is_tensor(src):
@@ -160,10 +163,14 @@ def _owned_roots(model, src, dst, t, num_neighbors, dist, rank, world):
             t64 = t_loc.to(torch.float64)
             nodes, times, gidx = route_roots(torch.cat([s_loc.to(torch.int64), d_loc.to(torch.int64)]),
                                              torch.cat([t64, t64]), torch.cat([ev, ev + e]), plan.node_inner, world, dist)
-            # source endpoints first (stable): the single-way decoder then reads a prefix instead of a gather
+            # source endpoints first: the single-way decoder then reads a prefix instead of a gather; inside each
+            # half the roots are kept in (node, time) order, the order the bulk kernels want (windows of one node's
+            # adjacency list stay in cache), so the per-pass sort of the embedding call is skipped for them
             is_dst = gidx >= e
-            order = torch.argsort(is_dst, stable=True)
-            nodes, times, gidx = nodes[order], times[order], gidx[order]
+            order = torch.argsort(times, stable=True)
+            order = order[torch.argsort(nodes[order], stable=True)]
+            order = order[torch.argsort(is_dst[order], stable=True)]
+            nodes, times, gidx = nodes[order].contiguous(), times[order].contiguous(), gidx[order].contiguous()
             n_src = int(gidx.numel() - int(is_dst.sum()))
             if is32:
                 times = times.to(torch.float32)       # the recursion's dtype rule follows the caller's dtype
@@ -173,7 +180,11 @@ def _owned_roots(model, src, dst, t, num_neighbors, dist, rank, world):
                 plan.routing[key] = routed
         nodes, times, gidx, n_src = routed
         t0 = _mark("route_roots", t0)
-        emb = model.compute_node_temporal_embeddings(nodes, times, model.num_layers, num_neighbors)
+        model._engine.presorted = True
+        try:
+            emb = model.compute_node_temporal_embeddings(nodes, times, model.num_layers, num_neighbors)
+        finally:
+            model._engine.presorted = False
         t0 = _mark("embed_roots", t0)
     return emb, gidx, n_src
 

@@ -90,7 +90,43 @@ class ShardPlan:
         self.peers = {}       # (slot, rows, dn) -> (table, peer pointers, bounds, keep-alive)
         self.p2p = None if os.environ.get("FLID_P2P", "1") != "0" else False   # None: not tried yet
         self._flag = torch.zeros(1, dtype=torch.int32, device=device)
+        self.flag_dev = torch.zeros(1, dtype=torch.int32, device=device)      # routing-cache agreement (passes._owned_roots)
+        self.flag_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._side = None
+        # host-side control group: one-integer agreements between the ranks that must not touch the GPU queue (the
+        # device is busy with the memo build while the hosts agree).  Collective: every rank builds its plan at the
+        # same point of the pass.
+        self.ctl_group = None
+        if os.environ.get("FLID_CTL_GLOO", "1") != "0":
+            import torch.distributed as dist
+            try:
+                self.ctl_group = dist.new_group(backend="gloo")
+            except Exception:
+                self.ctl_group = None
         del mirror
+
+    def side_stream(self):
+        """Stream for small control collectives that must not queue behind the pass's kernels."""
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.flag_dev.device)
+        return self._side
+
+    def all_agree(self, ok: bool, dist) -> bool:
+        """True when every rank passed ok=True.  Called after the memo build has been enqueued: over the host group
+        the exchange overlaps the device work; without one it is an NCCL all-reduce read back on a side stream."""
+        if self.ctl_group is not None:
+            t = torch.tensor([1 if ok else 0], dtype=torch.int32)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.ctl_group)
+            return int(t[0]) == 1
+        side = self.side_stream()
+        with torch.cuda.stream(side):
+            self.flag_dev.fill_(1 if ok else 0)
+            dist.all_reduce(self.flag_dev, op=dist.ReduceOp.MIN)
+            self.flag_host.copy_(self.flag_dev, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(side)
+        done.synchronize()
+        return int(self.flag_host[0]) == 1
 
     # ---- peer-mapped tables (CUDA IPC): the exchange as one kernel storing into the other ranks' HBM
     def peer_table(self, slot: int, rows: int, dn: int, device, dist):

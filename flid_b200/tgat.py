@@ -113,7 +113,11 @@ class _Engine:
         self.bulk_projection = os.environ.get("FLID_BULK_KV", "0") == "1"
         self.shard_tag = None         # (rank, world) while an owner-partitioned pass is running (flid_b200.passes)
         self.ln_fold = False          # bulk passes fold LayerNorm into fc1 (flid_tgat_set_ln_fold); set by flid_b200.passes
-        self.ln_state = {}            # depth -> value last handed to the C handle
+        self.ln_state = {}
+        self.overlap_exchange = False   # set by passes._owned_roots around the sharded memo build
+        self.pending_exchange = None
+        self.presorted = False     # the caller's bulk roots already arrive in (node, time) order (passes._owned_roots)
+        self.sort_state = {}            # depth -> value last handed to the C handle
         self.shard_plans = {}         # (sampler generation, rank, world) -> shard.ShardPlan
 
     def invalidate(self):
@@ -284,6 +288,17 @@ def build_layer_memo(engine, depth, time_encoder, conv_layers, merge_layers, sam
                     _t0 = _time.perf_counter()
                     plan.exchange_rows_p2p(sampler, ent, dist) if ent is not None else plan.exchange_rows(t, dist)
                     _p._mark("exchange", _t0)
+                elif ent is not None and engine.overlap_exchange and level == depth - 1 and os.environ.get("FLID_XCHG_OVERLAP", "1") != "0":
+                    # last level inside an owner-partitioned pass: exchange + barrier on a side stream; the embedding
+                    # call that follows waits for it before its first read of exchanged rows (flid_tgat_set_wait_event)
+                    side = plan.side_stream()
+                    side.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(side):
+                        plan.exchange_rows_p2p(sampler, ent, dist)
+                        done = torch.cuda.Event()
+                        done.record(side)
+                    _lib.check(lib.flid_tgat_set_wait_event(h, C.c_void_p(done.cuda_event)))
+                    engine.pending_exchange = done          # kept alive until the next one replaces it
                 elif ent is not None:
                     plan.exchange_rows_p2p(sampler, ent, dist)
                 else:
@@ -356,6 +371,10 @@ def embed_roots(engine, depth, time_encoder, conv_layers, merge_layers, sampler,
                                   edge_feat, int(num_neighbors), n)
         if memo is not None:
             tabs = (C.c_void_p * len(memo))(*[t.data_ptr() for t in memo])
+            want_sort = not engine.presorted
+            if engine.sort_state.get(depth, True) != want_sort:
+                _lib.check(_lib.lib().flid_tgat_set_sort_queries(h, 1 if want_sort else 0))
+                engine.sort_state[depth] = want_sort
             _lib.check(_lib.lib().flid_tgat_embed_memo(h, sampler.handle, _lib.ptr(node_feat), _lib.ptr(edge_feat),
                                                        tabs, _lib.ptr(d_nodes), _lib.ptr(d_times), is32, n,
                                                        int(num_neighbors), _lib.ptr(out), _lib.stream()))

@@ -215,6 +215,17 @@ int flid_tgat_set_numeric_mode(flid_tgat* m, int mode);
  * tolerance, not bit-identical to the unfolded path); the switch is per handle so that every chunk of a pass takes
  * the same path whatever its size.  Takes effect at the next flid_tgat_cache_node_table.  Static node tables only. */
 int flid_tgat_set_ln_fold(flid_tgat* m, int enable);
+/* Bulk memoised calls (n >= 8192 roots) evaluate their roots in (node, time) order and scatter the rows back
+ * (default on): consecutive roots then share most of their neighbour window.  A caller whose roots already
+ * arrive in that order (the owner-partitioned pass keeps its routed roots sorted) switches the sort off.
+ * Results do not depend on it.                                                                                 */
+int flid_tgat_set_sort_queries(flid_tgat* m, int enable);
+/* Owner-partitioned passes: the exchange of the last memo level runs on a side stream beside the next call's
+ * sampling and query-side GEMM, which only read rows this rank produced itself.  cuda_event (a cudaEvent_t recorded
+ * on that side stream after the exchange and its cross-rank barrier) is waited for by the next attention launch
+ * above level 1 -- the first reader of rows other ranks produced -- and then forgotten.  The caller keeps the event
+ * alive until then.  NULL clears it.                                                                          */
+int flid_tgat_set_wait_event(flid_tgat* m, void* cuda_event);
 /* upper bound on layer-1 targets processed per internal chunk (workspace ~7 KB per target;
  * default 606208 = 148 x 4096).  Results do not depend on it.                                   */
 int flid_tgat_set_chunk_targets(flid_tgat* m, int64_t max_layer1_targets);
