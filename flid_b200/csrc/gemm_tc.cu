@@ -78,7 +78,7 @@ struct TcShape {
 constexpr int TRACE_Q = 512;
 #define TRACE(role, q) do { if (sh.trace && blockIdx.x == 0 && (q) < TRACE_Q) sh.trace[(role) * TRACE_Q + (q)] = clock64(); } while (0)
 
-template <int MS, bool SINGLE>
+template <int MS, bool SINGLE, bool LATE>   // LATE: residual add / GELU in the store phase of the staged epilogue (dense.cu)
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(TcGemmArgs g, const float4* __restrict__ wbuf, TcShape sh) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar_full[MAX_STAGES], bar_empty[MAX_STAGES], bar_acc_full[2], bar_acc_empty[2];
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(TcGemmArgs g, cons
                             }
                         }
                     } else if (staged) {
-                        const bool late = g.resid != nullptr || g.gelu;   // residual / GELU are applied in the store phase
+                        constexpr bool late = LATE;
 #pragma unroll
                         for (int i = 0; i < 16; i += 4) {
                             float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
@@ -278,11 +278,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(TcGemmArgs g, cons
                         }
                         __syncwarp();
                         if (n0 + sc < sh.N) {
+                            if (!late) {   // the hot path of the TGAT chain: four independent row stores
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                float4 o = *reinterpret_cast<const float4*>(stg + (j * 8 + sr) * EPI_LD + sc);
-                                if (crow4[j] == nullptr) continue;
-                                if (late) {
+                                for (int j = 0; j < 4; ++j) {
+                                    const float4 o = *reinterpret_cast<const float4*>(stg + (j * 8 + sr) * EPI_LD + sc);
+                                    if (crow4[j] != nullptr) *reinterpret_cast<float4*>(crow4[j] + n0 + sc) = o;
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    float4 o = *reinterpret_cast<const float4*>(stg + (j * 8 + sr) * EPI_LD + sc);
+                                    if (crow4[j] == nullptr) continue;
                                     if (g.resid) {
                                         const float4 r = __ldg(reinterpret_cast<const float4*>(g.resid + (row0 + j * 8 + sr) * g.ldr + n0 + sc));
                                         o.x += r.x, o.y += r.y, o.z += r.z, o.w += r.w;
@@ -295,8 +301,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(TcGemmArgs g, cons
                                     } else if (g.relu) {
                                         o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
                                     }
+                                    *reinterpret_cast<float4*>(crow4[j] + n0 + sc) = o;
                                 }
-                                *reinterpret_cast<float4*>(crow4[j] + n0 + sc) = o;
                             }
                         }
                         __syncwarp();
@@ -466,8 +472,9 @@ template <int MS>
 static int launch_ms(const TcGemmArgs& g, const TcWeight& w, TcShape sh, int sm_count, int smem_max, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        FLID_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max - STATIC_SMEM));
-        FLID_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max - STATIC_SMEM));
+        FLID_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MS, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max - STATIC_SMEM));
+        FLID_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MS, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max - STATIC_SMEM));
+        FLID_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max - STATIC_SMEM));
         attr_set = true;
     }
     const size_t stage = (size_t)MS * A_SUB + 2 * (size_t)C4 * w.n_tile * 16;
@@ -485,11 +492,16 @@ static int launch_ms(const TcGemmArgs& g, const TcWeight& w, TcShape sh, int sm_
     const int64_t work = sh.m_groups * sh.n_blocks;
     FLID_REQUIRE(work < (1LL << 31) - 65536, "tc_gemm: too many tiles for one launch (M = %lld)", (long long)g.M);
     const unsigned grid = (unsigned)(work < sm_count ? work : sm_count);
-    if (w.single)
-        gemm_tc_kernel<MS, true><<<grid, NTHREADS, sh.stages * stage + (sh.staged_epilogue ? EPI_BYTES : 0), st>>>(
+    const bool late = g.resid != nullptr || g.gelu;
+    FLID_REQUIRE(!late || !w.single, "tc_gemm: the residual / GELU epilogue is built for the fp32-grade mode only");
+    if (late)
+        gemm_tc_kernel<MS, false, true><<<grid, NTHREADS, sh.stages * stage + (sh.staged_epilogue ? EPI_BYTES : 0), st>>>(
+            g, reinterpret_cast<const float4*>(w.buf), sh);
+    else if (w.single)
+        gemm_tc_kernel<MS, true, false><<<grid, NTHREADS, sh.stages * stage + (sh.staged_epilogue ? EPI_BYTES : 0), st>>>(
             g, reinterpret_cast<const float4*>(w.buf), sh);
     else
-        gemm_tc_kernel<MS, false><<<grid, NTHREADS, sh.stages * stage + (sh.staged_epilogue ? EPI_BYTES : 0), st>>>(
+        gemm_tc_kernel<MS, false, false><<<grid, NTHREADS, sh.stages * stage + (sh.staged_epilogue ? EPI_BYTES : 0), st>>>(
             g, reinterpret_cast<const float4*>(w.buf), sh);
     FLID_LAUNCH_CHECK();
     return FLID_OK;

@@ -59,7 +59,7 @@ struct TsShape {
 // LNF: LayerNorm folded into the product (TcGemmArgs::ln_*): producers add the residual and keep row statistics,
 // the (staged) epilogue rescales.  Row statistics live behind the epilogue staging area: [2 items][2 groups][128 rows].
 constexpr int LN_BYTES = 2 * 2 * 128 * 16;
-template <bool SINGLE, bool LNF>
+template <bool SINGLE, bool LNF, bool LATE>   // LATE: residual add / GELU in the store phase of the staged epilogue (dense.cu)
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_ts_kernel(TcGemmArgs g, const float4* __restrict__ wbuf, TsShape sh) {
     constexpr int MS = 1;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_ts_kernel(TcGemmArgs g, c
                             }
                         }
                     } else if (staged) {
-                        const bool late = g.resid != nullptr || g.gelu;   // residual / GELU are applied in the store phase
+                        constexpr bool late = LATE;
 #pragma unroll
                         for (int i = 0; i < 16; i += 4) {
                             float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
@@ -315,11 +315,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_ts_kernel(TcGemmArgs g, c
                         }
                         __syncwarp();
                         if (n0 + sc < sh.N) {
+                            if (!late) {   // the hot path of the TGAT chain: four independent row stores
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                float4 o = *reinterpret_cast<const float4*>(stg + (j * 8 + sr) * EPI_LD + sc);
-                                if (crow4[j] == nullptr) continue;
-                                if (late) {
+                                for (int j = 0; j < 4; ++j) {
+                                    const float4 o = *reinterpret_cast<const float4*>(stg + (j * 8 + sr) * EPI_LD + sc);
+                                    if (crow4[j] != nullptr) *reinterpret_cast<float4*>(crow4[j] + n0 + sc) = o;
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    float4 o = *reinterpret_cast<const float4*>(stg + (j * 8 + sr) * EPI_LD + sc);
+                                    if (crow4[j] == nullptr) continue;
                                     if (g.resid) {
                                         const float4 r = __ldg(reinterpret_cast<const float4*>(g.resid + (row0 + j * 8 + sr) * g.ldr + n0 + sc));
                                         o.x += r.x, o.y += r.y, o.z += r.z, o.w += r.w;
@@ -332,8 +338,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_ts_kernel(TcGemmArgs g, c
                                     } else if (g.relu) {
                                         o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
                                     }
+                                    *reinterpret_cast<float4*>(crow4[j] + n0 + sc) = o;
                                 }
-                                *reinterpret_cast<float4*>(crow4[j] + n0 + sc) = o;
                             }
                         }
                         __syncwarp();
@@ -428,10 +434,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_ts_kernel(TcGemmArgs g, c
 int tc_gemm_ts(const TcGemmArgs& g, const TcWeight& w, int sm_count, int smem_max, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        FLID_CUDA(cudaFuncSetAttribute(gemm_tc_ts_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max - STATIC_SMEM));
-        FLID_CUDA(cudaFuncSetAttribute(gemm_tc_ts_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max - STATIC_SMEM));
-        FLID_CUDA(cudaFuncSetAttribute(gemm_tc_ts_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max - STATIC_SMEM));
-        FLID_CUDA(cudaFuncSetAttribute(gemm_tc_ts_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max - STATIC_SMEM));
+        FLID_CUDA(cudaFuncSetAttribute(gemm_tc_ts_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max - STATIC_SMEM));
+        FLID_CUDA(cudaFuncSetAttribute(gemm_tc_ts_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max - STATIC_SMEM));
+        FLID_CUDA(cudaFuncSetAttribute(gemm_tc_ts_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max - STATIC_SMEM));
+        FLID_CUDA(cudaFuncSetAttribute(gemm_tc_ts_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max - STATIC_SMEM));
+        FLID_CUDA(cudaFuncSetAttribute(gemm_tc_ts_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max - STATIC_SMEM));
         attr_set = true;
     }
     const bool lnf = g.ln_c1 != nullptr;
@@ -461,15 +468,19 @@ int tc_gemm_ts(const TcGemmArgs& g, const TcWeight& w, int sm_count, int smem_ma
     const unsigned grid = (unsigned)(work < sm_count ? work : sm_count);
     const size_t dyn = sh.stages * stage + tail_bytes;
     const float4* wb = reinterpret_cast<const float4*>(w.buf);
-    if (lnf) {
+    const bool late = g.resid != nullptr || g.gelu;
+    FLID_REQUIRE(!late || (!w.single && !lnf), "tc_gemm_ts: the residual / GELU epilogue is built for the plain fp32-grade product only");
+    if (late) {
+        gemm_tc_ts_kernel<false, false, true><<<grid, NTHREADS, dyn, st>>>(g, wb, sh);
+    } else if (lnf) {
         if (w.single)
-            gemm_tc_ts_kernel<true, true><<<grid, NTHREADS, dyn, st>>>(g, wb, sh);
+            gemm_tc_ts_kernel<true, true, false><<<grid, NTHREADS, dyn, st>>>(g, wb, sh);
         else
-            gemm_tc_ts_kernel<false, true><<<grid, NTHREADS, dyn, st>>>(g, wb, sh);
+            gemm_tc_ts_kernel<false, true, false><<<grid, NTHREADS, dyn, st>>>(g, wb, sh);
     } else if (w.single) {
-        gemm_tc_ts_kernel<true, false><<<grid, NTHREADS, dyn, st>>>(g, wb, sh);
+        gemm_tc_ts_kernel<true, false, false><<<grid, NTHREADS, dyn, st>>>(g, wb, sh);
     } else {
-        gemm_tc_ts_kernel<false, false><<<grid, NTHREADS, dyn, st>>>(g, wb, sh);
+        gemm_tc_ts_kernel<false, false, false><<<grid, NTHREADS, dyn, st>>>(g, wb, sh);
     }
     FLID_LAUNCH_CHECK();
     return FLID_OK;
