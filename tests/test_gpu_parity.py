@@ -6,6 +6,7 @@ Tolerances (BASELINE.json north_star): sampler bit-exact; fp32 embeddings rel 1e
 here as three checks: every element within 2e-5 of the tensor's scale (max(1, max|want|)),
 every significant element (|want| >= 0.1 * scale) within 1e-4 relative, and a mean absolute
 error below 2e-6 of the scale; pseudo-label masks identical."""
+import ctypes
 import os
 
 import numpy as np
@@ -1080,3 +1081,42 @@ def test_tgn_pass_graph_equals_per_batch_calls():
                 assert torch.equal(x, y), mode
     with pytest.raises(AssertionError, match="time in the past"):
         m.embed_pass(src[:400], dst[:400], ts[:400], eid[:400], 200, 10)      # the bank is already at the end of the stream
+
+
+def test_bulk_sort_knob_and_wait_event_do_not_change_bits():
+    """flid_tgat_set_sort_queries (the owner-partitioned pass hands its roots over already in (node, time) order and
+    switches the per-call sort off) and flid_tgat_set_wait_event (the exchange of the last memo level on a side
+    stream) change the schedule, not the results: same bits for sorted, unsorted and pre-sorted root lists."""
+    g = synth.wikipedia_shape(seed=4, scale=0.08)
+    src, dst, eid, ts, nf, ef = (g.src_node_ids, g.dst_node_ids, g.edge_ids, g.node_interact_times,
+                                 g.node_raw_features, g.edge_raw_features)
+    L, k = 2, 10
+    p = otgat.default_params(172, 172, 100, L, 2, seed=21, time_bias_scale=0.25)
+    m, s = tgat_pair(nf, ef, src, dst, eid, ts, L, 2, p, memo=True)
+    nodes = np.concatenate([src, dst])
+    times = np.concatenate([ts, ts])
+    assert len(nodes) >= 8192                                  # the bulk branch that sorts its roots
+    with torch.no_grad():
+        base = m.compute_node_temporal_embeddings(nodes, times, L, k)
+        m._engine.presorted = True                             # what passes._owned_roots sets around its call
+        try:
+            unsorted = m.compute_node_temporal_embeddings(nodes, times, L, k)
+            order = np.lexsort((times, nodes))
+            pre = m.compute_node_temporal_embeddings(nodes[order], times[order], L, k)
+        finally:
+            m._engine.presorted = False
+        again = m.compute_node_temporal_embeddings(nodes, times, L, k)
+    assert torch.equal(base, unsorted) and torch.equal(base, again)
+    assert torch.equal(base[torch.from_numpy(order).to(base.device)], pre)
+    # an event recorded on a side stream after some unrelated work: the call waits for it and forgets it
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        junk = torch.randn(1 << 22, device=DEV).sin_()
+        ev = torch.cuda.Event()
+        ev.record(side)
+    h = m._engine.handles[L]
+    _lib.check(_lib.lib().flid_tgat_set_wait_event(h, ctypes.c_void_p(ev.cuda_event)))
+    with torch.no_grad():
+        waited = m.compute_node_temporal_embeddings(nodes, times, L, k)
+    assert ev.query() and torch.equal(base, waited)
+    del junk
