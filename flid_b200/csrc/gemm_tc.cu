@@ -40,11 +40,21 @@ namespace flid {
 // ---------------------------------------------------------------- weight tiling
 // image layout: [n_block][k_chunk][half][c4][n_tile] float4
 // element (n, k) of the logical weight is W[n * sn + k * sk]: (ldw, 1) for W[N, K], (1, ldw) for a stored W^T[K, N]
-__global__ void tc_prep_kernel(const float* __restrict__ W, int64_t sn, int64_t sk, int N, int K, int n_tile,
-                               int n_blocks, int k_chunks, int single, float4* __restrict__ out) {
-    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const int64_t total = (int64_t)n_blocks * k_chunks * 2 * C4 * n_tile;
-    if (idx >= total) return;
+// Both images of a weight (the wide tiles and the 32-column tiles of small launches) are written by one launch:
+// elements [0, total0) belong to image 0, the rest to image 1.
+struct TcPrepImage {
+    float4* out;
+    int n_tile, n_blocks;
+    int64_t total;
+};
+__global__ void tc_prep_kernel(const float* __restrict__ W, int64_t sn, int64_t sk, int N, int K, int k_chunks, int single,
+                               TcPrepImage im0, TcPrepImage im1) {
+    int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= im0.total + im1.total) return;
+    const bool second = idx >= im0.total;
+    if (second) idx -= im0.total;
+    const int n_tile = second ? im1.n_tile : im0.n_tile;
+    float4* out = second ? im1.out : im0.out;
     int64_t r = idx;
     const int nl = (int)(r % n_tile);
     r /= n_tile;
@@ -430,10 +440,8 @@ static int prepare_weight(const float* W, int64_t sn, int64_t sk, int N, int K, 
     }
     w->N = N, w->K = K, w->n_tile = n_tile, w->n_blocks = n_blocks, w->k_chunks = k_chunks, w->single = single;
     if (!w->buf) FLID_CUDA(cudaMalloc((void**)&w->buf, w->bytes()));
-    const int64_t total = (int64_t)n_blocks * k_chunks * 2 * C4 * n_tile;
-    tc_prep_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(W, sn, sk, N, K, n_tile, n_blocks, k_chunks, single,
-                                                                  reinterpret_cast<float4*>(w->buf));
-    FLID_LAUNCH_CHECK();
+    TcPrepImage im0{reinterpret_cast<float4*>(w->buf), n_tile, n_blocks, (int64_t)n_blocks * k_chunks * 2 * C4 * n_tile};
+    TcPrepImage im1{nullptr, 1, 0, 0};
     // companion image for small launches
     const int st_tile = 32, st_blocks = (N + st_tile - 1) / st_tile;
     if (n_tile > st_tile) {
@@ -445,12 +453,12 @@ static int prepare_weight(const float* W, int64_t sn, int64_t sk, int N, int K, 
         const int64_t stotal = (int64_t)st_blocks * k_chunks * 2 * C4 * st_tile;
         if (!w->small_buf) FLID_CUDA(cudaMalloc((void**)&w->small_buf, (size_t)stotal * 16));
         w->small_tile = st_tile, w->small_blocks = st_blocks;
-        tc_prep_kernel<<<(unsigned)ceil_div(stotal, 256), 256, 0, st>>>(W, sn, sk, N, K, st_tile, st_blocks, k_chunks, single,
-                                                                       reinterpret_cast<float4*>(w->small_buf));
-        FLID_LAUNCH_CHECK();
+        im1 = TcPrepImage{reinterpret_cast<float4*>(w->small_buf), st_tile, st_blocks, stotal};
     } else {
         w->small_tile = 0, w->small_blocks = 0;
     }
+    tc_prep_kernel<<<(unsigned)ceil_div(im0.total + im1.total, 256), 256, 0, st>>>(W, sn, sk, N, K, k_chunks, single, im0, im1);
+    FLID_LAUNCH_CHECK();
     return FLID_OK;
 }
 

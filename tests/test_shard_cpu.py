@@ -115,7 +115,10 @@ def _worker(rank, world, port, q):
         full = passes._scatter_all_reduce(vals, g_own, 2 * e, dist)
         ok_full = np.array_equal(full[:, 0].numpy(), all_nodes.astype(np.float32)) and \
             np.array_equal(full[:, 1].numpy(), all_t.astype(np.float32))
-        q.put((rank, ok_rows, ok_route, ok_full))
+        # routing-cache agreement over the host control group: a hit only when every rank has one
+        plan.ctl_group = dist.new_group(backend="gloo")
+        ok_agree = plan.all_agree(True, dist) and not plan.all_agree(rank == 0, dist) and not plan.all_agree(False, dist)
+        q.put((rank, ok_rows, ok_route, ok_full and ok_agree))
     finally:
         dist.destroy_process_group()
 
