@@ -33,6 +33,9 @@ class DenseWeights:
             ent[1] = weight._version
         return ent[0]
 
+    def __deepcopy__(self, memo):
+        return DenseWeights()         # handles belong to one module instance; the copy re-tiles on first use
+
     def clear(self):
         if self._h and torch.cuda.is_available():
             torch.cuda.synchronize()

@@ -68,6 +68,9 @@ class NeighborSampler:
         _lib.check(lib.flid_graph_info(self._handle, C.byref(n), C.byref(m), C.byref(d)))
         self.num_nodes, self.num_entries, self.max_degree = n.value, m.value, d.value
 
+    def __deepcopy__(self, memo):
+        return self                   # the device CSR is immutable: copies of a model share it
+
     def __del__(self):
         try:
             if getattr(self, "_handle", None) is not None and self._handle.value:

@@ -120,6 +120,13 @@ class _Engine:
         self.sort_state = {}            # depth -> value last handed to the C handle
         self.shard_plans = {}         # (sampler generation, rank, world) -> shard.ShardPlan
 
+    def __deepcopy__(self, memo):
+        """copy.deepcopy(model): the copy gets its own (empty) engine -- C handles and device caches are rebuilt on its
+        first call; they are never shared between module instances."""
+        new = _Engine(*self.dims)
+        new.memo_mode, new.bulk_projection = self.memo_mode, self.bulk_projection
+        return new
+
     def invalidate(self):
         """Forget the uploaded weights, the cached node table and the layer memo.  Needed after writes that
         autograd's version counter does not see (``param.data.copy_()``, ``.data`` mutation, feature tables
@@ -259,6 +266,10 @@ def build_layer_memo(engine, depth, time_encoder, conv_layers, merge_layers, sam
         if have is not None and have[0] == key:
             return have[1]
         engine.memo.pop(depth, None)
+        if engine.pending_exchange is not None:          # a side-stream exchange nobody waited for (no layer-2 call followed)
+            torch.cuda.current_stream().wait_event(engine.pending_exchange)
+            _lib.check(lib.flid_tgat_set_wait_event(h, None))
+            engine.pending_exchange = None
         _lib.check(lib.flid_tgat_bulk_invalidate(h))     # new memo contents: the projected per-entry tables follow
         rows = sampler.num_entries + 1
         dn = node_feat.shape[1]
