@@ -136,7 +136,9 @@ class GraphMixer(nn.Module):
                     dt = c_t.to(torch.float32)[:, None] - ts
                 else:                             # float64 minus float32 in float64, then .float()
                     dt = (c_t[:, None] - ts.to(torch.float64)).to(torch.float32)
-                fast = dense.fast_path(self) and m > 0
+                # the forward-only kernels cover up to 64 tokens / 256 token-mixing hidden units; wider mixers keep the modules
+                fast = (dense.fast_path(self) and m > 0 and k <= 64
+                        and all(mx.token_feedforward.ffn[0].weight.shape[0] <= 256 for mx in self.mlp_mixers))
                 if fast:
                     link = self._link_encoder_eval(dt, nbr, m, k)
                 else:

@@ -180,7 +180,10 @@ class TCL(nn.Module):
                 hi = lo + self.chunk_events
                 ids_s, eid_s, dt_s = self._sequences(d_src[lo:hi], d_t[lo:hi], f32, k)
                 ids_d, eid_d, dt_d = self._sequences(d_dst[lo:hi], d_t[lo:hi], f32, k)
-                if dense.fast_path(self) and ids_s.shape[0] > 0:
+                seq, d_model = ids_s.shape[1], self.node_feat_dim
+                # one CTA holds the Q, K, V rows of a sequence in shared memory (csrc/dense.cu); longer sequences keep the modules
+                fits = 4 * (3 * seq * (d_model + 1) + self.num_heads * seq * (seq + 1) + seq) <= 200 * 1024 and d_model % 4 == 0
+                if dense.fast_path(self) and ids_s.shape[0] > 0 and fits:
                     m, s = ids_s.shape
                     ids_s, ids_d = ids_s.contiguous(), ids_d.contiguous()
                     xs, xd = self._features_eval(ids_s, eid_s, dt_s), self._features_eval(ids_d, eid_d, dt_d)
