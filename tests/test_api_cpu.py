@@ -26,3 +26,15 @@ def test_models_survive_deepcopy_without_sharing_native_state():
             assert c._engine is not m._engine and c._engine.handles == {} and c._engine.dims == m._engine.dims
         if hasattr(m, "_dense"):
             assert isinstance(c._dense, DenseWeights) and c._dense is not m._dense and c._dense._h == {}
+
+
+def test_bench_reads_the_round2_traffic_capture():
+    """bench.py's roofline.traffic comes from the committed ncu --set full capture of the final kernels."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    per_eval, source = bench.measured_traffic_per_eval()
+    assert 4000.0 < per_eval < 12000.0 and "round-2" in source and "r2_final_attention_pass" in source
